@@ -1,0 +1,201 @@
+/* tvg_b200.h -- C ABI of the B200-native two-view geometry hot path.
+ *
+ * Drop-in boundary for the path  match_points -> fit_essential_matrix -> extract_Rt -> triangulate ->
+ * check_points  of OpenWork's MonocularSlam/slam.py (/root/reference/MonocularSlam/slam.py:125-237).
+ * The reference has no FFI of its own: its boundary is the Python function surface plus three
+ * third-party calls (cv2.BFMatcher.knnMatch, skimage.measure.ransac, numpy.linalg.svd).  Each entry
+ * point below names the reference call it replaces.  INTEGRATION.md shows the ctypes binding.
+ *
+ * Conventions
+ *   - plain pointers and sizes; every array pointer is a DEVICE pointer unless the name says host;
+ *   - arrays carry a leading pair ("batch") dimension with stride n_max rows; per-pair valid counts
+ *     are int32 device arrays so a whole batch runs with no host synchronisation;
+ *   - calls are asynchronous on `stream` (a cudaStream_t passed as void*; NULL = default stream);
+ *   - return 0 on success, <0 for a validation error, >0 for a cudaError_t; tvg_last_error() returns
+ *     a thread-local message; there is NO CPU fallback anywhere behind this ABI;
+ *   - descriptor / keypoint pointers must be 16-byte aligned (TMA bulk copies, 128-bit loads).
+ *   - layouts are the reference's: des u8[N][32] C-contiguous, kps f64[N][2] pixel (x,y),
+ *     pose / Rt f64[4][4] row-major, E f64[3][3] row-major, points4d f64[N][4] = (x,y,z,1).
+ */
+#ifndef TVG_B200_H
+#define TVG_B200_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#define TVG_API __attribute__((visibility("default")))
+#else
+#define TVG_API
+#endif
+
+typedef struct tvg_ctx tvg_ctx;
+
+/* Context = device + grow-only scratch arena (closest precedent in the reference repo, off-path:
+ * CreateSession / ReleaseSession, sort/src/sort.h:34-43). One context per host thread / stream. */
+TVG_API int tvg_ctx_create(tvg_ctx** out, int device);
+TVG_API void tvg_ctx_destroy(tvg_ctx* ctx);
+TVG_API const char* tvg_last_error(void);
+TVG_API int tvg_abi_version(void);
+/* Number of CUDA kernels this library has launched through `ctx` since creation (bench.py: gpu_launches). */
+TVG_API long long tvg_launch_count(const tvg_ctx* ctx);
+/* Matcher tuning: queries per thread r in {2,4,8}, popcount variant 0 = 8xPOPC, 1 = Harley-Seal 4xPOPC,
+ * 2 = 5xPOPC; ctas_per_sm sizes the split-Nt grid.  Results are bit-identical for every setting. */
+TVG_API int tvg_set_matcher_config(tvg_ctx* ctx, int r, int variant, int ctas_per_sm);
+
+/* cv2.BFMatcher(cv2.NORM_HAMMING).knnMatch(q, t, k=2)  (slam.py:126-127) + the Lowe ratio flag
+ * m.distance < ratio * n.distance (slam.py:131).
+ * Pair b matches query frame (pair_q ? pair_q[b] : b) of the pool q_des[frames][n_max][32] against train
+ * frame (pair_t ? pair_t[b] : b) of t_des.  q_count / t_count: valid rows per FRAME (NULL -> nq / nt).
+ * Outputs idx, dist int32[batch][n_max][2] (-1 where fewer than k train rows exist), keep u8[batch][n_max]
+ * (may be NULL).  Ties break to the lowest train index: bit-exact with OpenCV. */
+TVG_API int tvg_knn2_hamming256(tvg_ctx* ctx, const uint8_t* q_des, const uint8_t* t_des, int batch, int n_max,
+                        int nq, int nt, const int32_t* pair_q, const int32_t* pair_t,
+                        const int32_t* q_count, const int32_t* t_count, double ratio, int32_t* idx,
+                        int32_t* dist, uint8_t* keep, void* stream);
+
+/* The ratio loop + gathers of match_points (slam.py:130-141) and the two normalize(K, .) calls of
+ * fit_essential_matrix (slam.py:151-152; normalize at :87-92).  Emits the surviving (queryIdx, trainIdx)
+ * in ascending query order, their count, and (when keypoint pools are given) the K-normalised
+ * correspondences: src = LAST (train) side, dst = CURR (query) side, f64[batch][n_max][2] each,
+ * plus an fp32 copy corr32 float4[batch][n_max] = (src.x, src.y, dst.x, dst.y) for scoring.
+ * kinv = inv(K) row-major 3x3 (HOST pointer, 9 doubles). kps/src/dst/corr32 may all be NULL. */
+TVG_API int tvg_ratio_compact(tvg_ctx* ctx, const uint8_t* keep, const int32_t* idx, int batch, int n_max, int nq,
+                      const int32_t* pair_q, const int32_t* pair_t, const int32_t* q_count,
+                      const double* kps_q, const double* kps_t, const double* kinv_host, int32_t* qidx,
+                      int32_t* tidx, int32_t* m_count, double* src, double* dst, float* corr32,
+                      void* stream);
+
+/* skimage.measure.ransac((src, dst), EssentialMatrixTransform, min_samples=8, residual_threshold=thr,
+ * max_trials=H)  (slam.py:155-159), driven by a host-supplied sample table: either explicit indices
+ * samples int32[H][8] or random words u32[H][8] mapped on device by idx = (w*M)>>32 with in-row clashes
+ * bumped +1 mod M.  sample_stride = elements between pairs (0: one table shared by the batch).
+ * All outputs are optional (NULL -> internal scratch):
+ *   E f64[batch][9] (refit on the inliers), mask u8[batch][n_max] (PRE-refit best model's inliers),
+ *   n_inl, best int32[batch], E_best f64[batch][9], counts int32[batch][H] (-1 = failed fit; exact fp64
+ *   count for the finalists, fp32 count otherwise), sse32 f32[batch][H], models f64[batch][H][9],
+ *   Rt f64[batch][16] (extract_Rt of the refit E), status int32[batch] (0 ok, 1: M <= 8, 2: no model),
+ *   inl_idx int32[batch][n_max] (match indices of the inliers), samples_out int32[batch][H][8].
+ * Optional inlier gather for triangulation: when qidx/tidx and pixel keypoint pools are given,
+ *   pix_last / pix_curr f64[batch][n_max][2] receive frame.last_kps / frame.curr_kps after the
+ *   inlier filter of slam.py:161-162. */
+typedef struct tvg_ransac_io {
+    const double* src;
+    const double* dst;
+    const float* corr32;
+    const int32_t* m_count; /* NULL -> m */
+    int batch, n_max, m, H;
+    const int32_t* samples;
+    const uint32_t* words;
+    long long sample_stride;
+    double thr;
+    /* optional gather inputs */
+    const int32_t* qidx;
+    const int32_t* tidx;
+    const int32_t* pair_q;
+    const int32_t* pair_t;
+    const double* kps_q;
+    const double* kps_t;
+    /* outputs (all optional) */
+    double* E;
+    uint8_t* mask;
+    int32_t* n_inl;
+    int32_t* best;
+    double* E_best;
+    int32_t* counts;
+    float* sse32;
+    double* models;
+    double* Rt;
+    int32_t* status;
+    int32_t* inl_idx;
+    int32_t* samples_out;
+    double* pix_last;
+    double* pix_curr;
+    int32_t* band;      /* fp32 uncertainty-band count per hypothesis */
+    int32_t* n_cand;    /* finalists re-scored in fp64 */
+} tvg_ransac_io;
+TVG_API int tvg_ransac_essential(tvg_ctx* ctx, const tvg_ransac_io* io, void* stream);
+
+/* extract_Rt(E)  (slam.py:167-186): E f64[batch][9] -> Rt f64[batch][16]. */
+TVG_API int tvg_extract_rt(tvg_ctx* ctx, const double* E, int batch, double* Rt, void* stream);
+
+/* frame.curr_pose = np.dot(Rt, frame.last_pose)  (slam.py:261) chained over sequences.
+ * Pairs of sequence s are b in [seq_off[s], seq_off[s+1]); poses f64[batch + nseq][16]: the pose of
+ * pair b's LAST frame sits at row b + s, its CURR frame at row b + s + 1.
+ * init_pose f64[nseq][16] (NULL -> identity, slam.py:247).  pair_pinv f64[batch][2][16] (may be NULL)
+ * receives np.linalg.inv(last_pose), np.linalg.inv(curr_pose) per pair -- what triangulate needs. */
+TVG_API int tvg_pose_chain(tvg_ctx* ctx, const double* Rt, const int32_t* seq_off, int nseq,
+                   const double* init_pose, double* poses, double* pair_pinv, void* stream);
+
+/* triangulate(pts1, pts2, pose1, pose2) (slam.py:202-221) + check_points (slam.py:233-237).
+ * pix1 / pix2 f64[batch][n_max][2] pixels; P1 / P2 = inv(pose1) / inv(pose2), one 4x4 per pair at
+ * strides p1_stride / p2_stride doubles; n_pts int32[batch] (NULL -> n); kinv_host = inv(K).
+ * points4d f64[batch][n_max][4], good u8[batch][n_max] (z > 0; may be NULL). */
+TVG_API int tvg_triangulate(tvg_ctx* ctx, const double* pix1, const double* pix2, int batch, int n_max, int n,
+                    const int32_t* n_pts, const double* P1, long long p1_stride, const double* P2,
+                    long long p2_stride, const double* kinv_host, double* points4d, uint8_t* good,
+                    void* stream);
+
+/* Cheirality vote over the four (R, +-t) decompositions of E (north-star extra; the reference uses the
+ * trace / t_z heuristics of slam.py:174-181 instead).  votes int32[batch][4], Rts f64[batch][4][16],
+ * choice int32[batch].  mask may be NULL. */
+TVG_API int tvg_cheirality(tvg_ctx* ctx, const double* E, const double* src, const double* dst, const uint8_t* mask,
+                   const int32_t* m_count, int batch, int n_max, int m, int32_t* votes, double* Rts,
+                   int32_t* choice, void* stream);
+
+/* The `else` branch of process_frame (slam.py:249-266) for a batch of frame pairs, device resident,
+ * no host synchronisation: match -> ratio/compact -> RANSAC -> extract_Rt -> pose chain ->
+ * triangulate -> z>0.  Frame pools: des u8[frames][n_max][32], kps f64[frames][n_max][2],
+ * frame_count int32[frames] (NULL -> all n_max rows valid).  Pair b: curr = pair_q[b], last = pair_t[b]
+ * (NULL -> curr = b + 1 + s, last = b + s for sequence s, i.e. consecutive frames of each sequence).
+ * Outputs are optional (NULL -> scratch). */
+typedef struct tvg_pairs_io {
+    const uint8_t* des;
+    const double* kps;
+    const int32_t* frame_count;
+    const int32_t* pair_q;
+    const int32_t* pair_t;
+    int batch, n_max, H;
+    const int32_t* seq_off;   /* int32[nseq+1]; NULL -> one sequence holding all pairs */
+    int nseq;
+    const double* init_pose;  /* f64[nseq][16] or NULL */
+    const uint32_t* words;    /* u32[.][H][8] */
+    const int32_t* samples;   /* int32[.][H][8] (alternative to words) */
+    long long sample_stride;
+    double kinv[9];
+    double ratio, thr;
+    /* outputs */
+    int32_t* idx;       /* [batch][n_max][2] */
+    int32_t* dist;      /* [batch][n_max][2] */
+    int32_t* qidx;      /* [batch][n_max] */
+    int32_t* tidx;      /* [batch][n_max] */
+    int32_t* m_count;   /* [batch] */
+    double* E;          /* [batch][9] */
+    double* E_best;     /* [batch][9] */
+    int32_t* best;      /* [batch] */
+    int32_t* counts;    /* [batch][H] */
+    uint8_t* mask;      /* [batch][n_max] */
+    int32_t* n_inl;     /* [batch] */
+    int32_t* inl_idx;   /* [batch][n_max] */
+    double* Rt;         /* [batch][16] */
+    double* poses;      /* [batch + nseq][16] */
+    double* points4d;   /* [batch][n_max][4] */
+    uint8_t* good;      /* [batch][n_max] */
+    int32_t* status;    /* [batch] */
+} tvg_pairs_io;
+TVG_API int tvg_pairs_device(tvg_ctx* ctx, const tvg_pairs_io* io, void* stream);
+
+/* Same pipeline behind HOST buffers (what a numpy caller hands over): copies the frame pools and the
+ * sample words host->device, runs tvg_pairs_device, copies the per-pair results device->host and
+ * synchronises.  Every pointer in `io` is a HOST pointer here (pinned memory makes the copies async).
+ * bytes_h2d / bytes_d2h (may be NULL) receive the bytes moved. */
+TVG_API int tvg_pairs_host(tvg_ctx* ctx, const tvg_pairs_io* io, int frames, long long* bytes_h2d,
+                   long long* bytes_d2h, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TVG_B200_H */

@@ -1,0 +1,129 @@
+"""ctypes binding of ``libtvg_b200.so`` (C ABI: ``include/tvg_b200.h``).
+
+There is no fallback: if the library is missing or no B200 is visible the import / context creation
+raises.  PyTorch is used only for device memory and streams; signatures carry plain pointers.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "_lib", "libtvg_b200.so")
+
+c_i32p = C.POINTER(C.c_int32)
+c_u32p = C.POINTER(C.c_uint32)
+c_u8p = C.POINTER(C.c_uint8)
+c_f64p = C.POINTER(C.c_double)
+c_f32p = C.POINTER(C.c_float)
+c_vp = C.c_void_p
+
+
+class RansacIO(C.Structure):
+    """tvg_ransac_io"""
+    _fields_ = [
+        ("src", c_vp), ("dst", c_vp), ("corr32", c_vp), ("m_count", c_vp),
+        ("batch", C.c_int), ("n_max", C.c_int), ("m", C.c_int), ("H", C.c_int),
+        ("samples", c_vp), ("words", c_vp), ("sample_stride", C.c_longlong), ("thr", C.c_double),
+        ("qidx", c_vp), ("tidx", c_vp), ("pair_q", c_vp), ("pair_t", c_vp), ("kps_q", c_vp), ("kps_t", c_vp),
+        ("E", c_vp), ("mask", c_vp), ("n_inl", c_vp), ("best", c_vp), ("E_best", c_vp), ("counts", c_vp),
+        ("sse32", c_vp), ("models", c_vp), ("Rt", c_vp), ("status", c_vp), ("inl_idx", c_vp),
+        ("samples_out", c_vp), ("pix_last", c_vp), ("pix_curr", c_vp), ("band", c_vp), ("n_cand", c_vp),
+    ]
+
+
+class PairsIO(C.Structure):
+    """tvg_pairs_io"""
+    _fields_ = [
+        ("des", c_vp), ("kps", c_vp), ("frame_count", c_vp), ("pair_q", c_vp), ("pair_t", c_vp),
+        ("batch", C.c_int), ("n_max", C.c_int), ("H", C.c_int),
+        ("seq_off", c_vp), ("nseq", C.c_int), ("init_pose", c_vp), ("words", c_vp), ("samples", c_vp),
+        ("sample_stride", C.c_longlong), ("kinv", C.c_double * 9), ("ratio", C.c_double), ("thr", C.c_double),
+        ("idx", c_vp), ("dist", c_vp), ("qidx", c_vp), ("tidx", c_vp), ("m_count", c_vp), ("E", c_vp),
+        ("E_best", c_vp), ("best", c_vp), ("counts", c_vp), ("mask", c_vp), ("n_inl", c_vp), ("inl_idx", c_vp),
+        ("Rt", c_vp), ("poses", c_vp), ("points4d", c_vp), ("good", c_vp), ("status", c_vp),
+    ]
+
+
+# name -> (restype, argtypes); also the list tests check against include/tvg_b200.h
+SIGNATURES = {
+    "tvg_ctx_create": (C.c_int, [C.POINTER(c_vp), C.c_int]),
+    "tvg_ctx_destroy": (None, [c_vp]),
+    "tvg_last_error": (C.c_char_p, []),
+    "tvg_abi_version": (C.c_int, []),
+    "tvg_launch_count": (C.c_longlong, [c_vp]),
+    "tvg_set_matcher_config": (C.c_int, [c_vp, C.c_int, C.c_int, C.c_int]),
+    "tvg_knn2_hamming256": (C.c_int, [c_vp, c_vp, c_vp, C.c_int, C.c_int, C.c_int, C.c_int, c_vp, c_vp, c_vp,
+                                      c_vp, C.c_double, c_vp, c_vp, c_vp, c_vp]),
+    "tvg_ratio_compact": (C.c_int, [c_vp, c_vp, c_vp, C.c_int, C.c_int, C.c_int, c_vp, c_vp, c_vp, c_vp, c_vp,
+                                    c_f64p, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
+    "tvg_ransac_essential": (C.c_int, [c_vp, C.POINTER(RansacIO), c_vp]),
+    "tvg_extract_rt": (C.c_int, [c_vp, c_vp, C.c_int, c_vp, c_vp]),
+    "tvg_pose_chain": (C.c_int, [c_vp, c_vp, c_vp, C.c_int, c_vp, c_vp, c_vp, c_vp]),
+    "tvg_triangulate": (C.c_int, [c_vp, c_vp, c_vp, C.c_int, C.c_int, C.c_int, c_vp, c_vp, C.c_longlong, c_vp,
+                                  C.c_longlong, c_f64p, c_vp, c_vp, c_vp]),
+    "tvg_cheirality": (C.c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, C.c_int, C.c_int, C.c_int, c_vp, c_vp,
+                                 c_vp, c_vp]),
+    "tvg_pairs_device": (C.c_int, [c_vp, C.POINTER(PairsIO), c_vp]),
+    "tvg_pairs_host": (C.c_int, [c_vp, C.POINTER(PairsIO), C.c_int, C.POINTER(C.c_longlong),
+                                 C.POINTER(C.c_longlong), c_vp]),
+}
+
+_lib = None
+
+
+class TvgError(RuntimeError):
+    pass
+
+
+def load():
+    """dlopen the library (no GPU needed for this step). Raises if it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.isfile(LIB_PATH):
+        raise ImportError(
+            "openwork_b200: %s is missing -- build it with `python -m openwork_b200.build` "
+            "(or __graft_entry__.build()). There is no CPU fallback." % LIB_PATH)
+    lib = C.CDLL(LIB_PATH)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+def check(rc, what):
+    if rc != 0:
+        msg = load().tvg_last_error()
+        raise TvgError("%s failed (code %d): %s" % (what, rc, msg.decode() if msg else "?"))
+
+
+class Context:
+    """One tvg_ctx (device + scratch arena). Not thread-safe; use one per stream."""
+
+    def __init__(self, device=0):
+        self.lib = load()
+        h = c_vp()
+        check(self.lib.tvg_ctx_create(C.byref(h), int(device)), "tvg_ctx_create")
+        self.handle = h
+        self.device = int(device)
+
+    def close(self):
+        if getattr(self, "handle", None):
+            self.lib.tvg_ctx_destroy(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @property
+    def launches(self):
+        return int(self.lib.tvg_launch_count(self.handle))
+
+    def set_matcher_config(self, r=4, variant=0, ctas_per_sm=6):
+        check(self.lib.tvg_set_matcher_config(self.handle, r, variant, ctas_per_sm), "tvg_set_matcher_config")

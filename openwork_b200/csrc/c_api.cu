@@ -1,0 +1,519 @@
+// C ABI (include/tvg_b200.h) over the sm_100a kernels.  No CPU compute path exists here: every entry
+// point launches CUDA kernels or fails with an error code.
+#include <cuda_runtime.h>
+
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/tvg_b200.h"
+#include "tvg_common.cuh"
+#include "tvg_kernels.h"
+
+namespace {
+
+thread_local std::string g_err;
+
+int fail(int code, const std::string& msg) {
+    g_err = msg;
+    return code;
+}
+int cuda_fail(cudaError_t e, const char* where) {
+    g_err = std::string(where) + ": " + cudaGetErrorString(e);
+    return (int)e > 0 ? (int)e : 1;
+}
+#define TVG_CUDA(x)                                   \
+    do {                                              \
+        cudaError_t e__ = (x);                        \
+        if (e__ != cudaSuccess) return cuda_fail(e__, #x); \
+    } while (0)
+
+enum Slot {
+    S_PARTIAL, S_COUNTERS, S_IDX, S_DIST, S_KEEP, S_QIDX, S_TIDX, S_MCOUNT, S_SRC, S_DST, S_CORR32,
+    S_E64, S_E32, S_VALID, S_PARTCNT, S_PARTSSE, S_COUNTS, S_BAND, S_SSE32, S_CAND, S_NCAND, S_CANDSSE,
+    S_CANDCNT, S_BEST, S_BESTSSE, S_EBEST, S_MASK, S_NINL, S_INLIDX, S_PIXLAST, S_PIXCURR, S_E, S_RT,
+    S_STATUS, S_POSES, S_POSESINV, S_POINTS, S_GOOD, S_PAIRQ, S_PAIRT, S_SEQOFF, S_VOTES, S_RTS, S_CHOICE,
+    // host-entry staging
+    S_H_DES, S_H_KPS, S_H_FCOUNT, S_H_PAIRQ, S_H_PAIRT, S_H_SEQOFF, S_H_INIT, S_H_WORDS, S_H_SAMPLES,
+    S_NUM
+};
+
+}  // namespace
+
+struct tvg_ctx {
+    int device = 0;
+    int sm_count = 148;
+    int knn_r = 4, knn_variant = 0, knn_ctas_per_sm = 6;
+    long long launches = 0;
+    void* slot[S_NUM] = {};
+    size_t slot_bytes[S_NUM] = {};
+
+    // grow-only scratch; zero_on_grow for buffers the kernels expect zeroed (tile counters)
+    int get(Slot s, size_t bytes, void** out, bool zero_on_grow = false) {
+        if (bytes == 0) bytes = 16;
+        if (slot_bytes[s] < bytes) {
+            if (slot[s]) {
+                cudaError_t e = cudaDeviceSynchronize();
+                if (e != cudaSuccess) return cuda_fail(e, "cudaDeviceSynchronize");
+                cudaFree(slot[s]);
+                slot[s] = nullptr;
+                slot_bytes[s] = 0;
+            }
+            const size_t want = bytes + bytes / 4 + 256;
+            cudaError_t e = cudaMalloc(&slot[s], want);
+            if (e != cudaSuccess) return cuda_fail(e, "cudaMalloc(scratch)");
+            if (zero_on_grow) {
+                e = cudaMemset(slot[s], 0, want);
+                if (e != cudaSuccess) return cuda_fail(e, "cudaMemset(scratch)");
+            }
+            slot_bytes[s] = want;
+        }
+        *out = slot[s];
+        return 0;
+    }
+};
+
+#define TVG_GET(ctx, s, bytes, ptr, type)                              \
+    do {                                                               \
+        void* v__ = nullptr;                                           \
+        int rc__ = (ctx)->get(s, (bytes), &v__);                       \
+        if (rc__) return rc__;                                         \
+        ptr = reinterpret_cast<type>(v__);                             \
+    } while (0)
+// output pointer if the caller gave one, scratch otherwise
+#define TVG_OUT(ctx, user, s, bytes, ptr, type)                        \
+    do {                                                               \
+        if (user) ptr = reinterpret_cast<type>(user);                  \
+        else TVG_GET(ctx, s, bytes, ptr, type);                        \
+    } while (0)
+
+namespace {
+
+bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+struct DeviceGuard {
+    int prev = -1;
+    explicit DeviceGuard(int dev) {
+        cudaGetDevice(&prev);
+        if (prev != dev) cudaSetDevice(dev);
+        else prev = -1;
+    }
+    ~DeviceGuard() {
+        if (prev >= 0) cudaSetDevice(prev);
+    }
+};
+
+__global__ void make_pairs_kernel(const int32_t* seq_off, int nseq, int batch, int32_t* pair_q, int32_t* pair_t) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= batch) return;
+    int s = 0;
+    while (s + 1 < nseq && b >= seq_off[s + 1]) ++s;
+    pair_t[b] = b + s;      // last frame of the pair
+    pair_q[b] = b + s + 1;  // current frame
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* tvg_last_error(void) { return g_err.c_str(); }
+int tvg_abi_version(void) { return 1; }
+
+int tvg_ctx_create(tvg_ctx** out, int device) {
+    if (!out) return fail(-1, "tvg_ctx_create: out is NULL");
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaGetDeviceCount (no CUDA device: this library has no CPU path)");
+    if (device < 0 || device >= n) return fail(-2, "tvg_ctx_create: bad device ordinal");
+    cudaDeviceProp prop;
+    TVG_CUDA(cudaGetDeviceProperties(&prop, device));
+    if (prop.major < 10) return fail(-3, "tvg_ctx_create: sm_100a (Blackwell B200) required");
+    tvg_ctx* c = new tvg_ctx();
+    c->device = device;
+    c->sm_count = prop.multiProcessorCount;
+    *out = c;
+    return 0;
+}
+
+void tvg_ctx_destroy(tvg_ctx* ctx) {
+    if (!ctx) return;
+    DeviceGuard g(ctx->device);
+    cudaDeviceSynchronize();
+    for (int i = 0; i < S_NUM; ++i)
+        if (ctx->slot[i]) cudaFree(ctx->slot[i]);
+    delete ctx;
+}
+
+long long tvg_launch_count(const tvg_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+int tvg_set_matcher_config(tvg_ctx* ctx, int r, int variant, int ctas_per_sm) {
+    if (!ctx) return fail(-1, "ctx is NULL");
+    if (!(r == 2 || r == 4 || r == 8) || variant < 0 || variant > 2 || ctas_per_sm < 1 || ctas_per_sm > 16)
+        return fail(-2, "tvg_set_matcher_config: r in {2,4,8}, variant in {0,1,2}, ctas_per_sm in [1,16]");
+    ctx->knn_r = r;
+    ctx->knn_variant = variant;
+    ctx->knn_ctas_per_sm = ctas_per_sm;
+    return 0;
+}
+
+int tvg_knn2_hamming256(tvg_ctx* ctx, const uint8_t* q_des, const uint8_t* t_des, int batch, int n_max,
+                        int nq, int nt, const int32_t* pair_q, const int32_t* pair_t,
+                        const int32_t* q_count, const int32_t* t_count, double ratio, int32_t* idx,
+                        int32_t* dist, uint8_t* keep, void* stream) {
+    if (!ctx) return fail(-1, "ctx is NULL");
+    if (batch < 0 || n_max < 0 || nq < 0 || nt < 0 || nq > n_max || nt > n_max)
+        return fail(-2, "tvg_knn2_hamming256: bad sizes");
+    if (n_max >= (1 << TVG_KEY_SHIFT)) return fail(-2, "tvg_knn2_hamming256: n_max must be < 2^23");
+    if (batch == 0 || n_max == 0) return 0;
+    if (!q_des || !t_des || !idx || !dist) return fail(-3, "tvg_knn2_hamming256: NULL array");
+    if (!aligned16(q_des) || !aligned16(t_des)) return fail(-4, "tvg_knn2_hamming256: descriptors must be 16-byte aligned");
+    DeviceGuard g(ctx->device);
+    tvg::KnnParams p{};
+    p.q_base = q_des; p.t_base = t_des; p.pair_q = pair_q; p.pair_t = pair_t;
+    p.q_count = q_count; p.t_count = t_count;
+    p.n_max = n_max; p.nq = nq; p.nt = nt;
+    p.idx = idx; p.dist = dist; p.keep = keep; p.ratio = ratio;
+    const int bq = tvg::knn2_block_queries(ctx->knn_r);
+    const int qtiles = (n_max + bq - 1) / bq;
+    const long long slots = (long long)ctx->sm_count * ctx->knn_ctas_per_sm;
+    const long long base = (long long)qtiles * batch;
+    int splits = (int)(slots / base);
+    const int max_splits = (n_max + 63) / 64;
+    if (splits > max_splits) splits = max_splits;
+    if (splits < 1) splits = 1;
+    p.splits = splits;
+    p.rows_per_split = (n_max + splits - 1) / splits;
+    if (splits > 1) {
+        TVG_GET(ctx, S_PARTIAL, (size_t)batch * n_max * splits * sizeof(uint2), p.partial, uint2*);
+        void* v = nullptr;
+        int rc = ctx->get(S_COUNTERS, (size_t)batch * qtiles * sizeof(unsigned int), &v, true);
+        if (rc) return rc;
+        p.tile_counters = reinterpret_cast<unsigned int*>(v);
+    }
+    TVG_CUDA(tvg::launch_knn2(p, batch, ctx->knn_r, ctx->knn_variant, (cudaStream_t)stream));
+    ctx->launches += 1;
+    return 0;
+}
+
+int tvg_ratio_compact(tvg_ctx* ctx, const uint8_t* keep, const int32_t* idx, int batch, int n_max, int nq,
+                      const int32_t* pair_q, const int32_t* pair_t, const int32_t* q_count,
+                      const double* kps_q, const double* kps_t, const double* kinv_host, int32_t* qidx,
+                      int32_t* tidx, int32_t* m_count, double* src, double* dst, float* corr32,
+                      void* stream) {
+    if (!ctx) return fail(-1, "ctx is NULL");
+    if (batch < 0 || n_max < 0 || nq < 0 || nq > n_max) return fail(-2, "tvg_ratio_compact: bad sizes");
+    if (batch == 0) return 0;
+    if (!keep || !idx || !qidx || !tidx || !m_count) return fail(-3, "tvg_ratio_compact: NULL array");
+    const bool gather = kps_q || kps_t;
+    if (gather && (!kps_q || !kps_t || !kinv_host || !src || !dst || !corr32))
+        return fail(-3, "tvg_ratio_compact: gather needs kps_q, kps_t, kinv, src, dst, corr32");
+    DeviceGuard g(ctx->device);
+    tvg::CompactParams p{};
+    p.keep = keep; p.idx = idx; p.pair_q = pair_q; p.pair_t = pair_t; p.q_count = q_count;
+    p.n_max = n_max; p.nq = nq;
+    p.kps_q = gather ? kps_q : nullptr; p.kps_t = gather ? kps_t : nullptr;
+    if (gather) memcpy(p.kinv, kinv_host, sizeof(p.kinv));
+    p.qidx = qidx; p.tidx = tidx; p.m_count = m_count; p.src = src; p.dst = dst;
+    p.corr32 = reinterpret_cast<float4*>(corr32);
+    TVG_CUDA(tvg::launch_compact(p, batch, (cudaStream_t)stream));
+    ctx->launches += 1;
+    return 0;
+}
+
+int tvg_ransac_essential(tvg_ctx* ctx, const tvg_ransac_io* io, void* stream) {
+    if (!ctx || !io) return fail(-1, "ctx / io is NULL");
+    if (io->batch < 0 || io->n_max <= 0 || io->H <= 0 || io->m < 0 || io->m > io->n_max)
+        return fail(-2, "tvg_ransac_essential: bad sizes");
+    if (io->batch == 0) return 0;
+    if (!io->src || !io->dst || !io->corr32) return fail(-3, "tvg_ransac_essential: NULL correspondences");
+    if (!io->samples && !io->words) return fail(-3, "tvg_ransac_essential: need samples or words");
+    if (!(io->thr > 0.0)) return fail(-2, "tvg_ransac_essential: residual threshold must be > 0");
+    if (!aligned16(io->src) || !aligned16(io->dst) || !aligned16(io->corr32))
+        return fail(-4, "tvg_ransac_essential: correspondences must be 16-byte aligned");
+    DeviceGuard g(ctx->device);
+    const size_t B = (size_t)io->batch, N = (size_t)io->n_max, H = (size_t)io->H;
+    tvg::RansacParams p{};
+    p.src = io->src; p.dst = io->dst; p.corr32 = reinterpret_cast<const float4*>(io->corr32);
+    p.m_count = io->m_count; p.n_max = io->n_max; p.m = io->m; p.H = io->H;
+    p.samples = io->samples; p.words = io->samples ? nullptr : io->words;
+    p.sample_stride = io->sample_stride; p.samples_out = io->samples_out;
+    p.thr = io->thr;
+    p.band_rel = 2e-3f;  // |num^2 - thr^2 den| <= band_rel * thr^2 den  <=>  |r - thr| <~ 1e-3 thr = 5e-6
+    p.chunk = tvg::ransac_score_chunk_rows();
+    p.chunks = (io->n_max + p.chunk - 1) / p.chunk;
+    TVG_OUT(ctx, io->models, S_E64, B * H * 9 * sizeof(double), p.E64, double*);
+    TVG_GET(ctx, S_E32, B * H * 9 * sizeof(float), p.E32, float*);
+    TVG_GET(ctx, S_VALID, B * H * sizeof(int32_t), p.valid, int32_t*);
+    TVG_GET(ctx, S_PARTCNT, B * p.chunks * H * sizeof(int2), p.part_cnt, int2*);
+    TVG_GET(ctx, S_PARTSSE, B * p.chunks * H * sizeof(float), p.part_sse, float*);
+    TVG_OUT(ctx, io->counts, S_COUNTS, B * H * sizeof(int32_t), p.counts, int32_t*);
+    TVG_OUT(ctx, io->band, S_BAND, B * H * sizeof(int32_t), p.band, int32_t*);
+    TVG_OUT(ctx, io->sse32, S_SSE32, B * H * sizeof(float), p.sse32, float*);
+    TVG_GET(ctx, S_CAND, B * H * sizeof(int32_t), p.cand, int32_t*);
+    TVG_OUT(ctx, io->n_cand, S_NCAND, B * sizeof(int32_t), p.n_cand, int32_t*);
+    TVG_GET(ctx, S_CANDSSE, B * H * sizeof(double), p.cand_sse, double*);
+    TVG_GET(ctx, S_CANDCNT, B * H * sizeof(int32_t), p.cand_cnt, int32_t*);
+    p.qidx = io->qidx; p.tidx = io->tidx; p.pair_q = io->pair_q; p.pair_t = io->pair_t;
+    const bool gather = io->kps_q && io->kps_t && io->qidx && io->tidx;
+    p.kps_q = gather ? io->kps_q : nullptr; p.kps_t = gather ? io->kps_t : nullptr;
+    TVG_OUT(ctx, io->best, S_BEST, B * sizeof(int32_t), p.best, int32_t*);
+    TVG_GET(ctx, S_BESTSSE, B * sizeof(double), p.best_sse, double*);
+    TVG_OUT(ctx, io->E_best, S_EBEST, B * 9 * sizeof(double), p.E_best, double*);
+    TVG_OUT(ctx, io->mask, S_MASK, B * N, p.mask, uint8_t*);
+    TVG_OUT(ctx, io->n_inl, S_NINL, B * sizeof(int32_t), p.n_inl, int32_t*);
+    TVG_OUT(ctx, io->inl_idx, S_INLIDX, B * N * sizeof(int32_t), p.inl_idx, int32_t*);
+    TVG_OUT(ctx, io->pix_last, S_PIXLAST, B * N * 2 * sizeof(double), p.pix_last, double*);
+    TVG_OUT(ctx, io->pix_curr, S_PIXCURR, B * N * 2 * sizeof(double), p.pix_curr, double*);
+    TVG_OUT(ctx, io->E, S_E, B * 9 * sizeof(double), p.E, double*);
+    TVG_OUT(ctx, io->Rt, S_RT, B * 16 * sizeof(double), p.Rt, double*);
+    TVG_OUT(ctx, io->status, S_STATUS, B * sizeof(int32_t), p.status, int32_t*);
+    cudaStream_t st = (cudaStream_t)stream;
+    TVG_CUDA(tvg::launch_ransac_fit(p, io->batch, st));
+    TVG_CUDA(tvg::launch_ransac_score(p, io->batch, st));
+    TVG_CUDA(tvg::launch_ransac_reduce(p, io->batch, st));
+    TVG_CUDA(tvg::launch_ransac_rescore(p, io->batch, st));
+    TVG_CUDA(tvg::launch_ransac_refit(p, io->batch, st));
+    ctx->launches += 5;
+    return 0;
+}
+
+int tvg_extract_rt(tvg_ctx* ctx, const double* E, int batch, double* Rt, void* stream) {
+    if (!ctx) return fail(-1, "ctx is NULL");
+    if (batch < 0) return fail(-2, "tvg_extract_rt: bad batch");
+    if (batch == 0) return 0;
+    if (!E || !Rt) return fail(-3, "tvg_extract_rt: NULL array");
+    DeviceGuard g(ctx->device);
+    tvg::ExtractRtParams p{E, Rt};
+    TVG_CUDA(tvg::launch_extract_rt(p, batch, (cudaStream_t)stream));
+    ctx->launches += 1;
+    return 0;
+}
+
+int tvg_pose_chain(tvg_ctx* ctx, const double* Rt, const int32_t* seq_off, int nseq,
+                   const double* init_pose, double* poses, double* pair_pinv, void* stream) {
+    if (!ctx) return fail(-1, "ctx is NULL");
+    if (nseq < 0) return fail(-2, "tvg_pose_chain: bad nseq");
+    if (nseq == 0) return 0;
+    if (!Rt || !seq_off || !poses) return fail(-3, "tvg_pose_chain: NULL array");
+    DeviceGuard g(ctx->device);
+    tvg::PoseChainParams p{Rt, seq_off, init_pose, poses, pair_pinv};
+    TVG_CUDA(tvg::launch_pose_chain(p, nseq, (cudaStream_t)stream));
+    ctx->launches += 1;
+    return 0;
+}
+
+int tvg_triangulate(tvg_ctx* ctx, const double* pix1, const double* pix2, int batch, int n_max, int n,
+                    const int32_t* n_pts, const double* P1, long long p1_stride, const double* P2,
+                    long long p2_stride, const double* kinv_host, double* points4d, uint8_t* good,
+                    void* stream) {
+    if (!ctx) return fail(-1, "ctx is NULL");
+    if (batch < 0 || n_max < 0 || n < 0 || n > n_max) return fail(-2, "tvg_triangulate: bad sizes");
+    if (batch == 0 || n_max == 0) return 0;
+    if (!pix1 || !pix2 || !P1 || !P2 || !kinv_host || !points4d) return fail(-3, "tvg_triangulate: NULL array");
+    if (!aligned16(pix1) || !aligned16(pix2) || (reinterpret_cast<uintptr_t>(points4d) & 31u))
+        return fail(-4, "tvg_triangulate: pix arrays must be 16-byte, points4d 32-byte aligned");
+    DeviceGuard g(ctx->device);
+    tvg::TriParams p{};
+    p.pix1 = pix1; p.pix2 = pix2; p.n_pts = n_pts; p.n_max = n_max; p.n = n;
+    p.P1 = P1; p.P2 = P2; p.p1_stride = p1_stride; p.p2_stride = p2_stride;
+    memcpy(p.kinv, kinv_host, sizeof(p.kinv));
+    p.points4d = points4d; p.good = good;
+    TVG_CUDA(tvg::launch_triangulate(p, batch, (cudaStream_t)stream));
+    ctx->launches += 1;
+    return 0;
+}
+
+int tvg_cheirality(tvg_ctx* ctx, const double* E, const double* src, const double* dst, const uint8_t* mask,
+                   const int32_t* m_count, int batch, int n_max, int m, int32_t* votes, double* Rts,
+                   int32_t* choice, void* stream) {
+    if (!ctx) return fail(-1, "ctx is NULL");
+    if (batch < 0 || n_max < 0 || m < 0 || m > n_max) return fail(-2, "tvg_cheirality: bad sizes");
+    if (batch == 0) return 0;
+    if (!E || !src || !dst || !votes || !Rts || !choice) return fail(-3, "tvg_cheirality: NULL array");
+    DeviceGuard g(ctx->device);
+    tvg::CheiralityParams p{E, src, dst, mask, m_count, n_max, m, votes, Rts, choice};
+    TVG_CUDA(tvg::launch_cheirality(p, batch, (cudaStream_t)stream));
+    ctx->launches += 1;
+    return 0;
+}
+
+int tvg_pairs_device(tvg_ctx* ctx, const tvg_pairs_io* io, void* stream) {
+    if (!ctx || !io) return fail(-1, "ctx / io is NULL");
+    if (io->batch < 0 || io->n_max <= 0 || io->H <= 0) return fail(-2, "tvg_pairs_device: bad sizes");
+    if (io->batch == 0) return 0;
+    if (!io->des || !io->kps) return fail(-3, "tvg_pairs_device: NULL frame pools");
+    if (!io->words && !io->samples) return fail(-3, "tvg_pairs_device: need words or samples");
+    if ((io->pair_q == nullptr) != (io->pair_t == nullptr)) return fail(-3, "tvg_pairs_device: give both pair_q and pair_t or neither");
+    DeviceGuard g(ctx->device);
+    cudaStream_t st = (cudaStream_t)stream;
+    const size_t B = (size_t)io->batch, N = (size_t)io->n_max;
+    const int nseq = io->seq_off ? io->nseq : 1;
+    if (nseq < 1) return fail(-2, "tvg_pairs_device: nseq must be >= 1");
+
+    // sequence offsets + default consecutive-frame pairing
+    const int32_t* seq_off = io->seq_off;
+    if (!seq_off) {
+        int32_t* so;
+        TVG_GET(ctx, S_SEQOFF, 2 * sizeof(int32_t), so, int32_t*);
+        const int32_t h[2] = {0, io->batch};
+        TVG_CUDA(cudaMemcpyAsync(so, h, sizeof(h), cudaMemcpyHostToDevice, st));
+        seq_off = so;
+    }
+    const int32_t *pair_q = io->pair_q, *pair_t = io->pair_t;
+    if (!pair_q) {
+        int32_t *pq, *pt;
+        TVG_GET(ctx, S_PAIRQ, B * sizeof(int32_t), pq, int32_t*);
+        TVG_GET(ctx, S_PAIRT, B * sizeof(int32_t), pt, int32_t*);
+        make_pairs_kernel<<<(io->batch + 255) / 256, 256, 0, st>>>(seq_off, nseq, io->batch, pq, pt);
+        TVG_CUDA(cudaGetLastError());
+        ctx->launches += 1;
+        pair_q = pq; pair_t = pt;
+    }
+
+    int32_t *idx, *dist, *qidx, *tidx, *m_count;
+    uint8_t* keep;
+    double *src, *dst;
+    float* corr32;
+    TVG_OUT(ctx, io->idx, S_IDX, B * N * 2 * sizeof(int32_t), idx, int32_t*);
+    TVG_OUT(ctx, io->dist, S_DIST, B * N * 2 * sizeof(int32_t), dist, int32_t*);
+    TVG_GET(ctx, S_KEEP, B * N, keep, uint8_t*);
+    TVG_OUT(ctx, io->qidx, S_QIDX, B * N * sizeof(int32_t), qidx, int32_t*);
+    TVG_OUT(ctx, io->tidx, S_TIDX, B * N * sizeof(int32_t), tidx, int32_t*);
+    TVG_OUT(ctx, io->m_count, S_MCOUNT, B * sizeof(int32_t), m_count, int32_t*);
+    TVG_GET(ctx, S_SRC, B * N * 2 * sizeof(double), src, double*);
+    TVG_GET(ctx, S_DST, B * N * 2 * sizeof(double), dst, double*);
+    TVG_GET(ctx, S_CORR32, B * N * 4 * sizeof(float), corr32, float*);
+
+    int rc = tvg_knn2_hamming256(ctx, io->des, io->des, io->batch, io->n_max, io->n_max, io->n_max, pair_q, pair_t,
+                                 io->frame_count, io->frame_count, io->ratio, idx, dist, keep, stream);
+    if (rc) return rc;
+    rc = tvg_ratio_compact(ctx, keep, idx, io->batch, io->n_max, io->n_max, pair_q, pair_t, io->frame_count,
+                           io->kps, io->kps, io->kinv, qidx, tidx, m_count, src, dst, corr32, stream);
+    if (rc) return rc;
+
+    tvg_ransac_io r{};
+    r.src = src; r.dst = dst; r.corr32 = corr32; r.m_count = m_count;
+    r.batch = io->batch; r.n_max = io->n_max; r.m = io->n_max; r.H = io->H;
+    r.samples = io->samples; r.words = io->words; r.sample_stride = io->sample_stride; r.thr = io->thr;
+    r.qidx = qidx; r.tidx = tidx; r.pair_q = pair_q; r.pair_t = pair_t; r.kps_q = io->kps; r.kps_t = io->kps;
+    r.E = io->E; r.mask = io->mask; r.n_inl = io->n_inl; r.best = io->best; r.E_best = io->E_best;
+    r.counts = io->counts; r.Rt = io->Rt; r.status = io->status; r.inl_idx = io->inl_idx;
+    int32_t* n_inl;
+    double *Rt, *pix_last, *pix_curr;
+    TVG_OUT(ctx, io->n_inl, S_NINL, B * sizeof(int32_t), n_inl, int32_t*);
+    TVG_OUT(ctx, io->Rt, S_RT, B * 16 * sizeof(double), Rt, double*);
+    TVG_GET(ctx, S_PIXLAST, B * N * 2 * sizeof(double), pix_last, double*);
+    TVG_GET(ctx, S_PIXCURR, B * N * 2 * sizeof(double), pix_curr, double*);
+    r.n_inl = n_inl; r.Rt = Rt; r.pix_last = pix_last; r.pix_curr = pix_curr;
+    rc = tvg_ransac_essential(ctx, &r, stream);
+    if (rc) return rc;
+
+    double *poses, *pinv, *points;
+    uint8_t* good;
+    TVG_OUT(ctx, io->poses, S_POSES, (B + nseq) * 16 * sizeof(double), poses, double*);
+    TVG_GET(ctx, S_POSESINV, B * 32 * sizeof(double), pinv, double*);
+    TVG_OUT(ctx, io->points4d, S_POINTS, B * N * 4 * sizeof(double), points, double*);
+    TVG_OUT(ctx, io->good, S_GOOD, B * N, good, uint8_t*);
+    rc = tvg_pose_chain(ctx, Rt, seq_off, nseq, io->init_pose, poses, pinv, stream);
+    if (rc) return rc;
+    // triangulate(frame.last_kps, frame.curr_kps, frame.last_pose, frame.curr_pose)  (slam.py:263)
+    return tvg_triangulate(ctx, pix_last, pix_curr, io->batch, io->n_max, io->n_max, n_inl, pinv, 32, pinv + 16,
+                           32, io->kinv, points, good, stream);
+}
+
+int tvg_pairs_host(tvg_ctx* ctx, const tvg_pairs_io* hio, int frames, long long* bytes_h2d,
+                   long long* bytes_d2h, void* stream) {
+    if (!ctx || !hio) return fail(-1, "ctx / io is NULL");
+    if (hio->batch < 0 || hio->n_max <= 0 || hio->H <= 0 || frames <= 0) return fail(-2, "tvg_pairs_host: bad sizes");
+    if (!hio->des || !hio->kps) return fail(-3, "tvg_pairs_host: NULL frame pools");
+    if (!hio->words && !hio->samples) return fail(-3, "tvg_pairs_host: need words or samples");
+    DeviceGuard g(ctx->device);
+    cudaStream_t st = (cudaStream_t)stream;
+    const size_t B = (size_t)hio->batch, N = (size_t)hio->n_max, H = (size_t)hio->H, F = (size_t)frames;
+    const int nseq = hio->seq_off ? hio->nseq : 1;
+    long long h2d = 0, d2h = 0;
+    tvg_pairs_io d = *hio;
+#define TVG_UP(slot, hptr, bytes, field, type)                                              \
+    do {                                                                                    \
+        if (hptr) {                                                                         \
+            type dp__;                                                                      \
+            TVG_GET(ctx, slot, (bytes), dp__, type);                                        \
+            TVG_CUDA(cudaMemcpyAsync((void*)dp__, (hptr), (bytes), cudaMemcpyHostToDevice, st)); \
+            h2d += (long long)(bytes);                                                      \
+            field = dp__;                                                                   \
+        }                                                                                   \
+    } while (0)
+    TVG_UP(S_H_DES, hio->des, F * N * 32, d.des, uint8_t*);
+    TVG_UP(S_H_KPS, hio->kps, F * N * 2 * sizeof(double), d.kps, double*);
+    TVG_UP(S_H_FCOUNT, hio->frame_count, F * sizeof(int32_t), d.frame_count, int32_t*);
+    TVG_UP(S_H_PAIRQ, hio->pair_q, B * sizeof(int32_t), d.pair_q, int32_t*);
+    TVG_UP(S_H_PAIRT, hio->pair_t, B * sizeof(int32_t), d.pair_t, int32_t*);
+    TVG_UP(S_H_SEQOFF, hio->seq_off, (size_t)(nseq + 1) * sizeof(int32_t), d.seq_off, int32_t*);
+    TVG_UP(S_H_INIT, hio->init_pose, (size_t)nseq * 16 * sizeof(double), d.init_pose, double*);
+    const size_t tab = (hio->sample_stride ? B : 1) * H * 8 * 4;
+    TVG_UP(S_H_WORDS, hio->words, tab, d.words, uint32_t*);
+    TVG_UP(S_H_SAMPLES, hio->samples, tab, d.samples, int32_t*);
+#undef TVG_UP
+    // device-side outputs always go to scratch; requested ones are copied back
+    d.idx = d.dist = d.qidx = d.tidx = d.m_count = d.best = d.counts = d.n_inl = d.inl_idx = d.status = nullptr;
+    d.E = d.E_best = d.Rt = d.poses = d.points4d = nullptr;
+    d.mask = d.good = nullptr;
+    // route scratch-backed outputs through fixed slots so we know where they live
+    int32_t *idx, *dist, *qidx, *tidx, *m_count, *best, *counts, *n_inl, *inl_idx, *status;
+    double *E, *E_best, *Rt, *poses, *points;
+    uint8_t *mask, *good;
+    TVG_GET(ctx, S_IDX, B * N * 2 * sizeof(int32_t), idx, int32_t*);
+    TVG_GET(ctx, S_DIST, B * N * 2 * sizeof(int32_t), dist, int32_t*);
+    TVG_GET(ctx, S_QIDX, B * N * sizeof(int32_t), qidx, int32_t*);
+    TVG_GET(ctx, S_TIDX, B * N * sizeof(int32_t), tidx, int32_t*);
+    TVG_GET(ctx, S_MCOUNT, B * sizeof(int32_t), m_count, int32_t*);
+    TVG_GET(ctx, S_BEST, B * sizeof(int32_t), best, int32_t*);
+    TVG_GET(ctx, S_COUNTS, B * H * sizeof(int32_t), counts, int32_t*);
+    TVG_GET(ctx, S_NINL, B * sizeof(int32_t), n_inl, int32_t*);
+    TVG_GET(ctx, S_INLIDX, B * N * sizeof(int32_t), inl_idx, int32_t*);
+    TVG_GET(ctx, S_STATUS, B * sizeof(int32_t), status, int32_t*);
+    TVG_GET(ctx, S_E, B * 9 * sizeof(double), E, double*);
+    TVG_GET(ctx, S_EBEST, B * 9 * sizeof(double), E_best, double*);
+    TVG_GET(ctx, S_RT, B * 16 * sizeof(double), Rt, double*);
+    TVG_GET(ctx, S_POSES, (B + nseq) * 16 * sizeof(double), poses, double*);
+    TVG_GET(ctx, S_POINTS, B * N * 4 * sizeof(double), points, double*);
+    TVG_GET(ctx, S_MASK, B * N, mask, uint8_t*);
+    TVG_GET(ctx, S_GOOD, B * N, good, uint8_t*);
+    d.idx = idx; d.dist = dist; d.qidx = qidx; d.tidx = tidx; d.m_count = m_count; d.best = best;
+    d.counts = counts; d.n_inl = n_inl; d.inl_idx = inl_idx; d.status = status; d.E = E; d.E_best = E_best;
+    d.Rt = Rt; d.poses = poses; d.points4d = points; d.mask = mask; d.good = good;
+    int rc = tvg_pairs_device(ctx, &d, stream);
+    if (rc) return rc;
+#define TVG_DOWN(hptr, dptr, bytes)                                                          \
+    do {                                                                                     \
+        if (hptr) {                                                                          \
+            TVG_CUDA(cudaMemcpyAsync((hptr), (dptr), (bytes), cudaMemcpyDeviceToHost, st));  \
+            d2h += (long long)(bytes);                                                       \
+        }                                                                                    \
+    } while (0)
+    TVG_DOWN(hio->idx, idx, B * N * 2 * sizeof(int32_t));
+    TVG_DOWN(hio->dist, dist, B * N * 2 * sizeof(int32_t));
+    TVG_DOWN(hio->qidx, qidx, B * N * sizeof(int32_t));
+    TVG_DOWN(hio->tidx, tidx, B * N * sizeof(int32_t));
+    TVG_DOWN(hio->m_count, m_count, B * sizeof(int32_t));
+    TVG_DOWN(hio->best, best, B * sizeof(int32_t));
+    TVG_DOWN(hio->counts, counts, B * H * sizeof(int32_t));
+    TVG_DOWN(hio->n_inl, n_inl, B * sizeof(int32_t));
+    TVG_DOWN(hio->inl_idx, inl_idx, B * N * sizeof(int32_t));
+    TVG_DOWN(hio->status, status, B * sizeof(int32_t));
+    TVG_DOWN(hio->E, E, B * 9 * sizeof(double));
+    TVG_DOWN(hio->E_best, E_best, B * 9 * sizeof(double));
+    TVG_DOWN(hio->Rt, Rt, B * 16 * sizeof(double));
+    TVG_DOWN(hio->poses, poses, (B + nseq) * 16 * sizeof(double));
+    TVG_DOWN(hio->points4d, points, B * N * 4 * sizeof(double));
+    TVG_DOWN(hio->mask, mask, B * N);
+    TVG_DOWN(hio->good, good, B * N);
+#undef TVG_DOWN
+    TVG_CUDA(cudaStreamSynchronize(st));
+    if (bytes_h2d) *bytes_h2d = h2d;
+    if (bytes_d2h) *bytes_d2h = d2h;
+    return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,216 @@
+// Brute-force 256-bit Hamming kNN (k=2) + Lowe ratio flag  --  replaces
+// cv2.BFMatcher(cv2.NORM_HAMMING).knnMatch(curr_des, last_des, k=2) and the ratio test of
+// /root/reference/MonocularSlam/slam.py:126-137.
+//
+// Design (sm_100a):
+//   * one thread owns R query descriptors in registers (8 x u32 each, fetched with two 128-bit loads);
+//   * the CTA streams its slice of train rows through a STAGES-deep shared-memory ring filled by
+//     TMA bulk copies (cp.async.bulk + mbarrier complete_tx; SASS UBLKCP); every lane of a warp reads
+//     the SAME train row -> shared-memory broadcast, conflict-free, no swizzle needed;
+//   * distance = popcount(q ^ t) on the integer pipes: LOP3 (xor / carry-save adders) + POPC;
+//   * top-2 kept as packed keys  dist<<23 | trainIdx , so unsigned min() IS "lowest distance, then
+//     lowest train index" (OpenCV's strict-< insertion order) and results are bit-exact;
+//   * when Nq alone cannot fill 148 SMs the train rows are split over gridDim.y; the last CTA to
+//     finish a query tile merges the per-split partial top-2 lists with a warp-shuffle butterfly and
+//     applies the ratio test ( d1 < ratio * d2 , strict, evaluated in fp64 like the Python float compare).
+#include "tvg_common.cuh"
+#include "tvg_kernels.h"
+
+namespace tvg {
+
+__device__ __forceinline__ uint32_t lop3_xor3(uint32_t a, uint32_t b, uint32_t c) {
+    uint32_t d;
+    asm("lop3.b32 %0, %1, %2, %3, 0x96;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+    return d;
+}
+__device__ __forceinline__ uint32_t lop3_maj(uint32_t a, uint32_t b, uint32_t c) {
+    uint32_t d;
+    asm("lop3.b32 %0, %1, %2, %3, 0xE8;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+    return d;
+}
+
+// popcount of the 256-bit XOR.  VARIANT 0: 8 LOP3 + 8 POPC.  VARIANT 1: Harley-Seal carry-save
+// adders fold the eight words into one weight-1 pair, one weight-2 and one weight-4 word:
+// 16 LOP3 + 4 POPC (trades POPC-pipe work, 16 lanes/clk/SM, for ALU-pipe work, 64 lanes/clk/SM).
+// VARIANT 2: three CSAs, 14 LOP3 + 5 POPC.
+template <int VARIANT>
+__device__ __forceinline__ uint32_t hamming256(const uint32_t (&q)[8], const uint4& t0, const uint4& t1) {
+    const uint32_t x0 = q[0] ^ t0.x, x1 = q[1] ^ t0.y, x2 = q[2] ^ t0.z, x3 = q[3] ^ t0.w;
+    const uint32_t x4 = q[4] ^ t1.x, x5 = q[5] ^ t1.y, x6 = q[6] ^ t1.z, x7 = q[7] ^ t1.w;
+    if (VARIANT == 0) {
+        return (__popc(x0) + __popc(x1)) + (__popc(x2) + __popc(x3)) + (__popc(x4) + __popc(x5)) +
+               (__popc(x6) + __popc(x7));
+    } else if (VARIANT == 1) {
+        const uint32_t sa = lop3_xor3(x0, x1, x2), ca = lop3_maj(x0, x1, x2);
+        const uint32_t sb = lop3_xor3(x3, x4, x5), cb = lop3_maj(x3, x4, x5);
+        const uint32_t sc = lop3_xor3(x6, x7, sa), cc = lop3_maj(x6, x7, sa);
+        const uint32_t sd = lop3_xor3(ca, cb, cc), cd = lop3_maj(ca, cb, cc);
+        // weight 1: sb, sc ; weight 2: sd ; weight 4: cd
+        return (__popc(sb) + __popc(sc)) + 2u * __popc(sd) + 4u * __popc(cd);
+    } else {
+        const uint32_t sa = lop3_xor3(x0, x1, x2), ca = lop3_maj(x0, x1, x2);
+        const uint32_t sb = lop3_xor3(x3, x4, x5), cb = lop3_maj(x3, x4, x5);
+        const uint32_t sc = lop3_xor3(x6, x7, sa), cc = lop3_maj(x6, x7, sa);
+        return (__popc(sb) + __popc(sc)) + 2u * ((__popc(ca) + __popc(cb)) + __popc(cc));
+    }
+}
+
+// Final (idx, dist) pair of one query + the Lowe ratio flag (slam.py:131: m.distance < 0.75*n.distance).
+__device__ __forceinline__ void knn2_emit(const KnnParams& p, size_t o, uint32_t k1, uint32_t k2) {
+    int2 id, di;
+    id.x = (k1 == TVG_SENTINEL_KEY) ? -1 : (int)(k1 & TVG_KEY_IDX_MASK);
+    di.x = (k1 == TVG_SENTINEL_KEY) ? -1 : (int)(k1 >> TVG_KEY_SHIFT);
+    id.y = (k2 == TVG_SENTINEL_KEY) ? -1 : (int)(k2 & TVG_KEY_IDX_MASK);
+    di.y = (k2 == TVG_SENTINEL_KEY) ? -1 : (int)(k2 >> TVG_KEY_SHIFT);
+    reinterpret_cast<int2*>(p.idx)[o] = id;
+    reinterpret_cast<int2*>(p.dist)[o] = di;
+    if (p.keep) p.keep[o] = (k2 != TVG_SENTINEL_KEY) && ((double)di.x < p.ratio * (double)di.y);
+}
+
+template <int R, int THREADS, int CH, int STAGES, int VARIANT>
+__global__ void __launch_bounds__(THREADS) knn2_kernel(const KnnParams p) {
+    constexpr int BQ = R * THREADS;
+    __shared__ alignas(128) uint4 tile[STAGES][CH * 2];
+    __shared__ alignas(8) uint64_t full_bar[STAGES];
+    __shared__ int s_is_last;
+
+    const int tid = threadIdx.x;
+    const int b = blockIdx.z, split = blockIdx.y, qt = blockIdx.x;
+    const int fq = p.pair_q ? p.pair_q[b] : b;
+    const int ft = p.pair_t ? p.pair_t[b] : b;
+    const int nq = p.q_count ? min(p.q_count[fq], p.n_max) : p.nq;
+    const int nt = p.t_count ? min(p.t_count[ft], p.n_max) : p.nt;
+    const int q0 = qt * BQ;
+    if (q0 >= nq) return;  // whole tile empty for every split: nobody touches the counter
+
+    const uint4* __restrict__ qv = reinterpret_cast<const uint4*>(p.q_base + (size_t)fq * p.n_max * 32);
+    const uint8_t* __restrict__ tb = p.t_base + (size_t)ft * p.n_max * 32;
+    const int row0 = min(nt, split * p.rows_per_split);
+    const int row1 = min(nt, row0 + p.rows_per_split);
+    const int nrows = row1 - row0;
+    const int nchunks = (nrows + CH - 1) / CH;
+
+    uint32_t qd[R][8];
+    uint32_t m1[R], m2[R];
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+        const int qi = q0 + r * THREADS + tid;
+        uint4 a = make_uint4(0, 0, 0, 0), c = a;
+        if (qi < nq) {
+            a = __ldg(qv + 2 * (size_t)qi);
+            c = __ldg(qv + 2 * (size_t)qi + 1);
+        }
+        qd[r][0] = a.x; qd[r][1] = a.y; qd[r][2] = a.z; qd[r][3] = a.w;
+        qd[r][4] = c.x; qd[r][5] = c.y; qd[r][6] = c.z; qd[r][7] = c.w;
+        m1[r] = TVG_SENTINEL_KEY;
+        m2[r] = TVG_SENTINEL_KEY;
+    }
+
+    if (tid == 0) {
+#pragma unroll
+        for (int s = 0; s < STAGES; ++s) mbar_init(&full_bar[s], 1);
+        fence_mbar_init();
+    }
+    __syncthreads();
+
+    auto issue = [&](int c) {
+        const int st = c % STAGES;
+        const int rows = min(CH, nrows - c * CH);
+        const uint32_t bytes = (uint32_t)rows * 32u;
+        mbar_arrive_expect_tx(&full_bar[st], bytes);
+        tma_load_1d(&tile[st][0], tb + (size_t)(row0 + c * CH) * 32, bytes, &full_bar[st]);
+    };
+    if (tid == 0) {
+        for (int c = 0; c < STAGES - 1 && c < nchunks; ++c) issue(c);
+    }
+
+    for (int c = 0; c < nchunks; ++c) {
+        const int st = c % STAGES;
+        if (tid == 0 && c + STAGES - 1 < nchunks) issue(c + STAGES - 1);
+        mbar_wait(&full_bar[st], (uint32_t)((c / STAGES) & 1));
+        const int rows = min(CH, nrows - c * CH);
+        const uint4* __restrict__ tp = &tile[st][0];
+        uint32_t jg = (uint32_t)(row0 + c * CH);
+#pragma unroll 4
+        for (int j = 0; j < rows; ++j, ++jg) {
+            const uint4 t0 = tp[2 * j];
+            const uint4 t1 = tp[2 * j + 1];
+#pragma unroll
+            for (int r = 0; r < R; ++r) {
+                const uint32_t d = hamming256<VARIANT>(qd[r], t0, t1);
+                const uint32_t key = d * (1u << TVG_KEY_SHIFT) + jg;
+                top2_insert(m1[r], m2[r], key);
+            }
+        }
+        __syncthreads();  // every warp is done with stage st before TMA refills it
+    }
+
+    const int32_t ob = b * p.n_max;
+    if (p.splits == 1) {
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            const int qi = q0 + r * THREADS + tid;
+            if (qi < nq) knn2_emit(p, (size_t)(ob + qi), m1[r], m2[r]);
+        }
+        return;
+    }
+
+    // ---- split-Nt: publish partials, last CTA of this query tile merges -------------------
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+        const int qi = q0 + r * THREADS + tid;
+        if (qi < nq) p.partial[(size_t)(ob + qi) * p.splits + split] = make_uint2(m1[r], m2[r]);
+    }
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) {
+        unsigned int* ctr = p.tile_counters + (size_t)b * gridDim.x + qt;
+        const unsigned int old = atomicAdd(ctr, 1u);
+        s_is_last = (old == (unsigned)p.splits - 1u);
+        if (s_is_last) *ctr = 0u;  // self-resetting: the workspace stays zeroed between launches
+    }
+    __syncthreads();
+    if (!s_is_last) return;
+    __threadfence();
+
+    const int warp = tid >> 5, lane = tid & 31;
+    const int qend = min(nq, q0 + BQ);
+    for (int qi = q0 + warp; qi < qend; qi += THREADS / 32) {
+        uint32_t a1 = TVG_SENTINEL_KEY, a2 = TVG_SENTINEL_KEY;
+        const uint2* pp = p.partial + (size_t)(ob + qi) * p.splits;
+        for (int s = lane; s < p.splits; s += 32) {
+            const uint2 v = __ldcg(pp + s);
+            top2_merge(a1, a2, v.x, v.y);
+        }
+#pragma unroll
+        for (int m = 16; m > 0; m >>= 1) {  // warp-shuffle top-2 butterfly
+            const uint32_t b1 = __shfl_xor_sync(0xffffffffu, a1, m);
+            const uint32_t b2 = __shfl_xor_sync(0xffffffffu, a2, m);
+            top2_merge(a1, a2, b1, b2);
+        }
+        if (lane == 0) knn2_emit(p, (size_t)(ob + qi), a1, a2);
+    }
+}
+
+template <int R, int THREADS, int CH, int STAGES, int VARIANT>
+static cudaError_t launch_cfg(const KnnParams& p, int batch, int qtiles, cudaStream_t stream) {
+    dim3 grid(qtiles, p.splits, batch);
+    knn2_kernel<R, THREADS, CH, STAGES, VARIANT><<<grid, THREADS, 0, stream>>>(p);
+    return cudaGetLastError();
+}
+
+int knn2_block_queries(int r) { return r * 128; }
+
+cudaError_t launch_knn2(const KnnParams& p, int batch, int r, int variant, cudaStream_t stream) {
+    const int bq = knn2_block_queries(r);
+    const int qtiles = (p.n_max + bq - 1) / bq;
+#define TVG_KNN_CASE(RR, VV) \
+    if (r == RR && variant == VV) return launch_cfg<RR, 128, 128, 3, VV>(p, batch, qtiles, stream);
+    TVG_KNN_CASE(4, 0) TVG_KNN_CASE(4, 1) TVG_KNN_CASE(4, 2)
+    TVG_KNN_CASE(2, 0) TVG_KNN_CASE(2, 1) TVG_KNN_CASE(2, 2)
+    TVG_KNN_CASE(8, 0) TVG_KNN_CASE(8, 1) TVG_KNN_CASE(8, 2)
+#undef TVG_KNN_CASE
+    return cudaErrorInvalidValue;
+}
+
+}  // namespace tvg

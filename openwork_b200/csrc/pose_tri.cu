@@ -1,0 +1,186 @@
+// Pose extraction, pose chaining and DLT triangulation  --  replaces extract_Rt (slam.py:167-186),
+// `curr_pose = Rt @ last_pose` (slam.py:261), triangulate (slam.py:202-221) and check_points
+// (slam.py:233-237) of /root/reference/MonocularSlam/slam.py.
+//
+// triangulate: one thread per point, everything in registers: K-normalise the two pixel observations,
+// build the 4x4 DLT system, one-sided Jacobi SVD (fp64), take the right singular vector of the smallest
+// singular value, divide by w.  Algorithmic traffic 64 B/point (2 x (x,y) f64 in, (x,y,z,1) f64 out).
+#include "tvg_linalg.cuh"
+#include "tvg_kernels.h"
+
+namespace tvg {
+
+__global__ void extract_rt_kernel(const ExtractRtParams p, int batch) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= batch) return;
+    double E[9], Rt[16];
+#pragma unroll
+    for (int i = 0; i < 9; ++i) E[i] = p.E[(size_t)b * 9 + i];
+    extract_rt(E, Rt);
+#pragma unroll
+    for (int i = 0; i < 16; ++i) p.Rt[(size_t)b * 16 + i] = Rt[i];
+}
+
+cudaError_t launch_extract_rt(const ExtractRtParams& p, int batch, cudaStream_t stream) {
+    extract_rt_kernel<<<(batch + 31) / 32, 32, 0, stream>>>(p, batch);
+    return cudaGetLastError();
+}
+
+// One thread per sequence: pose[f+1] = Rt[f] @ pose[f]  (slam.py:261), plus the inverses triangulate needs.
+__global__ void pose_chain_kernel(const PoseChainParams p, int nseq) {
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= nseq) return;
+    const int b0 = p.seq_off[s], b1 = p.seq_off[s + 1];
+    double cur[16], inv[16];
+    for (int i = 0; i < 16; ++i) cur[i] = p.init_pose ? p.init_pose[(size_t)s * 16 + i] : ((i % 5 == 0) ? 1.0 : 0.0);
+    inverse4(cur, inv);
+    for (int i = 0; i < 16; ++i) p.poses[(size_t)(b0 + s) * 16 + i] = cur[i];
+    for (int b = b0; b < b1; ++b) {
+        double nxt[16];
+        const double* Rt = p.Rt + (size_t)b * 16;
+        for (int r = 0; r < 4; ++r)
+            for (int c = 0; c < 4; ++c) {
+                double a = 0.0;
+                for (int k = 0; k < 4; ++k) a = fma(Rt[r * 4 + k], cur[k * 4 + c], a);
+                nxt[r * 4 + c] = a;
+            }
+        if (p.pair_pinv)
+            for (int i = 0; i < 16; ++i) p.pair_pinv[(size_t)b * 32 + i] = inv[i];
+        for (int i = 0; i < 16; ++i) cur[i] = nxt[i];
+        inverse4(cur, inv);
+        for (int i = 0; i < 16; ++i) p.poses[(size_t)(b + s + 1) * 16 + i] = cur[i];
+        if (p.pair_pinv)
+            for (int i = 0; i < 16; ++i) p.pair_pinv[(size_t)b * 32 + 16 + i] = inv[i];
+    }
+}
+
+cudaError_t launch_pose_chain(const PoseChainParams& p, int nseq, cudaStream_t stream) {
+    pose_chain_kernel<<<(nseq + 31) / 32, 32, 0, stream>>>(p, nseq);
+    return cudaGetLastError();
+}
+
+constexpr int TRI_THREADS = 128;
+
+__device__ __forceinline__ void dlt_point(const double* __restrict__ P1, const double* __restrict__ P2,
+                                          double x1, double y1, double x2, double y2, double (&X)[4]) {
+    // rows: x1*P1[2]-P1[0], y1*P1[2]-P1[1], x2*P2[2]-P2[0], y2*P2[2]-P2[1]   (slam.py:212-216)
+    double G[4][4], V[4][4];  // G[c][r]: column c of A
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+        G[c][0] = x1 * P1[8 + c] - P1[c];
+        G[c][1] = y1 * P1[8 + c] - P1[4 + c];
+        G[c][2] = x2 * P2[8 + c] - P2[c];
+        G[c][3] = y2 * P2[8 + c] - P2[4 + c];
+    }
+    jacobi_onesided<4, 4>(G, V, 30);
+    double nmin = 0.0;
+    int best = 0;
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+        const double n = G[c][0] * G[c][0] + G[c][1] * G[c][1] + G[c][2] * G[c][2] + G[c][3] * G[c][3];
+        if (c == 0 || n < nmin) { nmin = n; best = c; }
+    }
+#pragma unroll
+    for (int c = 0; c < 4; ++c)
+        if (c == best) {
+            const double w = V[c][3];
+            X[0] = V[c][0] / w; X[1] = V[c][1] / w; X[2] = V[c][2] / w; X[3] = w / w;
+        }
+}
+
+__global__ void __launch_bounds__(TRI_THREADS) triangulate_kernel(const TriParams p) {
+    __shared__ double sP[32];
+    const int b = blockIdx.y;
+    const int n = p.n_pts ? min(p.n_pts[b], p.n_max) : p.n;
+    if (blockIdx.x * TRI_THREADS >= n) return;
+    if (threadIdx.x < 32) {
+        const double* P = (threadIdx.x < 16) ? p.P1 + (size_t)b * p.p1_stride : p.P2 + (size_t)b * p.p2_stride;
+        sP[threadIdx.x] = P[threadIdx.x & 15];
+    }
+    __syncthreads();
+    const int i = blockIdx.x * TRI_THREADS + threadIdx.x;
+    if (i >= n) return;
+    const size_t o = (size_t)b * p.n_max + i;
+    const double2 a = reinterpret_cast<const double2*>(p.pix1)[o];
+    const double2 c = reinterpret_cast<const double2*>(p.pix2)[o];
+    const double x1 = p.kinv[0] * a.x + p.kinv[1] * a.y + p.kinv[2];
+    const double y1 = p.kinv[3] * a.x + p.kinv[4] * a.y + p.kinv[5];
+    const double x2 = p.kinv[0] * c.x + p.kinv[1] * c.y + p.kinv[2];
+    const double y2 = p.kinv[3] * c.x + p.kinv[4] * c.y + p.kinv[5];
+    double X[4];
+    dlt_point(sP, sP + 16, x1, y1, x2, y2, X);
+    double4* out = reinterpret_cast<double4*>(p.points4d);
+    out[o] = make_double4(X[0], X[1], X[2], X[3]);
+    if (p.good) p.good[o] = (X[2] > 0.0) ? 1 : 0;  // check_points: world z > 0
+}
+
+cudaError_t launch_triangulate(const TriParams& p, int batch, cudaStream_t stream) {
+    dim3 grid((p.n_max + TRI_THREADS - 1) / TRI_THREADS, batch);
+    triangulate_kernel<<<grid, TRI_THREADS, 0, stream>>>(p);
+    return cudaGetLastError();
+}
+
+// Cheirality vote over the four (R, +-t) decompositions of E (north star (3); NOT in the reference,
+// which uses the trace / t_z heuristics).  One CTA per pair; thread-strided over correspondences.
+constexpr int CHEIR_THREADS = 256;
+
+__global__ void __launch_bounds__(CHEIR_THREADS) cheirality_kernel(const CheiralityParams p) {
+    __shared__ double sRt[4][16];
+    __shared__ int s_votes[4];
+    const int b = blockIdx.x, tid = threadIdx.x;
+    const int M = p.m_count ? min(p.m_count[b], p.n_max) : p.m;
+    if (tid == 0) {
+        double E[9], u[3][3], s[3], v[3][3];
+        for (int i = 0; i < 9; ++i) E[i] = p.E[(size_t)b * 9 + i];
+        svd3(E, u, s, v);
+        for (int cand = 0; cand < 4; ++cand) {
+            const double sw = (cand < 2) ? 1.0 : -1.0;     // W or W^T
+            const double st = (cand & 1) ? -1.0 : 1.0;     // +u3 or -u3
+            for (int r = 0; r < 3; ++r) {
+                for (int c = 0; c < 3; ++c)
+                    sRt[cand][r * 4 + c] = sw * (u[1][r] * v[0][c] - u[0][r] * v[1][c]) + u[2][r] * v[2][c];
+                sRt[cand][r * 4 + 3] = st * u[2][r];
+            }
+            sRt[cand][12] = 0.0; sRt[cand][13] = 0.0; sRt[cand][14] = 0.0; sRt[cand][15] = 1.0;
+            s_votes[cand] = 0;
+        }
+    }
+    __syncthreads();
+    const double I4[16] = {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1};
+    int votes[4] = {0, 0, 0, 0};
+    const size_t ob = (size_t)b * p.n_max;
+    for (int m = tid; m < M; m += CHEIR_THREADS) {
+        if (p.mask && !p.mask[ob + m]) continue;
+        const double2 s = reinterpret_cast<const double2*>(p.src)[ob + m];
+        const double2 d = reinterpret_cast<const double2*>(p.dst)[ob + m];
+        for (int cand = 0; cand < 4; ++cand) {
+            double X[4];
+            dlt_point(I4, sRt[cand], s.x, s.y, d.x, d.y, X);
+            const double z2 = sRt[cand][8] * X[0] + sRt[cand][9] * X[1] + sRt[cand][10] * X[2] + sRt[cand][11];
+            votes[cand] += (X[2] > 0.0 && z2 > 0.0) ? 1 : 0;
+        }
+    }
+    for (int cand = 0; cand < 4; ++cand) {
+        int v = votes[cand];
+#pragma unroll
+        for (int m = 16; m > 0; m >>= 1) v += __shfl_xor_sync(0xffffffffu, v, m);
+        if ((tid & 31) == 0) atomicAdd(&s_votes[cand], v);
+    }
+    __syncthreads();
+    if (tid == 0) {
+        int best = 0;
+        for (int cand = 0; cand < 4; ++cand) {
+            p.votes[b * 4 + cand] = s_votes[cand];
+            if (s_votes[cand] > s_votes[best]) best = cand;
+            for (int i = 0; i < 16; ++i) p.Rts[((size_t)b * 4 + cand) * 16 + i] = sRt[cand][i];
+        }
+        p.choice[b] = best;
+    }
+}
+
+cudaError_t launch_cheirality(const CheiralityParams& p, int batch, cudaStream_t stream) {
+    cheirality_kernel<<<batch, CHEIR_THREADS, 0, stream>>>(p);
+    return cudaGetLastError();
+}
+
+}  // namespace tvg

@@ -1,0 +1,573 @@
+// Seeded RANSAC over 8-point essential-matrix hypotheses  --  replaces
+// skimage.measure.ransac((norm_last, norm_curr), EssentialMatrixTransform, min_samples=8,
+//                        residual_threshold=0.005, max_trials=H)
+// at /root/reference/MonocularSlam/slam.py:155-159 (algorithm: SURVEY.md Appendix A.2 / A.3), with the
+// per-trial rng.choice replaced by a host-supplied sample table so hypotheses equal the oracle's.
+//
+// Kernels
+//   ransac_fit      one thread = one hypothesis, register-resident fp64: Hartley normalisation,
+//                   8x9 DLT null vector (Householder), 3x3 one-sided Jacobi SVD, (s,s,0) projection,
+//                   de-normalisation.  Emits E (fp64) and a Frobenius-normalised fp32 copy (SoA).
+//   ransac_score    fp32 Sampson scoring: thread = hypothesis (E in registers), correspondence chunk
+//                   resident in shared memory (TMA bulk copy), broadcast LDS.128 per correspondence.
+//                   Per-thread count / uncertainty-band count / sum r^2 -> deterministic partials.
+//   ransac_reduce   sums the partials, then lists every hypothesis whose count upper bound reaches the
+//                   best lower bound (fp32 cannot be trusted closer than the band).
+//   ransac_rescore  exact fp64 residuals for the listed candidates (count, sum r^2 over ALL points).
+//   ransac_refit    picks best = (max count, min sum r^2, earliest), writes the PRE-refit inlier mask,
+//                   compacts the inliers, re-estimates E on them (A^T A in fp64 + warp-parallel
+//                   Jacobi eigen-solve), and runs extract_Rt on the refit E.
+#include "tvg_linalg.cuh"
+#include "tvg_kernels.h"
+
+namespace tvg {
+
+// ------------------------------------------------------------------------------------ fit
+constexpr int FIT_THREADS = 64;
+
+__device__ __forceinline__ bool hartley8(const double (&x)[8], const double (&y)[8], double& s, double& cx,
+                                         double& cy) {
+    double sx = 0.0, sy = 0.0;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) { sx += x[k]; sy += y[k]; }
+    cx = sx / 8.0;
+    cy = sy / 8.0;
+    double q = 0.0;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        const double dx = x[k] - cx, dy = y[k] - cy;
+        q = fma(dx, dx, q);
+        q = fma(dy, dy, q);
+    }
+    const double rms = sqrt(q / 8.0);
+    if (!(rms > 0.0)) return false;
+    s = 1.4142135623730951 / rms;
+    return isfinite(s);
+}
+
+__global__ void __launch_bounds__(FIT_THREADS) ransac_fit_kernel(const RansacParams p) {
+    const int b = blockIdx.y;
+    const int h = blockIdx.x * FIT_THREADS + threadIdx.x;
+    if (h >= p.H) return;
+    const int M = p.m_count ? min(p.m_count[b], p.n_max) : p.m;
+    const size_t ob = (size_t)b * p.n_max;
+    const size_t oh = (size_t)b * p.H + h;
+
+    int idx[8];
+    bool ok = (M > 8);  // skimage: 0 < min_samples < num_samples
+    if (ok) {
+        if (p.samples) {
+            const int32_t* s = p.samples + (size_t)b * p.sample_stride + (size_t)h * 8;
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                idx[k] = s[k];
+                ok = ok && (idx[k] >= 0) && (idx[k] < M);
+            }
+        } else {
+            const uint32_t* w = p.words + (size_t)b * p.sample_stride + (size_t)h * 8;
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                int v = (int)(((unsigned long long)w[k] * (unsigned long long)M) >> 32);
+                // bump until distinct from every earlier slot (slot order, +1 mod M)
+                bool clash = true;
+                while (clash) {
+                    clash = false;
+#pragma unroll
+                    for (int j = 0; j < 8; ++j)
+                        if (j < k && idx[j] == v) clash = true;
+                    if (clash) v = (v + 1 == M) ? 0 : v + 1;
+                }
+                idx[k] = v;
+            }
+        }
+    }
+    if (p.samples_out) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) p.samples_out[oh * 8 + k] = ok ? idx[k] : -1;
+    }
+
+    double E[9];
+    if (ok) {
+        double sx[8], sy[8], dx[8], dy[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            const double2 s = reinterpret_cast<const double2*>(p.src)[ob + idx[k]];
+            const double2 d = reinterpret_cast<const double2*>(p.dst)[ob + idx[k]];
+            sx[k] = s.x; sy[k] = s.y; dx[k] = d.x; dy[k] = d.y;
+        }
+        double ss, csx, csy, sd, cdx, cdy;
+        ok = hartley8(sx, sy, ss, csx, csy);
+        ok = hartley8(dx, dy, sd, cdx, cdy) && ok;
+        if (ok) {
+            double a[8][9];
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                const double xs = ss * sx[k] - ss * csx, ys = ss * sy[k] - ss * csy;
+                const double xd = sd * dx[k] - sd * cdx, yd = sd * dy[k] - sd * cdy;
+                a[k][0] = xd * xs; a[k][1] = xd * ys; a[k][2] = xd;
+                a[k][3] = yd * xs; a[k][4] = yd * ys; a[k][5] = yd;
+                a[k][6] = xs;      a[k][7] = ys;      a[k][8] = 1.0;
+            }
+            double n[9], En[9];
+            null_vector_8x9(a, n);
+            essential_project(n, En);
+            essential_denormalise(En, ss, csx, csy, sd, cdx, cdy, E);
+#pragma unroll
+            for (int i = 0; i < 9; ++i) ok = ok && isfinite(E[i]);
+        }
+    }
+    double fro = 0.0;
+#pragma unroll
+    for (int i = 0; i < 9; ++i) {
+        if (!ok) E[i] = __longlong_as_double(0x7ff8000000000000LL);
+        fro = fma(E[i], E[i], fro);
+    }
+    const double inv = ok ? rsqrt(fro) : 0.0;
+    p.valid[oh] = ok ? 1 : 0;
+#pragma unroll
+    for (int i = 0; i < 9; ++i) {
+        p.E64[oh * 9 + i] = E[i];
+        p.E32[((size_t)b * 9 + i) * p.H + h] = ok ? (float)(E[i] * inv) : 0.0f;
+    }
+}
+
+cudaError_t launch_ransac_fit(const RansacParams& p, int batch, cudaStream_t stream) {
+    dim3 grid((p.H + FIT_THREADS - 1) / FIT_THREADS, batch);
+    ransac_fit_kernel<<<grid, FIT_THREADS, 0, stream>>>(p);
+    return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------ score (fp32)
+constexpr int SCORE_THREADS = 128;   // hypotheses per CTA
+constexpr int SCORE_CHUNK = 256;     // correspondences resident in shared memory per CTA
+int ransac_score_chunk_rows() { return SCORE_CHUNK; }
+
+__global__ void __launch_bounds__(SCORE_THREADS) ransac_score_kernel(const RansacParams p) {
+    __shared__ alignas(128) float4 corr[SCORE_CHUNK];
+    __shared__ alignas(8) uint64_t bar;
+    const int b = blockIdx.z, chunk = blockIdx.y;
+    const int h = blockIdx.x * SCORE_THREADS + threadIdx.x;
+    const int M = p.m_count ? min(p.m_count[b], p.n_max) : p.m;
+    const int r0 = chunk * SCORE_CHUNK;
+    const int rows = max(0, min(SCORE_CHUNK, M - r0));
+    const size_t oc = ((size_t)b * p.chunks + chunk) * p.H;
+
+    if (threadIdx.x == 0) {
+        mbar_init(&bar, 1);
+        fence_mbar_init();
+    }
+    __syncthreads();
+    if (rows > 0 && threadIdx.x == 0) {
+        mbar_arrive_expect_tx(&bar, (uint32_t)rows * 16u);
+        tma_load_1d(corr, p.corr32 + (size_t)b * p.n_max + r0, (uint32_t)rows * 16u, &bar);
+    }
+    float e[9];
+    const bool live = h < p.H;
+#pragma unroll
+    for (int i = 0; i < 9; ++i) e[i] = live ? p.E32[((size_t)b * 9 + i) * p.H + h] : 0.0f;
+
+    int cnt = 0, unc = 0;
+    float sse = 0.0f;
+    if (rows > 0) {
+        mbar_wait(&bar, 0);
+        const float thr2 = (float)(p.thr * p.thr);
+        const float band = p.band_rel * thr2;
+#pragma unroll 4
+        for (int j = 0; j < rows; ++j) {
+            const float4 c = corr[j];  // (x, y, u, v): x = src (last), u = dst (curr)
+            const float f0 = fmaf(e[0], c.x, fmaf(e[1], c.y, e[2]));
+            const float f1 = fmaf(e[3], c.x, fmaf(e[4], c.y, e[5]));
+            const float f2 = fmaf(e[6], c.x, fmaf(e[7], c.y, e[8]));
+            const float g0 = fmaf(e[0], c.z, fmaf(e[3], c.w, e[6]));
+            const float g1 = fmaf(e[1], c.z, fmaf(e[4], c.w, e[7]));
+            const float num = fmaf(c.z, f0, fmaf(c.w, f1, f2));
+            const float den = fmaf(f0, f0, fmaf(f1, f1, fmaf(g0, g0, g1 * g1)));
+            const float n2 = num * num;
+            const float t = fmaf(-thr2, den, n2);     // r < thr  <=>  num^2 - thr^2 den < 0
+            cnt += (t < 0.0f) ? 1 : 0;
+            unc += (fabsf(t) <= band * den) ? 1 : 0;
+            sse = fmaf(n2, __frcp_rn(den), sse);
+        }
+    }
+    if (live) {
+        p.part_cnt[oc + h] = make_int2(cnt, unc);
+        p.part_sse[oc + h] = sse;
+    }
+}
+
+cudaError_t launch_ransac_score(const RansacParams& p, int batch, cudaStream_t stream) {
+    dim3 grid((p.H + SCORE_THREADS - 1) / SCORE_THREADS, p.chunks, batch);
+    ransac_score_kernel<<<grid, SCORE_THREADS, 0, stream>>>(p);
+    return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------ reduce + candidates
+constexpr int REDUCE_THREADS = 1024;
+
+__global__ void __launch_bounds__(REDUCE_THREADS) ransac_reduce_kernel(const RansacParams p) {
+    __shared__ int s_red[32];
+    __shared__ int s_lb;
+    __shared__ int s_ncand;
+    const int b = blockIdx.x, tid = threadIdx.x;
+    const int M = p.m_count ? min(p.m_count[b], p.n_max) : p.m;
+    const int nchunks = min(p.chunks, (M + p.chunk - 1) / p.chunk);
+    const size_t oh = (size_t)b * p.H;
+    int lb = -1;
+    for (int h = tid; h < p.H; h += REDUCE_THREADS) {
+        int c = 0, u = 0;
+        float s = 0.0f;
+        for (int k = 0; k < nchunks; ++k) {
+            const size_t o = ((size_t)b * p.chunks + k) * p.H + h;
+            const int2 v = p.part_cnt[o];
+            c += v.x;
+            u += v.y;
+            s += p.part_sse[o];
+        }
+        const bool ok = p.valid[oh + h] != 0;
+        p.counts[oh + h] = ok ? c : -1;
+        p.band[oh + h] = ok ? u : 0;
+        p.sse32[oh + h] = ok ? s : __int_as_float(0x7f800000);
+        if (ok) lb = max(lb, c - u);
+    }
+#pragma unroll
+    for (int m = 16; m > 0; m >>= 1) lb = max(lb, __shfl_xor_sync(0xffffffffu, lb, m));
+    if ((tid & 31) == 0) s_red[tid >> 5] = lb;
+    if (tid == 0) s_ncand = 0;
+    __syncthreads();
+    if (tid < 32) {
+        int v = s_red[tid];
+#pragma unroll
+        for (int m = 16; m > 0; m >>= 1) v = max(v, __shfl_xor_sync(0xffffffffu, v, m));
+        if (tid == 0) s_lb = v;
+    }
+    __syncthreads();
+    lb = s_lb;
+    for (int h = tid; h < p.H; h += REDUCE_THREADS) {
+        const int c = p.counts[oh + h];
+        if (c >= 0 && c + p.band[oh + h] >= lb) {
+            const int slot = atomicAdd(&s_ncand, 1);
+            p.cand[oh + slot] = h;
+        }
+    }
+    __syncthreads();
+    if (tid == 0) p.n_cand[b] = s_ncand;
+}
+
+cudaError_t launch_ransac_reduce(const RansacParams& p, int batch, cudaStream_t stream) {
+    ransac_reduce_kernel<<<batch, REDUCE_THREADS, 0, stream>>>(p);
+    return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------ rescore (fp64)
+constexpr int RESCORE_THREADS = 256;
+
+template <int THREADS>
+__device__ __forceinline__ double block_sum_f64(double v, double* s_buf) {
+    v = warp_sum_f64(v);
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) s_buf[threadIdx.x >> 5] = v;
+    __syncthreads();
+    double t = 0.0;
+#pragma unroll
+    for (int w = 0; w < THREADS / 32; ++w) t += s_buf[w];
+    return t;
+}
+
+__global__ void __launch_bounds__(RESCORE_THREADS) ransac_rescore_kernel(const RansacParams p) {
+    __shared__ double s_buf[RESCORE_THREADS / 32];
+    const int b = blockIdx.y;
+    const int M = p.m_count ? min(p.m_count[b], p.n_max) : p.m;
+    const int ncand = p.n_cand[b];
+    const size_t ob = (size_t)b * p.n_max, oh = (size_t)b * p.H;
+    const double2* src = reinterpret_cast<const double2*>(p.src) + ob;
+    const double2* dst = reinterpret_cast<const double2*>(p.dst) + ob;
+    for (int ci = blockIdx.x; ci < ncand; ci += gridDim.x) {
+        const int h = p.cand[oh + ci];
+        double E[9];
+#pragma unroll
+        for (int i = 0; i < 9; ++i) E[i] = p.E64[(oh + h) * 9 + i];
+        double cnt = 0.0, sse = 0.0;
+        for (int m = threadIdx.x; m < M; m += RESCORE_THREADS) {
+            const double2 s = src[m], d = dst[m];
+            const double r = sampson_residual(E, s.x, s.y, d.x, d.y);
+            cnt += (r < p.thr) ? 1.0 : 0.0;
+            sse = fma(r, r, sse);
+        }
+        cnt = block_sum_f64<RESCORE_THREADS>(cnt, s_buf);
+        sse = block_sum_f64<RESCORE_THREADS>(sse, s_buf);
+        if (threadIdx.x == 0) {
+            p.cand_cnt[oh + h] = (int)cnt;
+            p.cand_sse[oh + h] = sse;
+            p.counts[oh + h] = (int)cnt;  // candidates report their exact count
+        }
+    }
+}
+
+cudaError_t launch_ransac_rescore(const RansacParams& p, int batch, cudaStream_t stream) {
+    const int gx = batch >= 148 ? 4 : (p.H < 592 ? p.H : 592);
+    dim3 grid(gx, batch);
+    ransac_rescore_kernel<<<grid, RESCORE_THREADS, 0, stream>>>(p);
+    return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------ select + mask + refit
+constexpr int REFIT_THREADS = 256;
+
+// Smallest-eigenvalue eigenvector of a symmetric 9x9 matrix by parallel-order cyclic Jacobi on one warp.
+// G and V live in shared memory; each round applies four disjoint rotations (round-robin tournament).
+__device__ void jacobi_eig9_warp(double (*G)[9], double (*V)[9], double* cs /*[8]*/, double (&out)[9]) {
+    const int lane = threadIdx.x & 31;
+    for (int i = lane; i < 81; i += 32) V[i / 9][i % 9] = (i / 9 == i % 9) ? 1.0 : 0.0;
+    __syncwarp();
+    for (int sweep = 0; sweep < 30; ++sweep) {
+        double off = 0.0, dg = 0.0;
+        for (int i = lane; i < 81; i += 32) {
+            const int r = i / 9, c = i % 9;
+            const double g = G[r][c];
+            if (r == c) dg = fma(g, g, dg); else off = fma(g, g, off);
+        }
+        off = warp_sum_f64(off);
+        dg = warp_sum_f64(dg);
+        if (!(off > 1e-30 * dg)) break;
+        for (int round = 0; round < 9; ++round) {
+            if (lane < 4) {
+                const int k = lane + 1;
+                const int pp = (round + k) % 9, qq = (round + 9 - k) % 9;
+                const double app = G[pp][pp], aqq = G[qq][qq], apq = G[pp][qq];
+                double c = 1.0, s = 0.0;
+                if (apq != 0.0) {
+                    const double theta = (aqq - app) / (2.0 * apq);
+                    const double t = copysign(1.0, theta) / (fabs(theta) + sqrt(fma(theta, theta, 1.0)));
+                    c = rsqrt(fma(t, t, 1.0));
+                    s = t * c;
+                }
+                cs[2 * lane] = c;
+                cs[2 * lane + 1] = s;
+            }
+            __syncwarp();
+            // columns: G <- G J, V <- V J      (72 element-pair tasks)
+            for (int task = lane; task < 72; task += 32) {
+                const int which = task / 36, rem = task % 36;
+                const int k = rem / 9, i = rem % 9;
+                const int pp = (round + k + 1) % 9, qq = (round + 9 - (k + 1)) % 9;
+                const double c = cs[2 * k], s = cs[2 * k + 1];
+                double(*Mx)[9] = which ? V : G;
+                const double a = Mx[i][pp], bq = Mx[i][qq];
+                Mx[i][pp] = c * a - s * bq;
+                Mx[i][qq] = s * a + c * bq;
+            }
+            __syncwarp();
+            // rows: G <- J^T G
+            for (int task = lane; task < 36; task += 32) {
+                const int k = task / 9, j = task % 9;
+                const int pp = (round + k + 1) % 9, qq = (round + 9 - (k + 1)) % 9;
+                const double c = cs[2 * k], s = cs[2 * k + 1];
+                const double a = G[pp][j], bq = G[qq][j];
+                G[pp][j] = c * a - s * bq;
+                G[qq][j] = s * a + c * bq;
+            }
+            __syncwarp();
+        }
+    }
+    int best = 0;
+    double lam = G[0][0];
+    for (int i = 1; i < 9; ++i)
+        if (G[i][i] < lam) { lam = G[i][i]; best = i; }
+    for (int i = 0; i < 9; ++i) out[i] = V[i][best];
+}
+
+__global__ void __launch_bounds__(REFIT_THREADS) ransac_refit_kernel(const RansacParams p) {
+    __shared__ double s_buf[REFIT_THREADS / 32];
+    __shared__ double s_G[9][9], s_V[9][9], s_cs[8];
+    __shared__ double s_acc[45][REFIT_THREADS / 32];
+    __shared__ int s_cnt[REFIT_THREADS / 32], s_bc[REFIT_THREADS / 32], s_bh[REFIT_THREADS / 32];
+    __shared__ double s_bs[REFIT_THREADS / 32];
+    __shared__ int s_best;
+    const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int M = p.m_count ? min(p.m_count[b], p.n_max) : p.m;
+    const size_t ob = (size_t)b * p.n_max, oh = (size_t)b * p.H;
+    const int ncand = p.n_cand[b];
+    const double qnan = __longlong_as_double(0x7ff8000000000000LL);
+
+    // ---- best = (max count, min sum r^2, earliest) over the exactly re-scored candidates
+    int bc = -1, bh = 0x7fffffff;
+    double bs = 0.0;
+    for (int ci = tid; ci < ncand; ci += REFIT_THREADS) {
+        const int h = p.cand[oh + ci];
+        const int c = p.cand_cnt[oh + h];
+        const double s = p.cand_sse[oh + h];
+        // NaN sums never win a tie (python: `rss < best_rss` is False)
+        const bool better = (c > bc) || (c == bc && (s < bs || (s == bs && h < bh)));
+        if (better) { bc = c; bs = s; bh = h; }
+    }
+#pragma unroll
+    for (int m = 16; m > 0; m >>= 1) {
+        const int oc = __shfl_xor_sync(0xffffffffu, bc, m);
+        const int ohh = __shfl_xor_sync(0xffffffffu, bh, m);
+        const double os = shfl_xor_f64(bs, m);
+        if ((oc > bc) || (oc == bc && (os < bs || (os == bs && ohh < bh)))) { bc = oc; bs = os; bh = ohh; }
+    }
+    if (lane == 0) { s_bc[warp] = bc; s_bs[warp] = bs; s_bh[warp] = bh; }
+    __syncthreads();
+    if (tid == 0) {
+        for (int w = 1; w < REFIT_THREADS / 32; ++w) {
+            const int oc = s_bc[w], ohh = s_bh[w];
+            const double os = s_bs[w];
+            if ((oc > bc) || (oc == bc && (os < bs || (os == bs && ohh < bh)))) { bc = oc; bs = os; bh = ohh; }
+        }
+        s_best = (bc >= 0) ? bh : -1;
+        p.best[b] = s_best;
+        p.best_sse[b] = (bc >= 0) ? bs : qnan;
+    }
+    __syncthreads();
+    const int best = s_best;
+    if (best < 0) {  // no valid hypothesis (fewer than 9 correspondences or every fit degenerate)
+        for (int m = tid; m < M; m += REFIT_THREADS) p.mask[ob + m] = 0;
+        if (tid == 0) {
+            p.n_inl[b] = 0;
+            p.status[b] = (M <= 8) ? 1 : 2;
+            for (int i = 0; i < 9; ++i) { p.E[b * 9 + i] = qnan; p.E_best[b * 9 + i] = qnan; }
+            for (int i = 0; i < 16; ++i) p.Rt[b * 16 + i] = qnan;
+        }
+        return;
+    }
+    double Eb[9];
+#pragma unroll
+    for (int i = 0; i < 9; ++i) Eb[i] = p.E64[(oh + best) * 9 + i];
+
+    // ---- pre-refit inlier mask (fp64), ordered compaction, centroid sums
+    const double2* src = reinterpret_cast<const double2*>(p.src) + ob;
+    const double2* dst = reinterpret_cast<const double2*>(p.dst) + ob;
+    const int per = (M + REFIT_THREADS - 1) / REFIT_THREADS;
+    const int lo = min(M, tid * per), hi = min(M, lo + per);
+    int cnt = 0;
+    double sum[4] = {0.0, 0.0, 0.0, 0.0};
+    for (int m = lo; m < hi; ++m) {
+        const double2 s = src[m], d = dst[m];
+        const bool in = sampson_residual(Eb, s.x, s.y, d.x, d.y) < p.thr;
+        p.mask[ob + m] = in ? 1 : 0;
+        if (in) { ++cnt; sum[0] += s.x; sum[1] += s.y; sum[2] += d.x; sum[3] += d.y; }
+    }
+    int incl = cnt;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const int v = __shfl_up_sync(0xffffffffu, incl, d);
+        if (lane >= d) incl += v;
+    }
+    if (lane == 31) s_cnt[warp] = incl;
+    __syncthreads();
+    int base = 0, total = 0;
+#pragma unroll
+    for (int w = 0; w < REFIT_THREADS / 32; ++w) {
+        if (w < warp) base += s_cnt[w];
+        total += s_cnt[w];
+    }
+    {
+        int pos = base + incl - cnt;
+        const int fq = p.pair_q ? p.pair_q[b] : b;
+        const int ft = p.pair_t ? p.pair_t[b] : b;
+        const double2* kq = p.kps_q ? reinterpret_cast<const double2*>(p.kps_q) + (size_t)fq * p.n_max : nullptr;
+        const double2* kt = p.kps_t ? reinterpret_cast<const double2*>(p.kps_t) + (size_t)ft * p.n_max : nullptr;
+        for (int m = lo; m < hi; ++m) {
+            if (!p.mask[ob + m]) continue;
+            p.inl_idx[ob + pos] = m;
+            if (kq) {
+                reinterpret_cast<double2*>(p.pix_curr)[ob + pos] = kq[p.qidx[ob + m]];
+                reinterpret_cast<double2*>(p.pix_last)[ob + pos] = kt[p.tidx[ob + m]];
+            }
+            ++pos;
+        }
+    }
+    if (tid == 0) {
+        p.n_inl[b] = total;
+        p.status[b] = 0;
+#pragma unroll
+        for (int i = 0; i < 9; ++i) p.E_best[b * 9 + i] = Eb[i];
+    }
+    double E[9];
+    if (total < 8) {  // skimage's refit would raise; report the un-refit model
+#pragma unroll
+        for (int i = 0; i < 9; ++i) E[i] = Eb[i];
+    } else {
+        // ---- Hartley normalisation of the inlier set
+        double c[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) c[k] = block_sum_f64<REFIT_THREADS>(sum[k], s_buf) / (double)total;
+        double qs = 0.0, qd = 0.0;
+        for (int m = lo; m < hi; ++m) {
+            if (!p.mask[ob + m]) continue;
+            const double2 s = src[m], d = dst[m];
+            qs = fma(s.x - c[0], s.x - c[0], qs); qs = fma(s.y - c[1], s.y - c[1], qs);
+            qd = fma(d.x - c[2], d.x - c[2], qd); qd = fma(d.y - c[3], d.y - c[3], qd);
+        }
+        qs = block_sum_f64<REFIT_THREADS>(qs, s_buf);
+        qd = block_sum_f64<REFIT_THREADS>(qd, s_buf);
+        const double ss = 1.4142135623730951 / sqrt(qs / (double)total);
+        const double sd = 1.4142135623730951 / sqrt(qd / (double)total);
+        // ---- A^T A (upper triangle, 45 sums) in fp64
+        double acc[45];
+#pragma unroll
+        for (int i = 0; i < 45; ++i) acc[i] = 0.0;
+        for (int m = lo; m < hi; ++m) {
+            if (!p.mask[ob + m]) continue;
+            const double2 s = src[m], d = dst[m];
+            const double xs = ss * s.x - ss * c[0], ys = ss * s.y - ss * c[1];
+            const double xd = sd * d.x - sd * c[2], yd = sd * d.y - sd * c[3];
+            const double a[9] = {xd * xs, xd * ys, xd, yd * xs, yd * ys, yd, xs, ys, 1.0};
+            int t = 0;
+#pragma unroll
+            for (int i = 0; i < 9; ++i)
+#pragma unroll
+                for (int j = i; j < 9; ++j) { acc[t] = fma(a[i], a[j], acc[t]); ++t; }
+        }
+#pragma unroll
+        for (int i = 0; i < 45; ++i) {
+            const double v = warp_sum_f64(acc[i]);
+            if (lane == 0) s_acc[i][warp] = v;
+        }
+        __syncthreads();
+        if (tid < 45) {
+            double v = 0.0;
+#pragma unroll
+            for (int w = 0; w < REFIT_THREADS / 32; ++w) v += s_acc[tid][w];
+            // unpack upper-triangle index tid -> (i, j)
+            int i = 0, rem = tid;
+            while (rem >= 9 - i) { rem -= 9 - i; ++i; }
+            const int j = i + rem;
+            s_G[i][j] = v;
+            s_G[j][i] = v;
+        }
+        __syncthreads();
+        if (warp == 0) {
+            double n[9];
+            jacobi_eig9_warp(s_G, s_V, s_cs, n);
+            if (lane == 0) {
+                double En[9];
+                essential_project(n, En);
+                essential_denormalise(En, ss, c[0], c[1], sd, c[2], c[3], E);
+                bool fin = true;
+#pragma unroll
+                for (int i = 0; i < 9; ++i) fin = fin && isfinite(E[i]);
+                if (!fin) {
+#pragma unroll
+                    for (int i = 0; i < 9; ++i) E[i] = Eb[i];
+                }
+            }
+        }
+    }
+    if (tid == 0) {
+        double Rt[16];
+        extract_rt(E, Rt);
+#pragma unroll
+        for (int i = 0; i < 9; ++i) p.E[b * 9 + i] = E[i];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) p.Rt[b * 16 + i] = Rt[i];
+    }
+}
+
+cudaError_t launch_ransac_refit(const RansacParams& p, int batch, cudaStream_t stream) {
+    ransac_refit_kernel<<<batch, REFIT_THREADS, 0, stream>>>(p);
+    return cudaGetLastError();
+}
+
+}  // namespace tvg

@@ -1,0 +1,146 @@
+// Internal launch interface between the C-ABI (c_api.cu) and the kernels.  Every array has a leading
+// pair ("batch") dimension with stride n_max rows (or H hypotheses); per-pair valid counts live on the
+// device so the whole pipeline runs without host synchronisation.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace tvg {
+
+// ---------------------------------------------------------------- matcher (hamming_knn2.cu)
+struct KnnParams {
+    const uint8_t* q_base;     // query descriptor pool  u8[frames][n_max][32]
+    const uint8_t* t_base;     // train descriptor pool  u8[frames][n_max][32]
+    const int32_t* pair_q;     // frame index of the query side per pair (NULL -> b)
+    const int32_t* pair_t;     // frame index of the train side per pair (NULL -> b)
+    const int32_t* q_count;    // valid rows per FRAME (NULL -> nq)
+    const int32_t* t_count;    // valid rows per FRAME (NULL -> nt)
+    int n_max, nq, nt;
+    int splits, rows_per_split;
+    uint2* partial;            // [batch][n_max][splits] packed top-2 keys
+    unsigned int* tile_counters;  // [batch][qtiles], zero on entry, zero on exit
+    int32_t* idx;              // [batch][n_max][2]
+    int32_t* dist;             // [batch][n_max][2]
+    uint8_t* keep;             // [batch][n_max] ratio-test flag (may be NULL)
+    double ratio;
+};
+cudaError_t launch_knn2(const KnnParams& p, int batch, int r, int variant, cudaStream_t stream);
+int knn2_block_queries(int r);
+
+// ---------------------------------------------------------------- ratio compaction (compact.cu)
+struct CompactParams {
+    const uint8_t* keep;       // [batch][n_max]
+    const int32_t* idx;        // [batch][n_max][2]
+    const int32_t* pair_q;
+    const int32_t* pair_t;
+    const int32_t* q_count;    // per frame
+    int n_max, nq;
+    const double* kps_q;       // keypoint pool f64[frames][n_max][2] (NULL -> no gather)
+    const double* kps_t;
+    double kinv[9];
+    int32_t* qidx;             // [batch][n_max]
+    int32_t* tidx;             // [batch][n_max]
+    int32_t* m_count;          // [batch]
+    double* src;               // [batch][n_max][2]  K-normalised LAST (train) points
+    double* dst;               // [batch][n_max][2]  K-normalised CURR (query) points
+    float4* corr32;            // [batch][n_max]     (src.x, src.y, dst.x, dst.y)
+};
+cudaError_t launch_compact(const CompactParams& p, int batch, cudaStream_t stream);
+
+// ---------------------------------------------------------------- RANSAC (ransac.cu)
+struct RansacParams {
+    const double* src;         // [batch][n_max][2]
+    const double* dst;         // [batch][n_max][2]
+    const float4* corr32;      // [batch][n_max]
+    const int32_t* m_count;    // [batch] (NULL -> m)
+    int n_max, m, H;
+    const int32_t* samples;    // int32[.][H][8] explicit indices (NULL -> words)
+    const uint32_t* words;     // u32[.][H][8] random words, idx = (w*M)>>32, +1 mod M on clash
+    long long sample_stride;   // elements between pairs (0 = one table shared by all pairs)
+    int32_t* samples_out;      // [batch][H][8] indices actually used (may be NULL)
+    double thr;
+    float band_rel;            // fp32 uncertainty band, relative to thr^2*den
+    // outputs / scratch
+    double* E64;               // [batch][H][9]
+    float* E32;                // [batch][9][H]  Frobenius-normalised, SoA
+    int32_t* valid;            // [batch][H]
+    int chunks, chunk;         // correspondence chunks per pair, rows per chunk
+    int2* part_cnt;            // [batch][chunks][H] (count, band)
+    float* part_sse;           // [batch][chunks][H]
+    int32_t* counts;           // [batch][H]  (-1 = failed fit)
+    int32_t* band;             // [batch][H]
+    float* sse32;              // [batch][H]
+    int32_t* cand;             // [batch][H]
+    int32_t* n_cand;           // [batch]
+    double* cand_sse;          // [batch][H]  exact fp64 sum r^2 (indexed by hypothesis)
+    int32_t* cand_cnt;         // [batch][H]  exact fp64 count   (indexed by hypothesis)
+    // final
+    const int32_t* qidx;       // [batch][n_max]
+    const int32_t* tidx;
+    const int32_t* pair_q;
+    const int32_t* pair_t;
+    const double* kps_q;       // pixel keypoints pool (for the inlier gather; may be NULL)
+    const double* kps_t;
+    int32_t* best;             // [batch]
+    double* best_sse;          // [batch]
+    double* E_best;            // [batch][9]
+    uint8_t* mask;             // [batch][n_max]
+    int32_t* n_inl;            // [batch]
+    int32_t* inl_idx;          // [batch][n_max] match indices of the inliers, ascending
+    double* pix_last;          // [batch][n_max][2] pixel coords of inliers (last / train side)
+    double* pix_curr;          // [batch][n_max][2]
+    double* E;                 // [batch][9]  refit on the inliers
+    double* Rt;                // [batch][16]
+    int32_t* status;           // [batch] 0 ok, 1 = fewer than 9 correspondences
+};
+cudaError_t launch_ransac_fit(const RansacParams& p, int batch, cudaStream_t stream);
+cudaError_t launch_ransac_score(const RansacParams& p, int batch, cudaStream_t stream);
+cudaError_t launch_ransac_reduce(const RansacParams& p, int batch, cudaStream_t stream);
+cudaError_t launch_ransac_rescore(const RansacParams& p, int batch, cudaStream_t stream);
+cudaError_t launch_ransac_refit(const RansacParams& p, int batch, cudaStream_t stream);
+int ransac_score_chunk_rows();
+
+// ---------------------------------------------------------------- pose + triangulation (pose_tri.cu)
+struct PoseChainParams {
+    const double* Rt;          // [batch][16]
+    const int32_t* seq_off;    // [nseq+1] pair offsets of each sequence
+    const double* init_pose;   // [nseq][16] (NULL -> identity)
+    double* poses;             // [batch + nseq][16]  pose of pair b's LAST frame at [b + s], CURR at [b + s + 1]
+    double* pair_pinv;         // [batch][2][16] inv(last pose), inv(curr pose) per pair (may be NULL)
+};
+cudaError_t launch_pose_chain(const PoseChainParams& p, int nseq, cudaStream_t stream);
+
+struct TriParams {
+    const double* pix1;        // [batch][n_max][2] pixel coords in the first view
+    const double* pix2;
+    const int32_t* n_pts;      // [batch] (NULL -> n)
+    int n_max, n;
+    const double* P1;          // [batch] x 16 stride p_stride doubles: inverse pose of view 1
+    const double* P2;
+    long long p1_stride, p2_stride;  // doubles between pairs
+    double kinv[9];
+    double* points4d;          // [batch][n_max][4]
+    uint8_t* good;             // [batch][n_max]  z > 0   (may be NULL)
+};
+cudaError_t launch_triangulate(const TriParams& p, int batch, cudaStream_t stream);
+
+struct ExtractRtParams {
+    const double* E;           // [batch][9]
+    double* Rt;                // [batch][16]
+};
+cudaError_t launch_extract_rt(const ExtractRtParams& p, int batch, cudaStream_t stream);
+
+struct CheiralityParams {
+    const double* E;           // [batch][9]
+    const double* src;         // [batch][n_max][2] normalised
+    const double* dst;
+    const uint8_t* mask;       // [batch][n_max] (NULL -> all)
+    const int32_t* m_count;    // [batch] (NULL -> m)
+    int n_max, m;
+    int32_t* votes;            // [batch][4]
+    double* Rts;               // [batch][4][16]
+    int32_t* choice;           // [batch]
+};
+cudaError_t launch_cheirality(const CheiralityParams& p, int batch, cudaStream_t stream);
+
+}  // namespace tvg

@@ -1,0 +1,327 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the CPU oracle on identical seeded
+inputs.  Bars (BASELINE.json north_star): matcher indices/distances bit-exact; per-hypothesis inlier
+counts bit-exact except points within 1e-5 of the threshold; E within 1e-4 Frobenius after
+normalisation + sign alignment; triangulated points within 1e-4 relative."""
+import numpy as np
+import pytest
+import torch
+
+from openwork_b200 import synth
+from oracle import two_view as tv
+
+pytestmark = pytest.mark.gpu
+
+THR = 0.005
+BAND = 1e-5          # north star: counts exact except points within 1e-5 of the residual threshold
+E_TOL = 1e-4         # Frobenius, after normalisation and sign alignment
+X_TOL = 1e-4         # relative error of triangulated points
+K = synth.K_640x480
+
+
+@pytest.fixture(scope="module")
+def ops():
+    from openwork_b200 import ops as _ops
+    assert torch.cuda.is_available(), "GPU tests need a B200"
+    _ops.context(0)   # raises loudly if the extension is missing
+    return _ops
+
+
+def _fro_diff(A, B):
+    A = A / np.linalg.norm(A)
+    B = B / np.linalg.norm(B)
+    return min(np.linalg.norm(A - B), np.linalg.norm(A + B))
+
+
+# ------------------------------------------------------------------------------ matcher
+@pytest.mark.parametrize("nq,nt", [(1, 2), (5, 1), (7, 3), (33, 129), (500, 700), (2048, 2048), (1000, 4099),
+                                   (4100, 257)])
+def test_knn2_bit_exact(ops, nq, nt):
+    rng = np.random.default_rng(nq * 10007 + nt)
+    q = rng.integers(0, 256, (nq, 32), dtype=np.uint8)
+    t = rng.integers(0, 256, (nt, 32), dtype=np.uint8)
+    if nt > 40:   # forced exact ties: duplicated train rows and queries equal to train rows
+        d = rng.choice(nt, nt // 5, replace=False)
+        t[d] = t[rng.choice(nt, nt // 5, replace=False)]
+        qq = rng.choice(nq, max(1, nq // 7), replace=False)
+        q[qq] = t[rng.integers(0, nt, len(qq))]
+    idx, dist = ops.knn2_hamming256(q, t)
+    ri, rd = tv.knn2_cv2(q, t)
+    assert np.array_equal(dist.cpu().numpy(), rd)
+    assert np.array_equal(idx.cpu().numpy(), ri)
+    ni, nd = tv.knn2_numpy(q, t)
+    assert np.array_equal(idx.cpu().numpy(), ni) and np.array_equal(dist.cpu().numpy(), nd)
+
+
+def test_knn2_all_equal_descriptors(ops):
+    q = np.full((300, 32), 0xA5, dtype=np.uint8)
+    t = np.full((513, 32), 0xA5, dtype=np.uint8)
+    idx, dist, keep = ops.knn2_hamming256(q, t, return_keep=True)
+    assert (idx.cpu().numpy() == np.array([0, 1])).all() and (dist.cpu().numpy() == 0).all()
+    assert not keep.any()           # 0 < 0.75*0 is False
+
+
+def test_knn2_empty(ops):
+    q = np.zeros((0, 32), dtype=np.uint8)
+    t = np.zeros((10, 32), dtype=np.uint8)
+    idx, dist = ops.knn2_hamming256(q, t)
+    assert idx.shape == (0, 2)
+    idx, dist = ops.knn2_hamming256(t, q)
+    assert (idx.cpu().numpy() == -1).all() and (dist.cpu().numpy() == -1).all()
+
+
+@pytest.mark.parametrize("r,variant,ctas", [(2, 0, 6), (4, 0, 1), (4, 1, 6), (4, 2, 6), (8, 0, 4), (8, 1, 8),
+                                            (2, 1, 16), (2, 2, 3), (8, 2, 2)])
+def test_knn2_every_config_is_bit_identical(ops, r, variant, ctas):
+    q, t = synth.correlated_descriptors(3000, 2500, seed=r * 100 + variant * 10 + ctas)
+    t[100:200] = t[300:400]
+    ctx = ops.context(0)
+    try:
+        ctx.set_matcher_config(r, variant, ctas)
+        idx, dist, keep = ops.knn2_hamming256(q, t, return_keep=True)
+    finally:
+        ctx.set_matcher_config(4, 0, 6)
+    ri, rd = tv.knn2_cv2(q, t)
+    assert np.array_equal(idx.cpu().numpy(), ri) and np.array_equal(dist.cpu().numpy(), rd)
+    qi, ti = tv.ratio_filter(ri, rd)
+    assert np.array_equal(np.flatnonzero(keep.cpu().numpy()), qi)
+
+
+def test_knn2_8k_matches_cv2(ops):
+    q, t = synth.correlated_descriptors(8192, 8192, seed=3)
+    idx, dist = ops.knn2_hamming256(q, t)
+    ri, rd = tv.knn2_cv2(q, t)
+    assert np.array_equal(idx.cpu().numpy(), ri) and np.array_equal(dist.cpu().numpy(), rd)
+
+
+def test_knn2_batched_ragged(ops):
+    F, N = 5, 700
+    rng = np.random.default_rng(5)
+    des = rng.integers(0, 256, (F, N, 32), dtype=np.uint8)
+    cnt = np.array([700, 650, 3, 512, 699], dtype=np.int32)
+    pq = np.array([1, 2, 3, 4, 0, 2], dtype=np.int32)
+    pt = np.array([0, 1, 2, 3, 4, 2], dtype=np.int32)
+    idx, dist, keep = ops.knn2_hamming256_batched(des, pq, pt, frame_count=cnt)
+    idx, dist = idx.cpu().numpy(), dist.cpu().numpy()
+    for b in range(len(pq)):
+        nq, nt = cnt[pq[b]], cnt[pt[b]]
+        ri, rd = tv.knn2_numpy(des[pq[b], :nq], des[pt[b], :nt])
+        assert np.array_equal(idx[b, :nq], ri) and np.array_equal(dist[b, :nq], rd)
+
+
+# ------------------------------------------------------------------------------ ratio + gather
+def test_ratio_compact_matches_reference_loop(ops):
+    lk, ld, ck, cd = synth.make_pair(1500, 77, forced_ties=40)
+    idx, dist, keep = ops.knn2_hamming256(cd, ld, return_keep=True)
+    out = ops.ratio_compact(idx, keep, ck, lk, K)
+    mk, i1, i2 = tv.match_points(ck, cd, lk, ld)
+    assert out["M"] == len(i1)
+    assert np.array_equal(out["qidx"].cpu().numpy(), i1) and np.array_equal(out["tidx"].cpu().numpy(), i2)
+    np.testing.assert_allclose(out["dst"].cpu().numpy(), tv.normalize(K, mk[:, 0]), rtol=0, atol=1e-14)
+    np.testing.assert_allclose(out["src"].cpu().numpy(), tv.normalize(K, mk[:, 1]), rtol=0, atol=1e-14)
+
+
+# ------------------------------------------------------------------------------ RANSAC
+def _pair_correspondences(n, seed):
+    lk, ld, ck, cd = synth.make_pair(n, seed)
+    mk, i1, i2 = tv.match_points(ck, cd, lk, ld)
+    return tv.normalize(K, mk[:, 1]), tv.normalize(K, mk[:, 0]), (lk, ck, i1, i2)
+
+
+@pytest.mark.parametrize("n,H,seed,use_words", [(2048, 512, 11, False), (700, 300, 12, True), (2048, 1024, 13, True)])
+def test_ransac_counts_best_mask_E(ops, n, H, seed, use_words):
+    src, dst, _ = _pair_correspondences(n, seed)
+    M = len(src)
+    if use_words:
+        words = synth.sample_words(H, seed)
+        samples = synth.samples_from_words(words, M)
+        g = ops.ransac_essential(src, dst, words=words, residual_threshold=THR, return_models=True)
+        assert np.array_equal(g["samples"].cpu().numpy(), samples)      # device mapping == oracle mapping
+    else:
+        samples = synth.sample_table(M, H, seed)
+        g = ops.ransac_essential(src, dst, samples=samples, residual_threshold=THR, return_models=True)
+    ref = tv.ransac_essential(src, dst, samples, THR, return_models=True)
+    cond = tv.sample_conditioning(src, dst, samples)
+    ok = cond > 1e-7                      # near-degenerate 8-samples: LAPACK's null vector is arbitrary
+    counts = g["counts"].cpu().numpy()
+    models = g["models"].cpu().numpy()
+    n_checked = n_exact = 0
+    for h in range(H):
+        if not ok[h] or ref["counts"][h] < 0:
+            continue
+        r = tv.essential_residuals(ref["models"][h], src, dst)
+        band = np.abs(r - THR) < BAND
+        lo = ref["counts"][h] - int(np.sum(band & (r < THR)))
+        hi = ref["counts"][h] + int(np.sum(band & (r >= THR)))
+        assert lo <= counts[h] <= hi, (h, counts[h], ref["counts"][h], lo, hi)
+        n_exact += counts[h] == ref["counts"][h]
+        n_checked += 1
+        assert _fro_diff(models[h], ref["models"][h]) < E_TOL
+    assert n_checked >= 0.95 * H
+    assert n_exact >= 0.98 * n_checked
+    assert g["best"] == ref["best"]
+    assert g["n_inl"] == int(ref["mask"].sum())
+    rb = tv.essential_residuals(ref["E_best"], src, dst)
+    differs = g["mask"].cpu().numpy() != ref["mask"]
+    assert not (differs & (np.abs(rb - THR) >= BAND)).any()
+    assert _fro_diff(g["E"].cpu().numpy(), ref["E"]) < E_TOL
+    assert _fro_diff(g["E_best"].cpu().numpy(), ref["E_best"]) < E_TOL
+    np.testing.assert_allclose(g["Rt"].cpu().numpy(), tv.extract_Rt(ref["E"]), atol=1e-6)
+
+
+def test_ransac_noise_free_scene_all_inliers(ops):
+    """Closed form: noise-free correspondences of E = [t]x R -> every hypothesis explains every point."""
+    rng = np.random.default_rng(0)
+    n = 400
+    X = np.stack([rng.uniform(-4, 4, n), rng.uniform(-3, 3, n), rng.uniform(4, 20, n)], axis=1)
+    R = synth._small_rotation(rng, 0.02)
+    t = np.array([0.05, -0.02, -0.5])
+    x1 = X[:, :2] / X[:, 2:]
+    Xc = X @ R.T + t
+    x2 = Xc[:, :2] / Xc[:, 2:]
+    samples = synth.sample_table(n, 64, 1)
+    g = ops.ransac_essential(x1, x2, samples=samples)
+    counts = g["counts"].cpu().numpy()
+    assert (counts == n).all()
+    assert g["n_cand"] == 64                      # all tie on count -> all re-scored in fp64
+    ref = tv.ransac_essential(x1, x2, samples)
+    tx = np.array([[0, -t[2], t[1]], [t[2], 0, -t[0]], [-t[1], t[0], 0]])
+    assert _fro_diff(g["E"].cpu().numpy(), tx @ R) < 1e-6
+    assert _fro_diff(g["E"].cpu().numpy(), ref["E"]) < E_TOL
+
+
+def test_ransac_too_few_correspondences_raises(ops):
+    src = np.random.default_rng(0).normal(size=(8, 2))
+    with pytest.raises(ValueError):
+        ops.ransac_essential(src, src, samples=np.arange(8, dtype=np.int32)[None])
+
+
+# ------------------------------------------------------------------------------ pose + triangulation
+def test_extract_rt_matches_reference_conventions(ops):
+    rng = np.random.default_rng(4)
+    Es, refs = [], []
+    for _ in range(64):
+        R = synth._small_rotation(rng, 0.3)
+        t = rng.normal(size=3)
+        tx = np.array([[0, -t[2], t[1]], [t[2], 0, -t[0]], [-t[1], t[0], 0]])
+        E = (tx @ R) * rng.uniform(0.1, 10) * rng.choice([-1, 1])
+        Es.append(E)
+        refs.append(tv.extract_Rt(E))
+    got = ops.extract_rt(np.stack(Es)).cpu().numpy()
+    np.testing.assert_allclose(got, np.stack(refs), atol=1e-9)
+
+
+def test_triangulate_matches_reference(ops):
+    src, dst, (lk, ck, i1, i2) = _pair_correspondences(2048, 21)
+    samples = synth.sample_table(len(src), 256, 3)
+    ref = tv.ransac_essential(src, dst, samples, THR)
+    inl = ref["mask"]
+    Rt = tv.extract_Rt(ref["E"])
+    pose0 = np.eye(4)
+    pose0[:3, 3] = [0.3, -0.2, 1.5]
+    pose1 = Rt @ pose0
+    p1, p2 = lk[i2][inl], ck[i1][inl]
+    Xr = tv.triangulate(p1, p2, pose0, pose1, K)
+    X, good = ops.triangulate(p1, p2, pose0, pose1, K, return_good=True)
+    X = X.cpu().numpy()
+    rel = np.linalg.norm(X[:, :3] - Xr[:, :3], axis=1) / np.maximum(np.linalg.norm(Xr[:, :3], axis=1), 1e-12)
+    assert rel.max() < X_TOL, rel.max()
+    assert (X[:, 3] == 1.0).all()
+    gr = tv.check_points(Xr)
+    safe = np.abs(Xr[:, 2]) > 1e-4 * np.linalg.norm(Xr[:, :3], axis=1)
+    assert np.array_equal(good.cpu().numpy()[safe], gr[safe])
+
+
+def test_cheirality_votes_match_oracle(ops):
+    src, dst, _ = _pair_correspondences(1200, 31)
+    samples = synth.sample_table(len(src), 128, 3)
+    ref = tv.ransac_essential(src, dst, samples, THR)
+    votes, Rts, choice = ops.cheirality(ref["E"], src, dst, mask=ref["mask"])
+    rv, rRts = tv.cheirality_votes(ref["E"], src[ref["mask"]], dst[ref["mask"]])
+    assert choice == int(np.argmax(rv))
+    assert np.abs(votes.cpu().numpy() - rv).max() <= 2      # points at |z| ~ 0 may flip
+    np.testing.assert_allclose(Rts.cpu().numpy()[choice], rRts[int(np.argmax(rv))], atol=1e-8)
+
+
+# ------------------------------------------------------------------------------ whole pairs
+def _check_sequence(ops, out, frames, words, H, seq_pairs, pose0=None):
+    pose = np.eye(4) if pose0 is None else pose0
+    for b, (fl, fc) in enumerate(seq_pairs):
+        (lk, ld), (ck, cd) = frames[fl], frames[fc]
+        ref = tv.process_pair(lk, ld, ck, cd, pose, K, words=words, residual_threshold=THR)
+        M = len(ref["idx1"])
+        assert int(out["m_count"][b]) == M
+        assert np.array_equal(out["qidx"][b, :M], ref["idx1"]) and np.array_equal(out["tidx"][b, :M], ref["idx2"])
+        assert int(out["best"][b]) == ref["ransac"]["best"]
+        n_in = int(ref["inliers"].sum())
+        assert int(out["n_inl"][b]) == n_in
+        assert np.array_equal(out["mask"][b, :M].astype(bool), ref["inliers"])
+        assert _fro_diff(out["E"][b], ref["E"]) < E_TOL
+        np.testing.assert_allclose(out["Rt"][b], ref["Rt"], atol=1e-6)
+        np.testing.assert_allclose(out["poses"][b + 1], ref["curr_pose"], atol=1e-5)
+        X, Xr = out["points4d"][b, :n_in], ref["points4d"]
+        rel = np.linalg.norm(X[:, :3] - Xr[:, :3], axis=1) / np.maximum(np.linalg.norm(Xr[:, :3], axis=1), 1e-12)
+        # the GPU triangulates with ITS pose chain; pose differences ~1e-9 feed through
+        assert np.median(rel) < X_TOL and (rel < 1e-3).mean() > 0.99
+        pose = ref["curr_pose"]
+
+
+ALL_OUT = ("idx", "dist", "qidx", "tidx", "m_count", "E", "E_best", "best", "counts", "mask", "n_inl", "inl_idx",
+           "Rt", "poses", "points4d", "good", "status")
+
+
+def test_pairs_device_sequence_matches_oracle(ops):
+    F, N, H = 5, 1024, 256
+    frames, _ = synth.make_sequence(F, N, seed=99)
+    des = np.stack([f[1] for f in frames])
+    kps = np.stack([f[0] for f in frames])
+    words = synth.sample_words(H, 7)
+    out = ops.process_pairs_device(torch.from_numpy(des).cuda(), torch.from_numpy(kps).cuda(), K, words=words,
+                                   residual_threshold=THR, outputs=ALL_OUT)
+    out = {k: v.cpu().numpy() for k, v in out.items() if k != "_keepalive"}
+    assert (out["status"] == 0).all()
+    _check_sequence(ops, out, frames, words, H, [(i, i + 1) for i in range(F - 1)])
+
+
+def test_pairs_host_entry_matches_device_entry(ops):
+    F, N, H = 4, 512, 128
+    frames, _ = synth.make_sequence(F, N, seed=5)
+    des = np.stack([f[1] for f in frames])
+    kps = np.stack([f[0] for f in frames])
+    words = synth.sample_words(H, 8)
+    outs = ("m_count", "E", "n_inl", "Rt", "poses", "points4d", "good", "status", "best")
+    dev = ops.process_pairs_device(torch.from_numpy(des).cuda(), torch.from_numpy(kps).cuda(), K, words=words,
+                                   outputs=outs)
+    host, h2d, d2h = ops.process_pairs_host(des, kps, K, words=words, outputs=outs)
+    assert h2d == des.nbytes + kps.nbytes + words.nbytes
+    assert d2h == sum(host[k].numel() * host[k].element_size() for k in outs)
+    for k in outs:
+        a, b = dev[k].cpu().numpy(), host[k].numpy()
+        if k == "points4d":
+            for i in range(F - 1):
+                n = int(host["n_inl"][i])
+                assert np.array_equal(a[i, :n], b[i, :n])
+        elif k == "good":
+            for i in range(F - 1):
+                n = int(host["n_inl"][i])
+                assert np.array_equal(a[i, :n], b[i, :n])
+        else:
+            assert np.array_equal(a, b, equal_nan=True), k
+
+
+def test_pairs_two_sequences(ops):
+    N, H = 600, 128
+    fa, _ = synth.make_sequence(3, N, seed=1)
+    fb, _ = synth.make_sequence(4, N, seed=2)
+    frames = fa + fb
+    des = np.stack([f[1] for f in frames])
+    kps = np.stack([f[0] for f in frames])
+    words = synth.sample_words(H, 9)
+    seq_off = np.array([0, 2, 5], dtype=np.int32)
+    out = ops.process_pairs_device(torch.from_numpy(des).cuda(), torch.from_numpy(kps).cuda(), K, words=words,
+                                   seq_off=seq_off, outputs=ALL_OUT)
+    out = {k: v.cpu().numpy() for k, v in out.items() if k != "_keepalive"}
+    # sequence 0: pairs 0,1 use frames (0,1),(1,2), poses rows 0..2 ; sequence 1: pairs 2..4, frames 3..6, poses rows 3..6
+    o0 = {k: (v[0:3] if k == "poses" else v[0:2]) for k, v in out.items()}
+    o1 = {k: (v[3:7] if k == "poses" else v[2:5]) for k, v in out.items()}
+    _check_sequence(ops, o0, frames, words, H, [(0, 1), (1, 2)])
+    _check_sequence(ops, o1, frames, words, H, [(3, 4), (4, 5), (5, 6)])
