@@ -1,0 +1,375 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the two-view geometry hot path (BASELINE.json metric).
+
+    python bench.py --gpus N --steps K --warmup W            (our arm, sm_100a kernels)
+    python bench.py --impl reference --gpus N --steps K ...  (the reference's CPU path on host cores)
+
+Workload (config C2 of BASELINE.json, "single frame pair 2k x 2k 256-bit descriptors, 1024 seeded
+RANSAC hypotheses, triangulate inliers, 1 B200"): one STEP = one pass of the whole path
+(match -> ratio/compact -> RANSAC fit/score/select/refit -> extract_Rt -> pose -> triangulate -> z>0)
+over a batch of P independent synthetic frame pairs of that shape.  P is chosen so that the inputs
+(descriptors + keypoints of 2P frames) exceed the 126 MB L2, hence no L2 flush between iterations.
+`value` = frame pairs / s with inputs resident in HBM; `e2e` = the same through the host-buffer C-ABI
+entry (tvg_pairs_host) with pinned host inputs, H2D + D2H inside the timed region.
+Multi-GPU: every rank processes its own P pairs (weak scaling, no data-path collective).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+N_KPTS = 2048
+N_HYP = 1024
+DISTINCT_PAIRS = 64      # synthetic pairs generated; the batch tiles them (distinct HBM addresses)
+THR = 0.005
+RATIO = 0.75
+SEED = 2002              # 1000*config + id, SURVEY.md §8d
+
+
+def make_batch(pairs, seed=SEED):
+    """2*pairs frames: pair b = (last = frame 2b, curr = frame 2b+1). Returns des u8[2P,N,32], kps f64[2P,N,2]."""
+    from openwork_b200 import synth
+    base = []
+    for i in range(min(pairs, DISTINCT_PAIRS)):
+        lk, ld, ck, cd = synth.make_pair(N_KPTS, seed + i)
+        base.append((lk, ld, ck, cd))
+    des = np.empty((2 * pairs, N_KPTS, 32), dtype=np.uint8)
+    kps = np.empty((2 * pairs, N_KPTS, 2), dtype=np.float64)
+    for b in range(pairs):
+        lk, ld, ck, cd = base[b % len(base)]
+        des[2 * b], des[2 * b + 1] = ld, cd
+        kps[2 * b], kps[2 * b + 1] = lk, ck
+    return des, kps
+
+
+class ClockSampler(threading.Thread):
+    """Samples SM clock + throttle reasons during the timed region (NVML, 50 ms period)."""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.stop_evt = index, threading.Event()
+        self.sm, self.reasons, self.max_mhz, self.power = [], set(), None, []
+        self.ok = False
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+            self.ok = True
+        except Exception as e:  # pragma: no cover
+            self.err = repr(e)
+
+    def run(self):
+        if not self.ok:
+            return
+        nv = self.nv
+        names = {
+            "hw_slowdown": getattr(nv, "nvmlClocksThrottleReasonHwSlowdown", 0x8),
+            "hw_thermal_slowdown": getattr(nv, "nvmlClocksThrottleReasonHwThermalSlowdown", 0x40),
+            "sw_thermal_slowdown": getattr(nv, "nvmlClocksThrottleReasonSwThermalSlowdown", 0x20),
+            "sw_power_cap": getattr(nv, "nvmlClocksThrottleReasonSwPowerCap", 0x4),
+            "hw_power_brake": getattr(nv, "nvmlClocksThrottleReasonHwPowerBrakeSlowdown", 0x80),
+        }
+        while not self.stop_evt.is_set():
+            try:
+                self.sm.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                self.power.append(nv.nvmlDeviceGetPowerUsage(self.h) / 1000.0)
+                r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for k, bit in names.items():
+                    if r & bit:
+                        self.reasons.add(k)
+            except Exception:
+                pass
+            self.stop_evt.wait(0.05)
+
+    def summary(self):
+        if not self.ok or not self.sm:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": [], "note": "nvml unavailable"}
+        return {"sm_mhz": float(np.median(self.sm)), "sm_max_mhz": float(self.max_mhz),
+                "reasons": sorted(self.reasons), "power_w_max": float(max(self.power)) if self.power else None,
+                "samples": len(self.sm)}
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.isfile(p):
+        d = json.load(open(p))
+        return d, "measured"
+    return {"hbm_gbs": 6650.0, "sm_max_mhz": 1965.0}, "fallback"
+
+
+# ----------------------------------------------------------------------------------------- reference arm
+def _cpu_pair_worker(args):
+    """One frame pair through the CPU oracle (cv2 BFMatcher + restated skimage RANSAC + per-point LAPACK)."""
+    import cv2
+    from oracle import two_view as tv
+    cv2.setNumThreads(1)
+    lk, ld, ck, cd, K, words = args
+    r = tv.process_pair(lk, ld, ck, cd, np.eye(4), K, words=words, residual_threshold=THR)
+    return int(r["inliers"].sum())
+
+
+def cpu_reference_rate(n_pairs, cores, seed=SEED):
+    """frame pairs/s of the reference's CPU path on `cores` host processes (bounded sample)."""
+    import multiprocessing as mp
+    from openwork_b200 import synth
+    K = synth.K_640x480
+    words = synth.sample_words(N_HYP, seed)
+    base = [synth.make_pair(N_KPTS, seed + i) for i in range(min(n_pairs, 8))]
+    jobs = [(*base[i % len(base)], K, words) for i in range(n_pairs)]
+    if cores <= 1:
+        _cpu_pair_worker(jobs[0])
+        t0 = time.perf_counter()
+        for j in jobs:
+            _cpu_pair_worker(j)
+        return n_pairs / (time.perf_counter() - t0)
+    ctx = mp.get_context("fork")
+    with ctx.Pool(cores) as pool:
+        pool.map(_cpu_pair_worker, jobs[:cores])          # warm-up (imports, page-in)
+        t0 = time.perf_counter()
+        pool.map(_cpu_pair_worker, jobs, chunksize=1)
+        dt = time.perf_counter() - t0
+    return n_pairs / dt
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    cores = len(os.sched_getaffinity(0))
+    per_step = 2 * cores
+    import multiprocessing as mp
+    from openwork_b200 import synth
+    K = synth.K_640x480
+    words = synth.sample_words(N_HYP, SEED)
+    base = [synth.make_pair(N_KPTS, SEED + i) for i in range(8)]
+    jobs = [(*base[i % len(base)], K, words) for i in range(per_step)]
+    ctx = mp.get_context("fork")
+    with ctx.Pool(cores) as pool:
+        for _ in range(max(args.warmup, 1)):
+            pool.map(_cpu_pair_worker, jobs, chunksize=1)
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            pool.map(_cpu_pair_worker, jobs, chunksize=1)
+        dt = time.perf_counter() - t0
+    value = per_step * args.steps / dt
+    sample = "%d pairs/step on a %d-process pool (cv2 BFMatcher + restated skimage ransac + reference triangulate loop)" % (
+        per_step, cores)
+    line = {
+        "impl": "reference", "metric": "frame pairs/s (2k kpts, match+RANSAC+triangulate)", "value": value,
+        "unit": "pairs/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "u8 popcount + f64", "data": "synthetic",
+        "config": {"workload": "C2: frame pairs 2048x2048 256-bit descriptors, 1024 seeded RANSAC hypotheses, "
+                               "triangulate inliers", "pairs_per_step": per_step},
+        "cpu_baseline": {"value": value, "unit": "pairs/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+    return 0
+
+
+# ----------------------------------------------------------------------------------------- our arm
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from openwork_b200 import ops, synth
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- the product has no CPU path")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    ctx = ops.context(local)
+    ctx.set_matcher_config(args.knn_r, args.knn_variant, args.knn_ctas)
+    K = synth.K_640x480
+    P = args.pairs
+    des_h, kps_h = make_batch(P, SEED + 100000 * rank)
+    words_h = synth.sample_words(N_HYP, SEED)
+    des_pin = torch.from_numpy(des_h).pin_memory()
+    kps_pin = torch.from_numpy(kps_h).pin_memory()
+    words_pin = torch.from_numpy(words_h.view(np.int32)).pin_memory()
+    des = des_pin.to(dev)
+    kps = kps_pin.to(dev)
+    words = words_pin.to(dev)
+    pair_q = torch.arange(1, 2 * P, 2, dtype=torch.int32, device=dev)
+    pair_t = torch.arange(0, 2 * P, 2, dtype=torch.int32, device=dev)
+    seq_off = torch.arange(0, P + 1, dtype=torch.int32, device=dev)        # every pair is its own sequence
+    outs = ("m_count", "E", "n_inl", "Rt", "poses", "points4d", "good", "status", "best")
+    out = None
+
+    def step():
+        nonlocal out
+        out = ops.process_pairs_device(des, kps, K, words=words, pair_q=pair_q, pair_t=pair_t, seq_off=seq_off,
+                                       ratio=RATIO, residual_threshold=THR, outputs=outs, out=out, ctx=ctx)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    barrier()
+    st = out["status"].cpu().numpy()
+    if (st != 0).any():
+        raise SystemExit("bench.py: pipeline reported status != 0")
+
+    sampler = ClockSampler(local)
+    sampler.start()
+    l0 = ctx.launches
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        step()
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    launches = ctx.launches - l0
+
+    # ---- dominant kernel: the Hamming matcher over the same batch, timed alone on its stream
+    idx = torch.empty((P, N_KPTS, 2), dtype=torch.int32, device=dev)
+    dst = torch.empty((P, N_KPTS, 2), dtype=torch.int32, device=dev)
+    keep = torch.empty((P, N_KPTS), dtype=torch.uint8, device=dev)
+    import ctypes as C
+
+    def knn():
+        ops.check(ctx.lib.tvg_knn2_hamming256(ctx.handle, C.c_void_p(des.data_ptr()), C.c_void_p(des.data_ptr()), P,
+                                              N_KPTS, N_KPTS, N_KPTS, C.c_void_p(pair_q.data_ptr()),
+                                              C.c_void_p(pair_t.data_ptr()), None, None, RATIO,
+                                              C.c_void_p(idx.data_ptr()), C.c_void_p(dst.data_ptr()),
+                                              C.c_void_p(keep.data_ptr()),
+                                              C.c_void_p(torch.cuda.current_stream().cuda_stream)), "knn2")
+    for _ in range(3):
+        knn()
+    torch.cuda.synchronize()
+    k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    reps = max(args.steps, 5)
+    k0.record()
+    for _ in range(reps):
+        knn()
+    k1.record()
+    k1.synchronize()
+    knn_ms = k0.elapsed_time(k1) / reps
+    sampler.stop_evt.set()
+    sampler.join()
+
+    # ---- e2e: host buffers in, results out, through the C-ABI host entry
+    e2e_outs = ("m_count", "E", "n_inl", "Rt", "poses", "status")
+    host_out = None
+    h2d = d2h = 0
+
+    pq_h, pt_h, so_h = pair_q.cpu(), pair_t.cpu(), seq_off.cpu()
+
+    def e2e_step():
+        nonlocal host_out, h2d, d2h
+        host_out, h2d, d2h = ops.process_pairs_host(des_pin, kps_pin, K, words=words_pin,
+                                                    pair_q=pq_h, pair_t=pt_h, seq_off=so_h,
+                                                    ratio=RATIO, residual_threshold=THR, outputs=e2e_outs,
+                                                    out=host_out, ctx=ctx)
+    for _ in range(2):
+        e2e_step()
+    barrier()
+    t0 = time.perf_counter()
+    e2e_steps = max(2, min(args.steps, 10))
+    for _ in range(e2e_steps):
+        e2e_step()
+    barrier()
+    e2e_s = time.perf_counter() - t0
+
+    t = torch.tensor([ms, knn_ms, e2e_s], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms, knn_ms, e2e_s = [float(x) for x in t.cpu()]
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return 0
+
+    peaks, peak_kind = measured_peaks()
+    clocks = sampler.summary()
+    value = world * P * args.steps / (ms / 1e3)
+    e2e_value = world * P * e2e_steps / e2e_s
+    cmp_per_launch = P * N_KPTS * N_KPTS
+    gcmp_s = cmp_per_launch / (knn_ms / 1e3) / 1e9
+    f_mhz = clocks.get("sm_mhz") or peaks.get("sm_max_mhz", 1965.0)
+    n_sm = torch.cuda.get_device_properties(local).multi_processor_count
+    popc_peak = 2.0 * n_sm * peaks.get("sm_max_mhz", 1965.0) * 1e6 / 1e9      # 8 POPC/cmp at 16 lanes/clk/SM
+    alg_bytes = P * (2 * N_KPTS * 32 + N_KPTS * 17)                           # descriptors in, idx+dist+keep out
+    hbm_gbs = alg_bytes / (knn_ms / 1e3) / 1e9
+    roofline = {
+        "kernel": "knn2_kernel (Hamming kNN-2, LOP3+POPC)", "bound": "int_pipe", "achieved": gcmp_s,
+        "peak": popc_peak, "unit": "Gcmp/s", "frac": gcmp_s / popc_peak,
+        "peak_note": "POPC-pipe bound of the plain 8xPOPC form: 2 cmp/clk/SM x %d SMs x sm_max_mhz (%s); the "
+                     "Harley-Seal variant needs 4 POPC/cmp so it may exceed 1.0" % (n_sm, peak_kind),
+        "ms_per_launch": knn_ms, "cmp_per_launch": cmp_per_launch, "sm_mhz_during_run": f_mhz,
+        "traffic": None,
+        "hbm": {"achieved": hbm_gbs, "peak": peaks.get("hbm_gbs"), "unit": "GB/s",
+                "frac": hbm_gbs / peaks.get("hbm_gbs", 6650.0), "algorithmic_bytes_per_launch": alg_bytes,
+                "note": "matcher is integer-pipe bound, far below the HBM roofline"},
+    }
+    cores = len(os.sched_getaffinity(0))
+    if args.no_cpu_baseline or world > 1:
+        cpu = None
+    else:
+        n_cpu = max(2 * cores, 16)
+        cpu_rate = cpu_reference_rate(n_cpu, cores)
+        cpu = {"value": cpu_rate, "unit": "pairs/s", "cores": cores, "kind": "port",
+               "sample": "%d pairs of the same C2 workload on a %d-process pool (cv2 BFMatcher + restated skimage "
+                         "ransac + reference triangulate loop)" % (n_cpu, cores)}
+    line = {
+        "metric": "frame pairs/s (2k kpts, match+RANSAC+triangulate)", "value": value, "unit": "pairs/s",
+        "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8 popcount + f32/f64",
+        "data": "synthetic",
+        "config": {"workload": "C2: frame pairs 2048x2048 256-bit descriptors, 1024 seeded RANSAC hypotheses, "
+                               "triangulate inliers", "pairs_per_step_per_gpu": P, "kpts": N_KPTS, "hypotheses": N_HYP,
+                   "l2_policy": "inputs larger than L2 (%.0f MB of descriptors+keypoints per step)" %
+                                ((des_h.nbytes + kps_h.nbytes) / 1e6),
+                   "matcher": {"r": args.knn_r, "variant": args.knn_variant, "ctas_per_sm": args.knn_ctas}},
+        "hamming_gcmp_s": gcmp_s * world, "clocks": clocks, "gpu_launches": int(launches),
+        "e2e": {"value": e2e_value, "unit": "pairs/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+                "steps": e2e_steps},
+        "roofline": roofline, "cpu_baseline": cpu,
+    }
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--pairs", type=int, default=1024, help="frame pairs per step per GPU")
+    ap.add_argument("--knn-r", type=int, default=4)
+    ap.add_argument("--knn-variant", type=int, default=1)
+    ap.add_argument("--knn-ctas", type=int, default=6)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+    return run_ours(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

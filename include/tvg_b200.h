@@ -116,6 +116,7 @@ typedef struct tvg_ransac_io {
     double* pix_curr;
     int32_t* band;      /* fp32 uncertainty-band count per hypothesis */
     int32_t* n_cand;    /* finalists re-scored in fp64 */
+    double* best_sse;   /* [batch] exact sum of squared residuals of the winner (all points) */
 } tvg_ransac_io;
 TVG_API int tvg_ransac_essential(tvg_ctx* ctx, const tvg_ransac_io* io, void* stream);
 

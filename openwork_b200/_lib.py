@@ -28,7 +28,7 @@ class RansacIO(C.Structure):
         ("qidx", c_vp), ("tidx", c_vp), ("pair_q", c_vp), ("pair_t", c_vp), ("kps_q", c_vp), ("kps_t", c_vp),
         ("E", c_vp), ("mask", c_vp), ("n_inl", c_vp), ("best", c_vp), ("E_best", c_vp), ("counts", c_vp),
         ("sse32", c_vp), ("models", c_vp), ("Rt", c_vp), ("status", c_vp), ("inl_idx", c_vp),
-        ("samples_out", c_vp), ("pix_last", c_vp), ("pix_curr", c_vp), ("band", c_vp), ("n_cand", c_vp),
+        ("samples_out", c_vp), ("pix_last", c_vp), ("pix_curr", c_vp), ("band", c_vp), ("n_cand", c_vp), ("best_sse", c_vp),
     ]
 
 

@@ -258,7 +258,7 @@ int tvg_ransac_essential(tvg_ctx* ctx, const tvg_ransac_io* io, void* stream) {
     const bool gather = io->kps_q && io->kps_t && io->qidx && io->tidx;
     p.kps_q = gather ? io->kps_q : nullptr; p.kps_t = gather ? io->kps_t : nullptr;
     TVG_OUT(ctx, io->best, S_BEST, B * sizeof(int32_t), p.best, int32_t*);
-    TVG_GET(ctx, S_BESTSSE, B * sizeof(double), p.best_sse, double*);
+    TVG_OUT(ctx, io->best_sse, S_BESTSSE, B * sizeof(double), p.best_sse, double*);
     TVG_OUT(ctx, io->E_best, S_EBEST, B * 9 * sizeof(double), p.E_best, double*);
     TVG_OUT(ctx, io->mask, S_MASK, B * N, p.mask, uint8_t*);
     TVG_OUT(ctx, io->n_inl, S_NINL, B * sizeof(int32_t), p.n_inl, int32_t*);

@@ -185,7 +185,8 @@ def ransac_essential(src, dst, samples=None, words=None, residual_threshold=RESI
         sse32=torch.empty(H, dtype=torch.float32, device=dev), Rt=torch.empty(16, dtype=torch.float64, device=dev),
         status=torch.zeros(1, dtype=torch.int32, device=dev), inl_idx=torch.empty(M, dtype=torch.int32, device=dev),
         samples_out=torch.empty((H, 8), dtype=torch.int32, device=dev),
-        band=torch.empty(H, dtype=torch.int32, device=dev), n_cand=torch.zeros(1, dtype=torch.int32, device=dev))
+        band=torch.empty(H, dtype=torch.int32, device=dev), n_cand=torch.zeros(1, dtype=torch.int32, device=dev),
+        best_sse=torch.zeros(1, dtype=torch.float64, device=dev))
     if return_models:
         o["models"] = torch.empty((H, 3, 3), dtype=torch.float64, device=dev)
     io = RansacIO()
@@ -204,7 +205,7 @@ def ransac_essential(src, dst, samples=None, words=None, residual_threshold=RESI
     res = dict(E=o["E"].view(3, 3), mask=o["mask"].bool(), counts=o["counts"], sse32=o["sse32"],
                best=int(o["best"].item()), E_best=o["E_best"].view(3, 3), n_inl=n_inl, Rt=o["Rt"].view(4, 4),
                status=int(o["status"].item()), inl_idx=o["inl_idx"][:n_inl], samples=o["samples_out"],
-               band=o["band"], n_cand=int(o["n_cand"].item()))
+               band=o["band"], n_cand=int(o["n_cand"].item()), best_sse=float(o["best_sse"].item()))
     if return_models:
         res["models"] = o["models"]
     return res
@@ -360,7 +361,8 @@ def process_pairs_device(des, kps, K, words=None, samples=None, H=None, frame_co
             B = F - 1
     nseq = 1
     if seq_off is not None:
-        so = _dev(np.asarray(_np(seq_off), dtype=np.int32), torch.int32, dev)
+        so = seq_off if isinstance(seq_off, torch.Tensor) else np.asarray(seq_off, dtype=np.int32)
+        so = _dev(so, torch.int32, dev)
         nseq = so.shape[0] - 1
     fc = _dev(frame_count, torch.int32, dev)
     ip = _dev(init_pose, torch.float64, dev)

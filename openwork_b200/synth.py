@@ -27,6 +27,18 @@ def _small_rotation(rng, max_angle):
     return np.eye(3) + np.sin(th) * Kx + (1 - np.cos(th)) * (Kx @ Kx)
 
 
+def _flip_masks(rng, n, max_flips):
+    """u8[n,32] masks with k ~ U{0..max_flips} distinct random bits set per row."""
+    if n == 0:
+        return np.zeros((0, 32), dtype=np.uint8)
+    k = rng.integers(0, max_flips + 1, n)
+    order = np.argsort(rng.random((n, 256)), axis=1)            # a random permutation of the 256 bits per row
+    rank = np.empty_like(order)
+    np.put_along_axis(rank, order, np.arange(256)[None, :].repeat(n, 0), axis=1)
+    bits = (rank < k[:, None]).astype(np.uint8)                 # the first k bits of the permutation
+    return np.packbits(bits, axis=1, bitorder="little")
+
+
 def camera_track(n_frames, seed, step=(0.3, 0.7), max_angle=0.01):
     """World->camera transforms T_i (x_cam = R_i x_world + t_i) of a forward-moving camera."""
     rng = np.random.default_rng(seed)
@@ -89,12 +101,7 @@ def make_sequence(n_frames, n_kpts, seed, K=K_640x480, width=640, height=480,
         kps = np.stack([u[ids], v[ids]], axis=1) + rng.normal(0, pix_sigma, (n_t, 2))
         bad = rng.random(n_t) < outlier
         kps[bad] += rng.normal(0, outlier_sigma, (int(bad.sum()), 2))
-        des = base_des[ids].copy()
-        flips = rng.integers(0, max_flips + 1, n_t)
-        for i in range(n_t):
-            if flips[i]:
-                bits = rng.choice(256, flips[i], replace=False)
-                np.bitwise_xor.at(des[i], bits >> 3, (1 << (bits & 7)).astype(np.uint8))
+        des = base_des[ids] ^ _flip_masks(rng, n_t, max_flips)
         n_c = n_kpts - n_t
         ckps = np.stack([rng.uniform(0, width, n_c), rng.uniform(0, height, n_c)], axis=1)
         cdes = rng.integers(0, 256, (n_c, 32), dtype=np.uint8)
@@ -125,14 +132,7 @@ def correlated_descriptors(nq, nt, seed, max_flips=49, clutter=0.2):
     rng = np.random.default_rng(seed)
     t = rng.integers(0, 256, (nt, 32), dtype=np.uint8)
     src = rng.permutation(nt)[:nq] if nq <= nt else rng.integers(0, nt, nq)
-    q = t[src].copy()
-    nflip = rng.integers(0, max_flips + 1, nq)
-    # flip random bits: build a random 256-bit mask with ~nflip bits set
-    bits = rng.integers(0, 256, (nq, max_flips))
-    live = np.arange(max_flips)[None, :] < nflip[:, None]
-    rows = np.repeat(np.arange(nq), max_flips)[live.ravel()]
-    b = bits.ravel()[live.ravel()]
-    np.bitwise_xor.at(q, (rows, b >> 3), (1 << (b & 7)).astype(np.uint8))
+    q = t[src] ^ _flip_masks(rng, nq, max_flips)
     c = rng.random(nq) < clutter
     q[c] = rng.integers(0, 256, (int(c.sum()), 32), dtype=np.uint8)
     return np.ascontiguousarray(q), np.ascontiguousarray(t)

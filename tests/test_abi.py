@@ -1,0 +1,81 @@
+"""CPU tests of the drop-in boundary: the shared library builds for sm_100a, loads, exports every
+symbol include/tvg_b200.h declares, the ctypes structs mirror the C structs, and the product has no
+CPU fallback (no oracle import, loud failure without a GPU)."""
+import ctypes
+import os
+import re
+import subprocess
+import sys
+
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HEADER = os.path.join(ROOT, "include", "tvg_b200.h")
+
+
+def _declared():
+    src = open(HEADER).read()
+    return re.findall(r"^TVG_API [\w \*]+?\b(tvg_\w+)\(", src, flags=re.M)
+
+
+def test_library_builds_and_exports_every_declared_symbol(lib_built):
+    from openwork_b200 import _lib
+    lib = _lib.load()
+    names = _declared()
+    assert len(names) >= 14
+    for n in names:
+        assert hasattr(lib, n), n
+    assert sorted(names) == sorted(_lib.SIGNATURES), "ctypes signature table out of sync with the header"
+    assert lib.tvg_abi_version() == 1
+    out = subprocess.run(["nm", "-D", "--defined-only", lib_built], capture_output=True, text=True).stdout
+    exported = set(re.findall(r" T (\w+)", out))
+    assert set(names) <= exported
+    assert all(e.startswith("tvg_") for e in exported), exported - set(names)   # nothing else leaks
+
+
+def test_ctypes_structs_mirror_the_c_structs(lib_built, tmp_path):
+    from openwork_b200 import _lib
+    prog = tmp_path / "sz.c"
+    prog.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "tvg_b200.h"\n'
+                    'int main(void){printf("%zu %zu %zu %zu %zu %zu\\n", sizeof(tvg_ransac_io), sizeof(tvg_pairs_io),'
+                    ' offsetof(tvg_ransac_io, thr), offsetof(tvg_ransac_io, n_cand), offsetof(tvg_pairs_io, kinv),'
+                    ' offsetof(tvg_pairs_io, status)); return 0;}\n')
+    exe = tmp_path / "sz"
+    subprocess.run(["gcc", "-I", os.path.join(ROOT, "include"), str(prog), "-o", str(exe)], check=True)
+    vals = [int(v) for v in subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.split()]
+    assert vals[0] == ctypes.sizeof(_lib.RansacIO)
+    assert vals[1] == ctypes.sizeof(_lib.PairsIO)
+    assert vals[2] == _lib.RansacIO.thr.offset and vals[3] == _lib.RansacIO.n_cand.offset
+    assert vals[4] == _lib.PairsIO.kinv.offset and vals[5] == _lib.PairsIO.status.offset
+
+
+def test_sass_shows_tma_and_integer_pipe(lib_built):
+    """The matcher is LOP3 + POPC fed by TMA bulk copies (UBLKCP); no tensor-core reshaping."""
+    sass = subprocess.run(["cuobjdump", "-sass", lib_built], capture_output=True, text=True).stdout
+    assert "UBLKCP" in sass and "POPC" in sass and "LOP3" in sass and "SYNCS" in sass
+    assert "sm_100a" in sass or "SM100a" in sass or "EF_CUDA_SM100" in sass
+
+
+def test_product_never_imports_the_oracle():
+    pkg = os.path.join(ROOT, "openwork_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                text = open(os.path.join(dirpath, f)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle\b", text, flags=re.M), f
+                assert not re.search(r"^\s*(from|import)\s+(cv2|skimage)\b", text, flags=re.M), f
+    code = "import sys; import openwork_b200, openwork_b200.slam, openwork_b200.ops, openwork_b200.dist; " \
+           "assert not any(m == 'oracle' or m.startswith('oracle.') for m in sys.modules); " \
+           "assert 'cv2' not in sys.modules and 'skimage' not in sys.modules"
+    subprocess.run([sys.executable, "-c", code], cwd=ROOT, check=True)
+
+
+@pytest.mark.skipif(torch.cuda.is_available(), reason="only meaningful on a GPU-less box")
+def test_fails_loudly_without_a_gpu(lib_built):
+    from openwork_b200 import _lib, ops
+    import numpy as np
+    with pytest.raises(_lib.TvgError):
+        _lib.Context(0)
+    with pytest.raises(Exception):
+        ops.knn2_hamming256(np.zeros((4, 32), np.uint8), np.zeros((4, 32), np.uint8))
