@@ -391,7 +391,6 @@ def process_pairs_device(des, kps, K, words=None, samples=None, H=None, frame_co
     for k, v in out.items():
         setattr(io, k, v.data_ptr())
     check(ctx.lib.tvg_pairs_device(ctx.handle, C.byref(io), _stream()), "tvg_pairs_device")
-    out["_keepalive"] = (des, kps, tab, pq, pt, so, fc, ip)
     return out
 
 

@@ -243,8 +243,10 @@ def test_cheirality_votes_match_oracle(ops):
     ref = tv.ransac_essential(src, dst, samples, THR)
     votes, Rts, choice = ops.cheirality(ref["E"], src, dst, mask=ref["mask"])
     rv, rRts = tv.cheirality_votes(ref["E"], src[ref["mask"]], dst[ref["mask"]])
-    assert choice == int(np.argmax(rv))
-    assert np.abs(votes.cpu().numpy() - rv).max() <= 2      # points at |z| ~ 0 may flip
+    # candidate ORDER depends on the SVD's sign choices (LAPACK vs Jacobi); the SET and the winner do not
+    v = votes.cpu().numpy()
+    assert np.abs(np.sort(v) - np.sort(rv)).max() <= 2      # points at |z| ~ 0 may flip
+    assert v[choice] == v.max()
     np.testing.assert_allclose(Rts.cpu().numpy()[choice], rRts[int(np.argmax(rv))], atol=1e-8)
 
 
@@ -283,7 +285,7 @@ def test_pairs_device_sequence_matches_oracle(ops):
     words = synth.sample_words(H, 7)
     out = ops.process_pairs_device(torch.from_numpy(des).cuda(), torch.from_numpy(kps).cuda(), K, words=words,
                                    residual_threshold=THR, outputs=ALL_OUT)
-    out = {k: v.cpu().numpy() for k, v in out.items() if k != "_keepalive"}
+    out = {k: v.cpu().numpy() for k, v in out.items()}
     assert (out["status"] == 0).all()
     _check_sequence(ops, out, frames, words, H, [(i, i + 1) for i in range(F - 1)])
 
@@ -325,7 +327,7 @@ def test_pairs_two_sequences(ops):
     seq_off = np.array([0, 2, 5], dtype=np.int32)
     out = ops.process_pairs_device(torch.from_numpy(des).cuda(), torch.from_numpy(kps).cuda(), K, words=words,
                                    seq_off=seq_off, outputs=ALL_OUT)
-    out = {k: v.cpu().numpy() for k, v in out.items() if k != "_keepalive"}
+    out = {k: v.cpu().numpy() for k, v in out.items()}
     # sequence 0: pairs 0,1 use frames (0,1),(1,2), poses rows 0..2 ; sequence 1: pairs 2..4, frames 3..6, poses rows 3..6
     o0 = {k: (v[0:3] if k == "poses" else v[0:2]) for k, v in out.items()}
     o1 = {k: (v[3:7] if k == "poses" else v[2:5]) for k, v in out.items()}
