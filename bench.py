@@ -197,6 +197,7 @@ def run_ours(args):
         dist.init_process_group("nccl", device_id=dev)
     ctx = ops.context(local)
     ctx.set_matcher_config(args.knn_r, args.knn_variant, args.knn_ctas)
+    ctx.set_host_chunk(args.host_chunk)
     K = synth.K_640x480
     P = args.pairs
     des_h, kps_h = make_batch(P, SEED + 100000 * rank)
@@ -364,6 +365,7 @@ def main():
     ap.add_argument("--knn-r", type=int, default=4)
     ap.add_argument("--knn-variant", type=int, default=1)
     ap.add_argument("--knn-ctas", type=int, default=6)
+    ap.add_argument("--host-chunk", type=int, default=256, help="pairs per chunk of the e2e host pipeline")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -189,10 +189,15 @@ typedef struct tvg_pairs_io {
 } tvg_pairs_io;
 TVG_API int tvg_pairs_device(tvg_ctx* ctx, const tvg_pairs_io* io, void* stream);
 
-/* Same pipeline behind HOST buffers (what a numpy caller hands over): copies the frame pools and the
- * sample words host->device, runs tvg_pairs_device, copies the per-pair results device->host and
- * synchronises.  Every pointer in `io` is a HOST pointer here (pinned memory makes the copies async).
- * bytes_h2d / bytes_d2h (may be NULL) receive the bytes moved. */
+/* Pairs per chunk of tvg_pairs_host's copy/compute pipeline (default 256). */
+TVG_API int tvg_set_host_chunk(tvg_ctx* ctx, int pairs);
+
+/* Same pipeline behind HOST buffers (what a numpy caller hands over).  Every pointer in `io` is a HOST
+ * pointer here (pinned memory makes the copies asynchronous).  The batch is cut into chunks of pairs:
+ * frame copies host->device (own stream), kernels (caller's stream) and result copies device->host (own
+ * stream) of successive chunks overlap; the call returns after synchronising.  Frames are copied in
+ * index order up to the highest frame a chunk references.  bytes_h2d / bytes_d2h (may be NULL) receive
+ * the bytes moved. */
 TVG_API int tvg_pairs_host(tvg_ctx* ctx, const tvg_pairs_io* io, int frames, long long* bytes_h2d,
                    long long* bytes_d2h, void* stream);
 

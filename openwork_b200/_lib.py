@@ -65,6 +65,7 @@ SIGNATURES = {
     "tvg_cheirality": (C.c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, C.c_int, C.c_int, C.c_int, c_vp, c_vp,
                                  c_vp, c_vp]),
     "tvg_pairs_device": (C.c_int, [c_vp, C.POINTER(PairsIO), c_vp]),
+    "tvg_set_host_chunk": (C.c_int, [c_vp, C.c_int]),
     "tvg_pairs_host": (C.c_int, [c_vp, C.POINTER(PairsIO), C.c_int, C.POINTER(C.c_longlong),
                                  C.POINTER(C.c_longlong), c_vp]),
 }
@@ -124,6 +125,9 @@ class Context:
     @property
     def launches(self):
         return int(self.lib.tvg_launch_count(self.handle))
+
+    def set_host_chunk(self, pairs=256):
+        check(self.lib.tvg_set_host_chunk(self.handle, int(pairs)), "tvg_set_host_chunk")
 
     def set_matcher_config(self, r=4, variant=0, ctas_per_sm=6):
         check(self.lib.tvg_set_matcher_config(self.handle, r, variant, ctas_per_sm), "tvg_set_matcher_config")

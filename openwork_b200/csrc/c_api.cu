@@ -33,7 +33,7 @@ enum Slot {
     S_PARTIAL, S_COUNTERS, S_IDX, S_DIST, S_KEEP, S_QIDX, S_TIDX, S_MCOUNT, S_SRC, S_DST, S_CORR32,
     S_E64, S_E32, S_VALID, S_PARTCNT, S_PARTSSE, S_COUNTS, S_BAND, S_SSE32, S_CAND, S_NCAND, S_CANDSSE,
     S_CANDCNT, S_BEST, S_BESTSSE, S_EBEST, S_MASK, S_NINL, S_INLIDX, S_PIXLAST, S_PIXCURR, S_E, S_RT,
-    S_STATUS, S_POSES, S_POSESINV, S_POINTS, S_GOOD, S_PAIRQ, S_PAIRT, S_SEQOFF, S_VOTES, S_RTS, S_CHOICE,
+    S_STATUS, S_POSES, S_POSESINV, S_POINTS, S_GOOD, S_PAIRQ, S_PAIRT, S_SEQOFF, S_VOTES, S_RTS, S_CHOICE, S_REFITWS,
     // host-entry staging
     S_H_DES, S_H_KPS, S_H_FCOUNT, S_H_PAIRQ, S_H_PAIRT, S_H_SEQOFF, S_H_INIT, S_H_WORDS, S_H_SAMPLES,
     S_NUM
@@ -46,6 +46,9 @@ struct tvg_ctx {
     int sm_count = 148;
     int knn_r = 4, knn_variant = 0, knn_ctas_per_sm = 6;
     long long launches = 0;
+    int host_chunk_pairs = 256;
+    cudaStream_t s_in = nullptr, s_out = nullptr;
+    std::vector<cudaEvent_t> events;
     void* slot[S_NUM] = {};
     size_t slot_bytes[S_NUM] = {};
 
@@ -142,6 +145,9 @@ void tvg_ctx_destroy(tvg_ctx* ctx) {
     cudaDeviceSynchronize();
     for (int i = 0; i < S_NUM; ++i)
         if (ctx->slot[i]) cudaFree(ctx->slot[i]);
+    for (cudaEvent_t e : ctx->events) cudaEventDestroy(e);
+    if (ctx->s_in) cudaStreamDestroy(ctx->s_in);
+    if (ctx->s_out) cudaStreamDestroy(ctx->s_out);
     delete ctx;
 }
 
@@ -268,13 +274,14 @@ int tvg_ransac_essential(tvg_ctx* ctx, const tvg_ransac_io* io, void* stream) {
     TVG_OUT(ctx, io->E, S_E, B * 9 * sizeof(double), p.E, double*);
     TVG_OUT(ctx, io->Rt, S_RT, B * 16 * sizeof(double), p.Rt, double*);
     TVG_OUT(ctx, io->status, S_STATUS, B * sizeof(int32_t), p.status, int32_t*);
+    TVG_GET(ctx, S_REFITWS, B * tvg::ransac_refit_ws_doubles() * sizeof(double), p.refit_ws, double*);
     cudaStream_t st = (cudaStream_t)stream;
     TVG_CUDA(tvg::launch_ransac_fit(p, io->batch, st));
     TVG_CUDA(tvg::launch_ransac_score(p, io->batch, st));
     TVG_CUDA(tvg::launch_ransac_reduce(p, io->batch, st));
     TVG_CUDA(tvg::launch_ransac_rescore(p, io->batch, st));
     TVG_CUDA(tvg::launch_ransac_refit(p, io->batch, st));
-    ctx->launches += 5;
+    ctx->launches += 6;
     return 0;
 }
 
@@ -297,7 +304,7 @@ int tvg_pose_chain(tvg_ctx* ctx, const double* Rt, const int32_t* seq_off, int n
     if (nseq == 0) return 0;
     if (!Rt || !seq_off || !poses) return fail(-3, "tvg_pose_chain: NULL array");
     DeviceGuard g(ctx->device);
-    tvg::PoseChainParams p{Rt, seq_off, init_pose, poses, pair_pinv};
+    tvg::PoseChainParams p{Rt, seq_off, init_pose, poses, pair_pinv, nullptr};
     TVG_CUDA(tvg::launch_pose_chain(p, nseq, (cudaStream_t)stream));
     ctx->launches += 1;
     return 0;
@@ -338,7 +345,7 @@ int tvg_cheirality(tvg_ctx* ctx, const double* E, const double* src, const doubl
     return 0;
 }
 
-int tvg_pairs_device(tvg_ctx* ctx, const tvg_pairs_io* io, void* stream) {
+static int pairs_device_impl(tvg_ctx* ctx, const tvg_pairs_io* io, const double* first_init, void* stream) {
     if (!ctx || !io) return fail(-1, "ctx / io is NULL");
     if (io->batch < 0 || io->n_max <= 0 || io->H <= 0) return fail(-2, "tvg_pairs_device: bad sizes");
     if (io->batch == 0) return 0;
@@ -415,11 +422,25 @@ int tvg_pairs_device(tvg_ctx* ctx, const tvg_pairs_io* io, void* stream) {
     TVG_GET(ctx, S_POSESINV, B * 32 * sizeof(double), pinv, double*);
     TVG_OUT(ctx, io->points4d, S_POINTS, B * N * 4 * sizeof(double), points, double*);
     TVG_OUT(ctx, io->good, S_GOOD, B * N, good, uint8_t*);
-    rc = tvg_pose_chain(ctx, Rt, seq_off, nseq, io->init_pose, poses, pinv, stream);
-    if (rc) return rc;
+    {
+        tvg::PoseChainParams pc{Rt, seq_off, io->init_pose, poses, pinv, first_init};
+        TVG_CUDA(tvg::launch_pose_chain(pc, nseq, st));
+        ctx->launches += 1;
+    }
     // triangulate(frame.last_kps, frame.curr_kps, frame.last_pose, frame.curr_pose)  (slam.py:263)
     return tvg_triangulate(ctx, pix_last, pix_curr, io->batch, io->n_max, io->n_max, n_inl, pinv, 32, pinv + 16,
                            32, io->kinv, points, good, stream);
+}
+
+int tvg_pairs_device(tvg_ctx* ctx, const tvg_pairs_io* io, void* stream) {
+    return pairs_device_impl(ctx, io, nullptr, stream);
+}
+
+int tvg_set_host_chunk(tvg_ctx* ctx, int pairs) {
+    if (!ctx) return fail(-1, "ctx is NULL");
+    if (pairs < 1) return fail(-2, "tvg_set_host_chunk: pairs must be >= 1");
+    ctx->host_chunk_pairs = pairs;
+    return 0;
 }
 
 int tvg_pairs_host(tvg_ctx* ctx, const tvg_pairs_io* hio, int frames, long long* bytes_h2d,
@@ -444,12 +465,16 @@ int tvg_pairs_host(tvg_ctx* ctx, const tvg_pairs_io* hio, int frames, long long*
             field = dp__;                                                                   \
         }                                                                                   \
     } while (0)
-    TVG_UP(S_H_DES, hio->des, F * N * 32, d.des, uint8_t*);
-    TVG_UP(S_H_KPS, hio->kps, F * N * 2 * sizeof(double), d.kps, double*);
+    // big frame pools: device buffers only; the copies are scheduled per chunk below
+    uint8_t* des_d;
+    double* kps_d;
+    TVG_GET(ctx, S_H_DES, F * N * 32, des_d, uint8_t*);
+    TVG_GET(ctx, S_H_KPS, F * N * 2 * sizeof(double), kps_d, double*);
+    d.des = des_d;
+    d.kps = kps_d;
     TVG_UP(S_H_FCOUNT, hio->frame_count, F * sizeof(int32_t), d.frame_count, int32_t*);
     TVG_UP(S_H_PAIRQ, hio->pair_q, B * sizeof(int32_t), d.pair_q, int32_t*);
     TVG_UP(S_H_PAIRT, hio->pair_t, B * sizeof(int32_t), d.pair_t, int32_t*);
-    TVG_UP(S_H_SEQOFF, hio->seq_off, (size_t)(nseq + 1) * sizeof(int32_t), d.seq_off, int32_t*);
     TVG_UP(S_H_INIT, hio->init_pose, (size_t)nseq * 16 * sizeof(double), d.init_pose, double*);
     const size_t tab = (hio->sample_stride ? B : 1) * H * 8 * 4;
     TVG_UP(S_H_WORDS, hio->words, tab, d.words, uint32_t*);
@@ -480,36 +505,135 @@ int tvg_pairs_host(tvg_ctx* ctx, const tvg_pairs_io* hio, int frames, long long*
     TVG_GET(ctx, S_POINTS, B * N * 4 * sizeof(double), points, double*);
     TVG_GET(ctx, S_MASK, B * N, mask, uint8_t*);
     TVG_GET(ctx, S_GOOD, B * N, good, uint8_t*);
-    d.idx = idx; d.dist = dist; d.qidx = qidx; d.tidx = tidx; d.m_count = m_count; d.best = best;
-    d.counts = counts; d.n_inl = n_inl; d.inl_idx = inl_idx; d.status = status; d.E = E; d.E_best = E_best;
-    d.Rt = Rt; d.poses = poses; d.points4d = points; d.mask = mask; d.good = good;
-    int rc = tvg_pairs_device(ctx, &d, stream);
-    if (rc) return rc;
-#define TVG_DOWN(hptr, dptr, bytes)                                                          \
-    do {                                                                                     \
-        if (hptr) {                                                                          \
-            TVG_CUDA(cudaMemcpyAsync((hptr), (dptr), (bytes), cudaMemcpyDeviceToHost, st));  \
-            d2h += (long long)(bytes);                                                       \
-        }                                                                                    \
+    // ---- chunked schedule: frame copies (stream s_in), kernels (caller's stream), result copies (s_out)
+    if (!ctx->s_in) TVG_CUDA(cudaStreamCreateWithFlags(&ctx->s_in, cudaStreamNonBlocking));
+    if (!ctx->s_out) TVG_CUDA(cudaStreamCreateWithFlags(&ctx->s_out, cudaStreamNonBlocking));
+    const int C = ctx->host_chunk_pairs;
+    const int nchunks = (hio->batch + C - 1) / C;
+    while ((int)ctx->events.size() < 2 * nchunks + 1) {
+        cudaEvent_t e;
+        TVG_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        ctx->events.push_back(e);
+    }
+    // host view of the sequence offsets (one sequence holding everything when absent)
+    std::vector<int32_t> so_h(nseq + 1);
+    if (hio->seq_off) memcpy(so_h.data(), hio->seq_off, (size_t)(nseq + 1) * sizeof(int32_t));
+    else { so_h[0] = 0; so_h[1] = hio->batch; }
+    if (so_h[0] != 0 || so_h[nseq] != hio->batch) return fail(-2, "tvg_pairs_host: seq_off must run from 0 to batch");
+    // chunk-local sequence offsets, all chunks concatenated, one upload
+    std::vector<int32_t> so_all;
+    std::vector<int> so_pos(nchunks), s_first(nchunks), n_local(nchunks);
+    {
+        int s = 0;
+        for (int c = 0; c < nchunks; ++c) {
+            const int b0 = c * C, b1 = (b0 + C < hio->batch) ? b0 + C : hio->batch;
+            while (so_h[s + 1] <= b0) ++s;
+            int s1 = s;
+            while (so_h[s1 + 1] < b1) ++s1;
+            s_first[c] = s; n_local[c] = s1 - s + 1; so_pos[c] = (int)so_all.size();
+            for (int k = s; k <= s1 + 1; ++k) {
+                int v = so_h[k] < b0 ? b0 : (so_h[k] > b1 ? b1 : so_h[k]);
+                so_all.push_back(v - b0);
+            }
+        }
+    }
+    int32_t* so_d;
+    TVG_GET(ctx, S_H_SEQOFF, so_all.size() * sizeof(int32_t), so_d, int32_t*);
+    TVG_CUDA(cudaMemcpyAsync(so_d, so_all.data(), so_all.size() * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+    h2d += (long long)((size_t)(nseq + 1) * sizeof(int32_t));
+    // the copy streams must not start before the caller's stream reaches this call
+    cudaEvent_t ev_start = ctx->events[2 * nchunks];
+    TVG_CUDA(cudaEventRecord(ev_start, st));
+    TVG_CUDA(cudaStreamWaitEvent(ctx->s_in, ev_start, 0));
+    TVG_CUDA(cudaStreamWaitEvent(ctx->s_out, ev_start, 0));
+
+    long long copied_upto = 0;   // frames [0, copied_upto) are on the device (or queued on s_in)
+    int rc = 0;
+    for (int c = 0; c < nchunks; ++c) {
+        const int b0 = c * C, b1 = (b0 + C < hio->batch) ? b0 + C : hio->batch, nb = b1 - b0;
+        // frames this chunk needs
+        long long need = 0;
+        if (hio->pair_q) {
+            for (int b = b0; b < b1; ++b) {
+                if (hio->pair_q[b] < 0 || hio->pair_q[b] >= frames || hio->pair_t[b] < 0 || hio->pair_t[b] >= frames)
+                    return fail(-2, "tvg_pairs_host: pair frame index out of range");
+                if (hio->pair_q[b] + 1 > need) need = hio->pair_q[b] + 1;
+                if (hio->pair_t[b] + 1 > need) need = hio->pair_t[b] + 1;
+            }
+        } else {
+            need = (long long)(b1 - 1) + (s_first[c] + n_local[c] - 1) + 2;   // curr frame of the last pair, +1
+            if (need > frames) return fail(-2, "tvg_pairs_host: not enough frames for the consecutive pairing");
+        }
+        if (need > copied_upto) {
+            const size_t f0 = (size_t)copied_upto, nf = (size_t)(need - copied_upto);
+            TVG_CUDA(cudaMemcpyAsync(des_d + f0 * N * 32, hio->des + f0 * N * 32, nf * N * 32, cudaMemcpyHostToDevice, ctx->s_in));
+            TVG_CUDA(cudaMemcpyAsync(kps_d + f0 * N * 2, hio->kps + f0 * N * 2, nf * N * 2 * sizeof(double),
+                                     cudaMemcpyHostToDevice, ctx->s_in));
+            h2d += (long long)(nf * N * (32 + 2 * sizeof(double)));
+            copied_upto = need;
+        }
+        TVG_CUDA(cudaEventRecord(ctx->events[2 * c], ctx->s_in));
+        TVG_CUDA(cudaStreamWaitEvent(st, ctx->events[2 * c], 0));
+
+        tvg_pairs_io k = d;
+        k.batch = nb;
+        k.seq_off = so_d + so_pos[c];
+        k.nseq = n_local[c];
+        const size_t row0 = (size_t)b0 + s_first[c];          // pose row / frame shift of this chunk
+        if (hio->pair_q) { k.pair_q = d.pair_q + b0; k.pair_t = d.pair_t + b0; }
+        else {
+            k.des = des_d + row0 * N * 32;
+            k.kps = kps_d + row0 * N * 2;
+            if (d.frame_count) k.frame_count = d.frame_count + row0;
+        }
+        k.init_pose = d.init_pose ? d.init_pose + (size_t)s_first[c] * 16 : nullptr;
+        if (hio->sample_stride) {
+            if (d.words) k.words = d.words + (size_t)b0 * hio->sample_stride;
+            if (d.samples) k.samples = d.samples + (size_t)b0 * hio->sample_stride;
+        }
+        k.idx = idx + (size_t)b0 * N * 2; k.dist = dist + (size_t)b0 * N * 2;
+        k.qidx = qidx + (size_t)b0 * N; k.tidx = tidx + (size_t)b0 * N; k.m_count = m_count + b0;
+        k.best = best + b0; k.counts = counts + (size_t)b0 * H; k.n_inl = n_inl + b0;
+        k.inl_idx = inl_idx + (size_t)b0 * N; k.status = status + b0; k.E = E + (size_t)b0 * 9;
+        k.E_best = E_best + (size_t)b0 * 9; k.Rt = Rt + (size_t)b0 * 16; k.poses = poses + row0 * 16;
+        k.points4d = points + (size_t)b0 * N * 4; k.mask = mask + (size_t)b0 * N; k.good = good + (size_t)b0 * N;
+        // a sequence continuing from the previous chunk starts from that chunk's last pose (already at `row0`)
+        const double* first_init = (so_h[s_first[c]] < b0) ? poses + row0 * 16 : nullptr;
+        rc = pairs_device_impl(ctx, &k, first_init, stream);
+        if (rc) return rc;
+        TVG_CUDA(cudaEventRecord(ctx->events[2 * c + 1], st));
+        TVG_CUDA(cudaStreamWaitEvent(ctx->s_out, ctx->events[2 * c + 1], 0));
+        cudaStream_t so = ctx->s_out;
+#define TVG_DOWN(hptr, dptr, off, bytes)                                                               \
+    do {                                                                                               \
+        if (hptr) {                                                                                    \
+            TVG_CUDA(cudaMemcpyAsync((hptr) + (off), (dptr) + (off), (bytes), cudaMemcpyDeviceToHost, so)); \
+            d2h += (long long)(bytes);                                                                 \
+        }                                                                                              \
     } while (0)
-    TVG_DOWN(hio->idx, idx, B * N * 2 * sizeof(int32_t));
-    TVG_DOWN(hio->dist, dist, B * N * 2 * sizeof(int32_t));
-    TVG_DOWN(hio->qidx, qidx, B * N * sizeof(int32_t));
-    TVG_DOWN(hio->tidx, tidx, B * N * sizeof(int32_t));
-    TVG_DOWN(hio->m_count, m_count, B * sizeof(int32_t));
-    TVG_DOWN(hio->best, best, B * sizeof(int32_t));
-    TVG_DOWN(hio->counts, counts, B * H * sizeof(int32_t));
-    TVG_DOWN(hio->n_inl, n_inl, B * sizeof(int32_t));
-    TVG_DOWN(hio->inl_idx, inl_idx, B * N * sizeof(int32_t));
-    TVG_DOWN(hio->status, status, B * sizeof(int32_t));
-    TVG_DOWN(hio->E, E, B * 9 * sizeof(double));
-    TVG_DOWN(hio->E_best, E_best, B * 9 * sizeof(double));
-    TVG_DOWN(hio->Rt, Rt, B * 16 * sizeof(double));
-    TVG_DOWN(hio->poses, poses, (B + nseq) * 16 * sizeof(double));
-    TVG_DOWN(hio->points4d, points, B * N * 4 * sizeof(double));
-    TVG_DOWN(hio->mask, mask, B * N);
-    TVG_DOWN(hio->good, good, B * N);
+        const size_t nbz = (size_t)nb;
+        TVG_DOWN(hio->idx, idx, (size_t)b0 * N * 2, nbz * N * 2 * sizeof(int32_t));
+        TVG_DOWN(hio->dist, dist, (size_t)b0 * N * 2, nbz * N * 2 * sizeof(int32_t));
+        TVG_DOWN(hio->qidx, qidx, (size_t)b0 * N, nbz * N * sizeof(int32_t));
+        TVG_DOWN(hio->tidx, tidx, (size_t)b0 * N, nbz * N * sizeof(int32_t));
+        TVG_DOWN(hio->m_count, m_count, (size_t)b0, nbz * sizeof(int32_t));
+        TVG_DOWN(hio->best, best, (size_t)b0, nbz * sizeof(int32_t));
+        TVG_DOWN(hio->counts, counts, (size_t)b0 * H, nbz * H * sizeof(int32_t));
+        TVG_DOWN(hio->n_inl, n_inl, (size_t)b0, nbz * sizeof(int32_t));
+        TVG_DOWN(hio->inl_idx, inl_idx, (size_t)b0 * N, nbz * N * sizeof(int32_t));
+        TVG_DOWN(hio->status, status, (size_t)b0, nbz * sizeof(int32_t));
+        TVG_DOWN(hio->E, E, (size_t)b0 * 9, nbz * 9 * sizeof(double));
+        TVG_DOWN(hio->E_best, E_best, (size_t)b0 * 9, nbz * 9 * sizeof(double));
+        TVG_DOWN(hio->Rt, Rt, (size_t)b0 * 16, nbz * 16 * sizeof(double));
+        TVG_DOWN(hio->points4d, points, (size_t)b0 * N * 4, nbz * N * 4 * sizeof(double));
+        TVG_DOWN(hio->mask, mask, (size_t)b0 * N, nbz * N);
+        TVG_DOWN(hio->good, good, (size_t)b0 * N, nbz * N);
+        // pose rows of this chunk: [row0, row0 + nb + n_local)
+        const size_t prow = (c == 0 || !first_init) ? row0 : row0 + 1, pend = row0 + nbz + (size_t)n_local[c];
+        TVG_DOWN(hio->poses, poses, prow * 16, (pend - prow) * 16 * sizeof(double));
 #undef TVG_DOWN
+    }
+    TVG_CUDA(cudaStreamSynchronize(ctx->s_out));
     TVG_CUDA(cudaStreamSynchronize(st));
     if (bytes_h2d) *bytes_h2d = h2d;
     if (bytes_d2h) *bytes_d2h = d2h;

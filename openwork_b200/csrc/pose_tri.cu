@@ -32,7 +32,8 @@ __global__ void pose_chain_kernel(const PoseChainParams p, int nseq) {
     if (s >= nseq) return;
     const int b0 = p.seq_off[s], b1 = p.seq_off[s + 1];
     double cur[16], inv[16];
-    for (int i = 0; i < 16; ++i) cur[i] = p.init_pose ? p.init_pose[(size_t)s * 16 + i] : ((i % 5 == 0) ? 1.0 : 0.0);
+    const double* init = (s == 0 && p.first_init) ? p.first_init : (p.init_pose ? p.init_pose + (size_t)s * 16 : nullptr);
+    for (int i = 0; i < 16; ++i) cur[i] = init ? init[i] : ((i % 5 == 0) ? 1.0 : 0.0);
     inverse4(cur, inv);
     for (int i = 0; i < 16; ++i) p.poses[(size_t)(b0 + s) * 16 + i] = cur[i];
     for (int b = b0; b < b1; ++b) {

@@ -15,8 +15,9 @@
 //                   best lower bound (fp32 cannot be trusted closer than the band).
 //   ransac_rescore  exact fp64 residuals for the listed candidates (count, sum r^2 over ALL points).
 //   ransac_refit    picks best = (max count, min sum r^2, earliest), writes the PRE-refit inlier mask,
-//                   compacts the inliers, re-estimates E on them (A^T A in fp64 + warp-parallel
-//                   Jacobi eigen-solve), and runs extract_Rt on the refit E.
+//                   compacts the inliers and accumulates the refit system A^T A (fp64, Hartley-normalised).
+//   ransac_solve    one warp per pair: warp-parallel Jacobi eigen-solve of A^T A, (s,s,0) projection,
+//                   de-normalisation, extract_Rt on the refit E.
 #include "tvg_linalg.cuh"
 #include "tvg_kernels.h"
 
@@ -166,7 +167,7 @@ __global__ void __launch_bounds__(SCORE_THREADS) ransac_score_kernel(const Ransa
 #pragma unroll
     for (int i = 0; i < 9; ++i) e[i] = live ? p.E32[((size_t)b * 9 + i) * p.H + h] : 0.0f;
 
-    int cnt = 0, unc = 0;
+    unsigned int cnt = 0, unc = 0;
     float sse = 0.0f;
     if (rows > 0) {
         mbar_wait(&bar, 0);
@@ -183,14 +184,17 @@ __global__ void __launch_bounds__(SCORE_THREADS) ransac_score_kernel(const Ransa
             const float num = fmaf(c.z, f0, fmaf(c.w, f1, f2));
             const float den = fmaf(f0, f0, fmaf(f1, f1, fmaf(g0, g0, g1 * g1)));
             const float n2 = num * num;
-            const float t = fmaf(-thr2, den, n2);     // r < thr  <=>  num^2 - thr^2 den < 0
-            cnt += (t < 0.0f) ? 1 : 0;
-            unc += (fabsf(t) <= band * den) ? 1 : 0;
-            sse = fmaf(n2, __frcp_rn(den), sse);
+            const float t = fmaf(-thr2, den, n2);              // r < thr  <=>  num^2 - thr^2 den < 0
+            const float bt = fmaf(-band, den, fabsf(t));       // |t| < band*den : too close for fp32 to call
+            cnt += __float_as_uint(t) >> 31;                   // sign bit == (t < 0)
+            unc += __float_as_uint(bt) >> 31;
+            float rinv;
+            asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(rinv) : "f"(den));
+            sse = fmaf(n2, rinv, sse);
         }
     }
     if (live) {
-        p.part_cnt[oc + h] = make_int2(cnt, unc);
+        p.part_cnt[oc + h] = make_int2((int)cnt, (int)unc);
         p.part_sse[oc + h] = sse;
     }
 }
@@ -312,6 +316,8 @@ cudaError_t launch_ransac_rescore(const RansacParams& p, int batch, cudaStream_t
 
 // ------------------------------------------------------------------------------------ select + mask + refit
 constexpr int REFIT_THREADS = 256;
+constexpr int REFIT_WS = 64;   // doubles of hand-off per pair between the accumulate and solve kernels
+int ransac_refit_ws_doubles() { return REFIT_WS; }
 
 // Smallest-eigenvalue eigenvector of a symmetric 9x9 matrix by parallel-order cyclic Jacobi on one warp.
 // G and V live in shared memory; each round applies four disjoint rotations (round-robin tournament).
@@ -376,9 +382,8 @@ __device__ void jacobi_eig9_warp(double (*G)[9], double (*V)[9], double* cs /*[8
     for (int i = 0; i < 9; ++i) out[i] = V[i][best];
 }
 
-__global__ void __launch_bounds__(REFIT_THREADS) ransac_refit_kernel(const RansacParams p) {
+__global__ void __launch_bounds__(REFIT_THREADS, 2) ransac_refit_kernel(const RansacParams p) {
     __shared__ double s_buf[REFIT_THREADS / 32];
-    __shared__ double s_G[9][9], s_V[9][9], s_cs[8];
     __shared__ double s_acc[45][REFIT_THREADS / 32];
     __shared__ int s_cnt[REFIT_THREADS / 32], s_bc[REFIT_THREADS / 32], s_bh[REFIT_THREADS / 32];
     __shared__ double s_bs[REFIT_THREADS / 32];
@@ -428,6 +433,7 @@ __global__ void __launch_bounds__(REFIT_THREADS) ransac_refit_kernel(const Ransa
             p.status[b] = (M <= 8) ? 1 : 2;
             for (int i = 0; i < 9; ++i) { p.E[b * 9 + i] = qnan; p.E_best[b * 9 + i] = qnan; }
             for (int i = 0; i < 16; ++i) p.Rt[b * 16 + i] = qnan;
+            p.refit_ws[(size_t)b * REFIT_WS + 51] = 0.0;
         }
         return;
     }
@@ -484,78 +490,108 @@ __global__ void __launch_bounds__(REFIT_THREADS) ransac_refit_kernel(const Ransa
 #pragma unroll
         for (int i = 0; i < 9; ++i) p.E_best[b * 9 + i] = Eb[i];
     }
-    double E[9];
+    double* ws = p.refit_ws + (size_t)b * REFIT_WS;
     if (total < 8) {  // skimage's refit would raise; report the un-refit model
+        if (tid == 0) {
+            ws[51] = 1.0;
 #pragma unroll
-        for (int i = 0; i < 9; ++i) E[i] = Eb[i];
-    } else {
-        // ---- Hartley normalisation of the inlier set
-        double c[4];
-#pragma unroll
-        for (int k = 0; k < 4; ++k) c[k] = block_sum_f64<REFIT_THREADS>(sum[k], s_buf) / (double)total;
-        double qs = 0.0, qd = 0.0;
-        for (int m = lo; m < hi; ++m) {
-            if (!p.mask[ob + m]) continue;
-            const double2 s = src[m], d = dst[m];
-            qs = fma(s.x - c[0], s.x - c[0], qs); qs = fma(s.y - c[1], s.y - c[1], qs);
-            qd = fma(d.x - c[2], d.x - c[2], qd); qd = fma(d.y - c[3], d.y - c[3], qd);
+            for (int i = 0; i < 9; ++i) ws[52 + i] = Eb[i];
         }
-        qs = block_sum_f64<REFIT_THREADS>(qs, s_buf);
-        qd = block_sum_f64<REFIT_THREADS>(qd, s_buf);
-        const double ss = 1.4142135623730951 / sqrt(qs / (double)total);
-        const double sd = 1.4142135623730951 / sqrt(qd / (double)total);
-        // ---- A^T A (upper triangle, 45 sums) in fp64
-        double acc[45];
+        return;
+    }
+    // ---- Hartley normalisation of the inlier set
+    double c[4];
 #pragma unroll
-        for (int i = 0; i < 45; ++i) acc[i] = 0.0;
-        for (int m = lo; m < hi; ++m) {
-            if (!p.mask[ob + m]) continue;
-            const double2 s = src[m], d = dst[m];
-            const double xs = ss * s.x - ss * c[0], ys = ss * s.y - ss * c[1];
-            const double xd = sd * d.x - sd * c[2], yd = sd * d.y - sd * c[3];
-            const double a[9] = {xd * xs, xd * ys, xd, yd * xs, yd * ys, yd, xs, ys, 1.0};
-            int t = 0;
+    for (int k = 0; k < 4; ++k) c[k] = block_sum_f64<REFIT_THREADS>(sum[k], s_buf) / (double)total;
+    double qs = 0.0, qd = 0.0;
+    for (int m = lo; m < hi; ++m) {
+        if (!p.mask[ob + m]) continue;
+        const double2 s = src[m], d = dst[m];
+        qs = fma(s.x - c[0], s.x - c[0], qs); qs = fma(s.y - c[1], s.y - c[1], qs);
+        qd = fma(d.x - c[2], d.x - c[2], qd); qd = fma(d.y - c[3], d.y - c[3], qd);
+    }
+    qs = block_sum_f64<REFIT_THREADS>(qs, s_buf);
+    qd = block_sum_f64<REFIT_THREADS>(qd, s_buf);
+    const double ss = 1.4142135623730951 / sqrt(qs / (double)total);
+    const double sd = 1.4142135623730951 / sqrt(qd / (double)total);
+    // ---- A^T A (upper triangle, 45 sums) in fp64
+    double acc[45];
 #pragma unroll
-            for (int i = 0; i < 9; ++i)
+    for (int i = 0; i < 45; ++i) acc[i] = 0.0;
+    for (int m = lo; m < hi; ++m) {
+        if (!p.mask[ob + m]) continue;
+        const double2 s = src[m], d = dst[m];
+        const double xs = ss * s.x - ss * c[0], ys = ss * s.y - ss * c[1];
+        const double xd = sd * d.x - sd * c[2], yd = sd * d.y - sd * c[3];
+        const double a[9] = {xd * xs, xd * ys, xd, yd * xs, yd * ys, yd, xs, ys, 1.0};
+        int t = 0;
 #pragma unroll
-                for (int j = i; j < 9; ++j) { acc[t] = fma(a[i], a[j], acc[t]); ++t; }
-        }
+        for (int i = 0; i < 9; ++i)
 #pragma unroll
-        for (int i = 0; i < 45; ++i) {
-            const double v = warp_sum_f64(acc[i]);
-            if (lane == 0) s_acc[i][warp] = v;
-        }
-        __syncthreads();
-        if (tid < 45) {
-            double v = 0.0;
+            for (int j = i; j < 9; ++j) { acc[t] = fma(a[i], a[j], acc[t]); ++t; }
+    }
 #pragma unroll
-            for (int w = 0; w < REFIT_THREADS / 32; ++w) v += s_acc[tid][w];
-            // unpack upper-triangle index tid -> (i, j)
-            int i = 0, rem = tid;
-            while (rem >= 9 - i) { rem -= 9 - i; ++i; }
-            const int j = i + rem;
-            s_G[i][j] = v;
-            s_G[j][i] = v;
-        }
-        __syncthreads();
-        if (warp == 0) {
-            double n[9];
-            jacobi_eig9_warp(s_G, s_V, s_cs, n);
-            if (lane == 0) {
-                double En[9];
-                essential_project(n, En);
-                essential_denormalise(En, ss, c[0], c[1], sd, c[2], c[3], E);
-                bool fin = true;
+    for (int i = 0; i < 45; ++i) {
+        const double v = warp_sum_f64(acc[i]);
+        if (lane == 0) s_acc[i][warp] = v;
+    }
+    __syncthreads();
+    if (tid < 45) {
+        double v = 0.0;
 #pragma unroll
-                for (int i = 0; i < 9; ++i) fin = fin && isfinite(E[i]);
-                if (!fin) {
-#pragma unroll
-                    for (int i = 0; i < 9; ++i) E[i] = Eb[i];
-                }
-            }
-        }
+        for (int w = 0; w < REFIT_THREADS / 32; ++w) v += s_acc[tid][w];
+        ws[tid] = v;
     }
     if (tid == 0) {
+        ws[45] = ss; ws[46] = c[0]; ws[47] = c[1]; ws[48] = sd; ws[49] = c[2]; ws[50] = c[3];
+        ws[51] = 2.0;
+#pragma unroll
+        for (int i = 0; i < 9; ++i) ws[52 + i] = Eb[i];
+    }
+}
+
+// One warp per pair: smallest eigenvector of A^T A, (s,s,0) projection, de-normalisation, extract_Rt.
+// Split from the accumulation kernel so that all pairs' (latency-bound) solves run concurrently.
+constexpr int SOLVE_WARPS = 4;
+
+__global__ void __launch_bounds__(SOLVE_WARPS * 32) ransac_solve_kernel(const RansacParams p, int batch) {
+    __shared__ double s_G[SOLVE_WARPS][9][9], s_V[SOLVE_WARPS][9][9], s_cs[SOLVE_WARPS][8];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int b = blockIdx.x * SOLVE_WARPS + warp;
+    if (b >= batch) return;
+    const double* ws = p.refit_ws + (size_t)b * REFIT_WS;
+    const int flag = (int)ws[51];
+    if (flag == 0) return;   // no model: NaNs already written
+    double E[9];
+    if (flag == 2) {
+        for (int t = lane; t < 45; t += 32) {
+            int i = 0, rem = t;
+            while (rem >= 9 - i) { rem -= 9 - i; ++i; }
+            const int j = i + rem;
+            const double v = ws[t];
+            s_G[warp][i][j] = v;
+            s_G[warp][j][i] = v;
+        }
+        __syncwarp();
+        double n[9];
+        jacobi_eig9_warp(s_G[warp], s_V[warp], s_cs[warp], n);
+        if (lane == 0) {
+            double En[9];
+            essential_project(n, En);
+            essential_denormalise(En, ws[45], ws[46], ws[47], ws[48], ws[49], ws[50], E);
+            bool fin = true;
+#pragma unroll
+            for (int i = 0; i < 9; ++i) fin = fin && isfinite(E[i]);
+            if (!fin) {
+#pragma unroll
+                for (int i = 0; i < 9; ++i) E[i] = ws[52 + i];
+            }
+        }
+    } else {
+#pragma unroll
+        for (int i = 0; i < 9; ++i) E[i] = ws[52 + i];
+    }
+    if (lane == 0) {
         double Rt[16];
         extract_rt(E, Rt);
 #pragma unroll
@@ -567,6 +603,9 @@ __global__ void __launch_bounds__(REFIT_THREADS) ransac_refit_kernel(const Ransa
 
 cudaError_t launch_ransac_refit(const RansacParams& p, int batch, cudaStream_t stream) {
     ransac_refit_kernel<<<batch, REFIT_THREADS, 0, stream>>>(p);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+    ransac_solve_kernel<<<(batch + SOLVE_WARPS - 1) / SOLVE_WARPS, SOLVE_WARPS * 32, 0, stream>>>(p, batch);
     return cudaGetLastError();
 }
 

@@ -92,6 +92,7 @@ struct RansacParams {
     double* E;                 // [batch][9]  refit on the inliers
     double* Rt;                // [batch][16]
     int32_t* status;           // [batch] 0 ok, 1 = fewer than 9 correspondences
+    double* refit_ws;          // [batch][ransac_refit_ws_doubles()] accumulate -> solve hand-off
 };
 cudaError_t launch_ransac_fit(const RansacParams& p, int batch, cudaStream_t stream);
 cudaError_t launch_ransac_score(const RansacParams& p, int batch, cudaStream_t stream);
@@ -99,6 +100,7 @@ cudaError_t launch_ransac_reduce(const RansacParams& p, int batch, cudaStream_t 
 cudaError_t launch_ransac_rescore(const RansacParams& p, int batch, cudaStream_t stream);
 cudaError_t launch_ransac_refit(const RansacParams& p, int batch, cudaStream_t stream);
 int ransac_score_chunk_rows();
+int ransac_refit_ws_doubles();
 
 // ---------------------------------------------------------------- pose + triangulation (pose_tri.cu)
 struct PoseChainParams {
@@ -107,6 +109,7 @@ struct PoseChainParams {
     const double* init_pose;   // [nseq][16] (NULL -> identity)
     double* poses;             // [batch + nseq][16]  pose of pair b's LAST frame at [b + s], CURR at [b + s + 1]
     double* pair_pinv;         // [batch][2][16] inv(last pose), inv(curr pose) per pair (may be NULL)
+    const double* first_init;  // device 4x4 overriding the initial pose of sequence 0 of this launch (may be NULL)
 };
 cudaError_t launch_pose_chain(const PoseChainParams& p, int nseq, cudaStream_t stream);
 

@@ -290,30 +290,69 @@ def test_pairs_device_sequence_matches_oracle(ops):
     _check_sequence(ops, out, frames, words, H, [(i, i + 1) for i in range(F - 1)])
 
 
-def test_pairs_host_entry_matches_device_entry(ops):
-    F, N, H = 4, 512, 128
+@pytest.mark.parametrize("chunk,seq_off", [(128, None), (2, None), (1, None), (2, [0, 3, 4, 7]), (3, [0, 1, 7])])
+def test_pairs_host_entry_matches_device_entry(ops, chunk, seq_off):
+    """tvg_pairs_host (chunked copy/compute pipeline, sequences continuing across chunks) == device entry."""
+    npairs, N, H = 7, 512, 128
+    nseq = 1 if seq_off is None else len(seq_off) - 1
+    F = npairs + nseq
     frames, _ = synth.make_sequence(F, N, seed=5)
     des = np.stack([f[1] for f in frames])
     kps = np.stack([f[0] for f in frames])
     words = synth.sample_words(H, 8)
-    outs = ("m_count", "E", "n_inl", "Rt", "poses", "points4d", "good", "status", "best")
+    so = None if seq_off is None else np.array(seq_off, dtype=np.int32)
+    outs = ("m_count", "E", "n_inl", "Rt", "poses", "points4d", "good", "status", "best", "mask", "qidx")
     dev = ops.process_pairs_device(torch.from_numpy(des).cuda(), torch.from_numpy(kps).cuda(), K, words=words,
-                                   outputs=outs)
-    host, h2d, d2h = ops.process_pairs_host(des, kps, K, words=words, outputs=outs)
-    assert h2d == des.nbytes + kps.nbytes + words.nbytes
+                                   seq_off=so, outputs=outs)
+    ctx = ops.context(0)
+    try:
+        ctx.set_host_chunk(chunk)
+        host, h2d, d2h = ops.process_pairs_host(des, kps, K, words=words, seq_off=so, outputs=outs)
+    finally:
+        ctx.set_host_chunk(256)
+    assert h2d == des.nbytes + kps.nbytes + words.nbytes + 4 * (nseq + 1)
     assert d2h == sum(host[k].numel() * host[k].element_size() for k in outs)
+    assert (host["status"].numpy() == 0).all()
     for k in outs:
         a, b = dev[k].cpu().numpy(), host[k].numpy()
-        if k == "points4d":
-            for i in range(F - 1):
+        if k in ("points4d", "good"):
+            for i in range(npairs):
                 n = int(host["n_inl"][i])
-                assert np.array_equal(a[i, :n], b[i, :n])
-        elif k == "good":
-            for i in range(F - 1):
-                n = int(host["n_inl"][i])
-                assert np.array_equal(a[i, :n], b[i, :n])
+                assert np.array_equal(a[i, :n], b[i, :n]), (k, i)
+        elif k in ("mask", "qidx"):
+            for i in range(npairs):
+                n = int(host["m_count"][i])
+                assert np.array_equal(a[i, :n], b[i, :n]), (k, i)
         else:
             assert np.array_equal(a, b, equal_nan=True), k
+
+
+def test_pairs_host_explicit_pair_lists(ops):
+    """Arbitrary (curr, last) frame lists, each pair its own sequence, chunked."""
+    N, H = 400, 64
+    frames, _ = synth.make_sequence(6, N, seed=17)
+    des = np.stack([f[1] for f in frames])
+    kps = np.stack([f[0] for f in frames])
+    words = synth.sample_words(H, 3)
+    pq = np.array([1, 3, 5, 2, 4], dtype=np.int32)
+    pt = np.array([0, 2, 4, 1, 3], dtype=np.int32)
+    so = np.arange(6, dtype=np.int32)
+    outs = ("m_count", "E", "n_inl", "Rt", "poses", "status", "best")
+    dev = ops.process_pairs_device(torch.from_numpy(des).cuda(), torch.from_numpy(kps).cuda(), K, words=words,
+                                   pair_q=pq, pair_t=pt, seq_off=so, outputs=outs)
+    ctx = ops.context(0)
+    try:
+        ctx.set_host_chunk(2)
+        host, h2d, d2h = ops.process_pairs_host(des, kps, K, words=words, pair_q=pq, pair_t=pt, seq_off=so,
+                                                outputs=outs)
+    finally:
+        ctx.set_host_chunk(256)
+    for k in outs:
+        assert np.array_equal(dev[k].cpu().numpy(), host[k].numpy(), equal_nan=True), k
+    for b in range(5):
+        (lk, ld), (ck, cd) = frames[pt[b]], frames[pq[b]]
+        ref = tv.process_pair(lk, ld, ck, cd, np.eye(4), K, words=words)
+        assert int(host["best"][b]) == ref["ransac"]["best"] and int(host["n_inl"][b]) == int(ref["inliers"].sum())
 
 
 def test_pairs_two_sequences(ops):
