@@ -363,7 +363,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--pairs", type=int, default=1024, help="frame pairs per step per GPU")
     ap.add_argument("--knn-r", type=int, default=4)
-    ap.add_argument("--knn-variant", type=int, default=1)
+    ap.add_argument("--knn-variant", type=int, default=3)
     ap.add_argument("--knn-ctas", type=int, default=6)
     ap.add_argument("--host-chunk", type=int, default=256, help="pairs per chunk of the e2e host pipeline")
     ap.add_argument("--no-cpu-baseline", action="store_true")

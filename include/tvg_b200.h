@@ -42,8 +42,9 @@ TVG_API const char* tvg_last_error(void);
 TVG_API int tvg_abi_version(void);
 /* Number of CUDA kernels this library has launched through `ctx` since creation (bench.py: gpu_launches). */
 TVG_API long long tvg_launch_count(const tvg_ctx* ctx);
-/* Matcher tuning: queries per thread r in {2,4,8}, popcount variant 0 = 8xPOPC, 1 = Harley-Seal 4xPOPC,
- * 2 = 5xPOPC; ctas_per_sm sizes the split-Nt grid.  Results are bit-identical for every setting. */
+/* Matcher tuning: queries per thread r in {2,4,8}; popcount variant 0 = 8xPOPC, 1 = Harley-Seal 4xPOPC,
+ * 2 = 5xPOPC, 3 = Harley-Seal with query/train-shared XOR combos (14 LOP3 + 4 POPC); +4 (variants 5, 7) =
+ * lazy top-2 insertion; ctas_per_sm sizes the split-Nt grid.  Results are bit-identical for every setting. */
 TVG_API int tvg_set_matcher_config(tvg_ctx* ctx, int r, int variant, int ctas_per_sm);
 
 /* cv2.BFMatcher(cv2.NORM_HAMMING).knnMatch(q, t, k=2)  (slam.py:126-127) + the Lowe ratio flag

@@ -44,7 +44,7 @@ enum Slot {
 struct tvg_ctx {
     int device = 0;
     int sm_count = 148;
-    int knn_r = 4, knn_variant = 0, knn_ctas_per_sm = 6;
+    int knn_r = 4, knn_variant = 3, knn_ctas_per_sm = 6;
     long long launches = 0;
     int host_chunk_pairs = 256;
     cudaStream_t s_in = nullptr, s_out = nullptr;
@@ -155,8 +155,8 @@ long long tvg_launch_count(const tvg_ctx* ctx) { return ctx ? ctx->launches : 0;
 
 int tvg_set_matcher_config(tvg_ctx* ctx, int r, int variant, int ctas_per_sm) {
     if (!ctx) return fail(-1, "ctx is NULL");
-    if (!(r == 2 || r == 4 || r == 8) || variant < 0 || variant > 2 || ctas_per_sm < 1 || ctas_per_sm > 16)
-        return fail(-2, "tvg_set_matcher_config: r in {2,4,8}, variant in {0,1,2}, ctas_per_sm in [1,16]");
+    if (!(r == 2 || r == 4 || r == 8) || !(variant >= 0 && variant <= 3 || variant == 5 || variant == 7) || ctas_per_sm < 1 || ctas_per_sm > 16)
+        return fail(-2, "tvg_set_matcher_config: r in {2,4,8}, variant in {0,1,2,3,5,7}, ctas_per_sm in [1,16]");
     ctx->knn_r = r;
     ctx->knn_variant = variant;
     ctx->knn_ctas_per_sm = ctas_per_sm;
@@ -180,6 +180,7 @@ int tvg_knn2_hamming256(tvg_ctx* ctx, const uint8_t* q_des, const uint8_t* t_des
     p.q_count = q_count; p.t_count = t_count;
     p.n_max = n_max; p.nq = nq; p.nt = nt;
     p.idx = idx; p.dist = dist; p.keep = keep; p.ratio = ratio;
+    p.key_mul = 1u << TVG_KEY_SHIFT; p.w2 = 2u;
     const int bq = tvg::knn2_block_queries(ctx->knn_r);
     const int qtiles = (n_max + bq - 1) / bq;
     const long long slots = (long long)ctx->sm_count * ctx->knn_ctas_per_sm;

@@ -67,10 +67,133 @@ __device__ __forceinline__ void knn2_emit(const KnnParams& p, size_t o, uint32_t
     if (p.keep) p.keep[o] = (k2 != TVG_SENTINEL_KEY) && ((double)di.x < p.ratio * (double)di.y);
 }
 
-template <int R, int THREADS, int CH, int STAGES, int VARIANT>
+// mad.lo with a multiplier the compiler cannot see (kernel parameter): stays an IMAD on the FMA pipe
+// instead of being strength-reduced to LEA / SHF on the (saturated) ALU pipe.
+__device__ __forceinline__ uint32_t imad(uint32_t a, uint32_t b, uint32_t c) {
+    uint32_t d;
+    asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+    return d;
+}
+
+// VARIANT 3: Harley-Seal with the first-level carry-save adders sharing XOR work between the query and
+// the train row.  With x_i = q_i ^ t_i :  sum(x0,x1,x2) = Q012 ^ T012  and
+// maj(x0,x1,x2) = x0 ^ ((x0^x1) & (x0^x2)) = (q0^t0) ^ ((Q01^T01) & (Q02^T02)), where Q01 = q0^q1 etc. are
+// computed once per query and T01 = t0^t1 etc. once per train row (by the CTA when the TMA tile lands).
+// 14 LOP3 + 4 POPC per comparison instead of 16 + 4.
+// Expanded train row (12 words): t0 T01 T02 T012 | t3 T34 T35 T345 | t6 T67 - -
+// Query combos (10 words):       q0 Q01 Q02 Q012   q3 Q34 Q35 Q345   q6 Q67
+__device__ __forceinline__ uint32_t lop3_and_xor(uint32_t a, uint32_t b, uint32_t c) {  // a & (b ^ c)
+    uint32_t d;
+    asm("lop3.b32 %0, %1, %2, %3, 0x60;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+    return d;
+}
+__device__ __forceinline__ uint32_t lop3_maj_via(uint32_t a, uint32_t b, uint32_t c) {  // a ^ (b & (a ^ c))
+    uint32_t d;
+    asm("lop3.b32 %0, %1, %2, %3, 0xB8;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+    return d;
+}
+__device__ __forceinline__ void expand_query(const uint32_t (&q)[8], uint32_t (&qc)[10]) {
+    qc[0] = q[0]; qc[1] = q[0] ^ q[1]; qc[2] = q[0] ^ q[2]; qc[3] = q[0] ^ q[1] ^ q[2];
+    qc[4] = q[3]; qc[5] = q[3] ^ q[4]; qc[6] = q[3] ^ q[5]; qc[7] = q[3] ^ q[4] ^ q[5];
+    qc[8] = q[6]; qc[9] = q[6] ^ q[7];
+}
+__device__ __forceinline__ uint32_t hamming256_x(const uint32_t (&qc)[10], const uint4& e0, const uint4& e1,
+                                                 const uint2& e2, uint32_t w2) {
+    // CSA over (x0,x1,x2)
+    const uint32_t ua = qc[1] ^ e0.y;
+    const uint32_t va = lop3_and_xor(ua, qc[2], e0.z);
+    const uint32_t ca = lop3_xor3(qc[0], e0.x, va);
+    const uint32_t sa = qc[3] ^ e0.w;
+    // CSA over (x3,x4,x5)
+    const uint32_t ub = qc[5] ^ e1.y;
+    const uint32_t vb = lop3_and_xor(ub, qc[6], e1.z);
+    const uint32_t cb = lop3_xor3(qc[4], e1.x, vb);
+    const uint32_t sb = qc[7] ^ e1.w;
+    // CSA over (x6,x7,sa)
+    const uint32_t uc = qc[9] ^ e2.y;          // x6 ^ x7
+    const uint32_t x6 = qc[8] ^ e2.x;
+    const uint32_t sc = uc ^ sa;
+    const uint32_t cc = lop3_maj_via(x6, uc, sa);
+    // CSA over the three carries
+    const uint32_t sd = lop3_xor3(ca, cb, cc), cd = lop3_maj(ca, cb, cc);
+    // weight 1: sb, sc ; weight 2: sd ; weight 4: cd
+    return imad(imad(__popc(cd), w2, __popc(sd)), w2, __popc(sb) + __popc(sc));
+}
+
+// Publish this CTA's top-2 (directly when the train rows are not split, else as partials that the last
+// CTA of the query tile merges with a warp-shuffle butterfly) and apply the ratio test.
+template <int R, int THREADS>
+__device__ __forceinline__ void knn2_finish(const KnnParams& p, int b, int qt, int split, int q0, int nq,
+                                            const uint32_t (&m1)[R], const uint32_t (&m2)[R], int* s_is_last) {
+    constexpr int BQ = R * THREADS;
+    const int tid = threadIdx.x;
+    const int32_t ob = b * p.n_max;
+    if (p.splits == 1) {
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            const int qi = q0 + r * THREADS + tid;
+            if (qi < nq) knn2_emit(p, (size_t)(ob + qi), m1[r], m2[r]);
+        }
+        return;
+    }
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+        const int qi = q0 + r * THREADS + tid;
+        if (qi < nq) p.partial[(size_t)(ob + qi) * p.splits + split] = make_uint2(m1[r], m2[r]);
+    }
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) {
+        unsigned int* ctr = p.tile_counters + (size_t)b * gridDim.x + qt;
+        const unsigned int old = atomicAdd(ctr, 1u);
+        *s_is_last = (old == (unsigned)p.splits - 1u);
+        if (*s_is_last) *ctr = 0u;  // self-resetting: the workspace stays zeroed between launches
+    }
+    __syncthreads();
+    if (!*s_is_last) return;
+    __threadfence();
+
+    const int warp = tid >> 5, lane = tid & 31;
+    const int qend = min(nq, q0 + BQ);
+    for (int qi = q0 + warp; qi < qend; qi += THREADS / 32) {
+        uint32_t a1 = TVG_SENTINEL_KEY, a2 = TVG_SENTINEL_KEY;
+        const uint2* pp = p.partial + (size_t)(ob + qi) * p.splits;
+        for (int s = lane; s < p.splits; s += 32) {
+            const uint2 v = __ldcg(pp + s);
+            top2_merge(a1, a2, v.x, v.y);
+        }
+#pragma unroll
+        for (int m = 16; m > 0; m >>= 1) {  // warp-shuffle top-2 butterfly
+            const uint32_t b1 = __shfl_xor_sync(0xffffffffu, a1, m);
+            const uint32_t b2 = __shfl_xor_sync(0xffffffffu, a2, m);
+            top2_merge(a1, a2, b1, b2);
+        }
+        if (lane == 0) knn2_emit(p, (size_t)(ob + qi), a1, a2);
+    }
+}
+
+// Top-2 update for four keys of one query.  LAZY: most groups cannot change the top-2, so test the group
+// minimum against the current second-best first (3 ALU ops per 4 comparisons instead of 12).
+template <bool LAZY>
+__device__ __forceinline__ void top2_insert4(uint32_t& m1, uint32_t& m2, uint32_t k0, uint32_t k1, uint32_t k2,
+                                             uint32_t k3) {
+    if (LAZY) {
+        const uint32_t kmin = min(min(k0, k1), min(k2, k3));
+        if (kmin >= m2) return;
+    }
+    top2_insert(m1, m2, k0);
+    top2_insert(m1, m2, k1);
+    top2_insert(m1, m2, k2);
+    top2_insert(m1, m2, k3);
+}
+
+template <int R, int THREADS, int CH, int STAGES, int VARIANT, bool LAZY>
 __global__ void __launch_bounds__(THREADS) knn2_kernel(const KnnParams p) {
     constexpr int BQ = R * THREADS;
+    constexpr bool X = (VARIANT == 3);
+    constexpr int QW = X ? 10 : 8;
     __shared__ alignas(128) uint4 tile[STAGES][CH * 2];
+    __shared__ alignas(16) uint4 xtile[X ? CH * 3 : 1];   // expanded rows (VARIANT 3)
     __shared__ alignas(8) uint64_t full_bar[STAGES];
     __shared__ int s_is_last;
 
@@ -89,8 +212,9 @@ __global__ void __launch_bounds__(THREADS) knn2_kernel(const KnnParams p) {
     const int row1 = min(nt, row0 + p.rows_per_split);
     const int nrows = row1 - row0;
     const int nchunks = (nrows + CH - 1) / CH;
+    const uint32_t key_mul = p.key_mul, w2 = p.w2;
 
-    uint32_t qd[R][8];
+    uint32_t qd[R][QW];
     uint32_t m1[R], m2[R];
 #pragma unroll
     for (int r = 0; r < R; ++r) {
@@ -100,8 +224,16 @@ __global__ void __launch_bounds__(THREADS) knn2_kernel(const KnnParams p) {
             a = __ldg(qv + 2 * (size_t)qi);
             c = __ldg(qv + 2 * (size_t)qi + 1);
         }
-        qd[r][0] = a.x; qd[r][1] = a.y; qd[r][2] = a.z; qd[r][3] = a.w;
-        qd[r][4] = c.x; qd[r][5] = c.y; qd[r][6] = c.z; qd[r][7] = c.w;
+        const uint32_t raw[8] = {a.x, a.y, a.z, a.w, c.x, c.y, c.z, c.w};
+        if (X) {
+            uint32_t qc[10];
+            expand_query(raw, qc);
+#pragma unroll
+            for (int i = 0; i < QW; ++i) qd[r][i] = qc[i];
+        } else {
+#pragma unroll
+            for (int i = 0; i < QW; ++i) qd[r][i] = raw[i];
+        }
         m1[r] = TVG_SENTINEL_KEY;
         m2[r] = TVG_SENTINEL_KEY;
     }
@@ -124,91 +256,82 @@ __global__ void __launch_bounds__(THREADS) knn2_kernel(const KnnParams p) {
         for (int c = 0; c < STAGES - 1 && c < nchunks; ++c) issue(c);
     }
 
+    // distance + key of query r against row j of the current chunk
+    auto key_of = [&](const uint4* __restrict__ tp, int j, int r, uint32_t jg) -> uint32_t {
+        uint32_t d;
+        if (X) {
+            const uint4 e0 = xtile[3 * j], e1 = xtile[3 * j + 1];
+            const uint4 e2 = xtile[3 * j + 2];
+            uint32_t qc[10];
+#pragma unroll
+            for (int i = 0; i < 10; ++i) qc[i] = qd[r][i < QW ? i : 0];
+            d = hamming256_x(qc, e0, e1, make_uint2(e2.x, e2.y), w2);
+        } else {
+            uint32_t q8[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) q8[i] = qd[r][i];
+            d = hamming256<VARIANT>(q8, tp[2 * j], tp[2 * j + 1]);
+        }
+        return imad(d, key_mul, jg);
+    };
+
     for (int c = 0; c < nchunks; ++c) {
         const int st = c % STAGES;
         if (tid == 0 && c + STAGES - 1 < nchunks) issue(c + STAGES - 1);
         mbar_wait(&full_bar[st], (uint32_t)((c / STAGES) & 1));
         const int rows = min(CH, nrows - c * CH);
         const uint4* __restrict__ tp = &tile[st][0];
-        uint32_t jg = (uint32_t)(row0 + c * CH);
-#pragma unroll 4
-        for (int j = 0; j < rows; ++j, ++jg) {
-            const uint4 t0 = tp[2 * j];
-            const uint4 t1 = tp[2 * j + 1];
+        if (X) {
+            // cooperative expansion of the landed rows: one row per thread
+            for (int j = tid; j < rows; j += THREADS) {
+                const uint4 a = tp[2 * j], d = tp[2 * j + 1];
+                xtile[3 * j] = make_uint4(a.x, a.x ^ a.y, a.x ^ a.z, a.x ^ a.y ^ a.z);
+                xtile[3 * j + 1] = make_uint4(a.w, a.w ^ d.x, a.w ^ d.y, a.w ^ d.x ^ d.y);
+                xtile[3 * j + 2] = make_uint4(d.z, d.z ^ d.w, 0u, 0u);
+            }
+            __syncthreads();
+        }
+        const uint32_t jbase = (uint32_t)(row0 + c * CH);
+        int j = 0;
+        for (; j + 4 <= rows; j += 4) {
 #pragma unroll
             for (int r = 0; r < R; ++r) {
-                const uint32_t d = hamming256<VARIANT>(qd[r], t0, t1);
-                const uint32_t key = d * (1u << TVG_KEY_SHIFT) + jg;
-                top2_insert(m1[r], m2[r], key);
+                const uint32_t k0 = key_of(tp, j, r, jbase + j);
+                const uint32_t k1 = key_of(tp, j + 1, r, jbase + j + 1);
+                const uint32_t k2 = key_of(tp, j + 2, r, jbase + j + 2);
+                const uint32_t k3 = key_of(tp, j + 3, r, jbase + j + 3);
+                top2_insert4<LAZY>(m1[r], m2[r], k0, k1, k2, k3);
             }
         }
-        __syncthreads();  // every warp is done with stage st before TMA refills it
-    }
-
-    const int32_t ob = b * p.n_max;
-    if (p.splits == 1) {
+        for (; j < rows; ++j) {
 #pragma unroll
-        for (int r = 0; r < R; ++r) {
-            const int qi = q0 + r * THREADS + tid;
-            if (qi < nq) knn2_emit(p, (size_t)(ob + qi), m1[r], m2[r]);
+            for (int r = 0; r < R; ++r) top2_insert(m1[r], m2[r], key_of(tp, j, r, jbase + j));
         }
-        return;
+        __syncthreads();  // every warp is done with stage st (and xtile) before they are refilled
     }
-
-    // ---- split-Nt: publish partials, last CTA of this query tile merges -------------------
-#pragma unroll
-    for (int r = 0; r < R; ++r) {
-        const int qi = q0 + r * THREADS + tid;
-        if (qi < nq) p.partial[(size_t)(ob + qi) * p.splits + split] = make_uint2(m1[r], m2[r]);
-    }
-    __threadfence();
-    __syncthreads();
-    if (tid == 0) {
-        unsigned int* ctr = p.tile_counters + (size_t)b * gridDim.x + qt;
-        const unsigned int old = atomicAdd(ctr, 1u);
-        s_is_last = (old == (unsigned)p.splits - 1u);
-        if (s_is_last) *ctr = 0u;  // self-resetting: the workspace stays zeroed between launches
-    }
-    __syncthreads();
-    if (!s_is_last) return;
-    __threadfence();
-
-    const int warp = tid >> 5, lane = tid & 31;
-    const int qend = min(nq, q0 + BQ);
-    for (int qi = q0 + warp; qi < qend; qi += THREADS / 32) {
-        uint32_t a1 = TVG_SENTINEL_KEY, a2 = TVG_SENTINEL_KEY;
-        const uint2* pp = p.partial + (size_t)(ob + qi) * p.splits;
-        for (int s = lane; s < p.splits; s += 32) {
-            const uint2 v = __ldcg(pp + s);
-            top2_merge(a1, a2, v.x, v.y);
-        }
-#pragma unroll
-        for (int m = 16; m > 0; m >>= 1) {  // warp-shuffle top-2 butterfly
-            const uint32_t b1 = __shfl_xor_sync(0xffffffffu, a1, m);
-            const uint32_t b2 = __shfl_xor_sync(0xffffffffu, a2, m);
-            top2_merge(a1, a2, b1, b2);
-        }
-        if (lane == 0) knn2_emit(p, (size_t)(ob + qi), a1, a2);
-    }
+    knn2_finish<R, THREADS>(p, b, qt, split, q0, nq, m1, m2, &s_is_last);
 }
 
-template <int R, int THREADS, int CH, int STAGES, int VARIANT>
+template <int R, int THREADS, int CH, int STAGES, int VARIANT, bool LAZY>
 static cudaError_t launch_cfg(const KnnParams& p, int batch, int qtiles, cudaStream_t stream) {
     dim3 grid(qtiles, p.splits, batch);
-    knn2_kernel<R, THREADS, CH, STAGES, VARIANT><<<grid, THREADS, 0, stream>>>(p);
+    knn2_kernel<R, THREADS, CH, STAGES, VARIANT, LAZY><<<grid, THREADS, 0, stream>>>(p);
     return cudaGetLastError();
 }
 
 int knn2_block_queries(int r) { return r * 128; }
 
+// variant: 0..3 popcount form, +4 = lazy top-2 insertion (variants 1 and 3 only)
 cudaError_t launch_knn2(const KnnParams& p, int batch, int r, int variant, cudaStream_t stream) {
     const int bq = knn2_block_queries(r);
     const int qtiles = (p.n_max + bq - 1) / bq;
-#define TVG_KNN_CASE(RR, VV) \
-    if (r == RR && variant == VV) return launch_cfg<RR, 128, 128, 3, VV>(p, batch, qtiles, stream);
-    TVG_KNN_CASE(4, 0) TVG_KNN_CASE(4, 1) TVG_KNN_CASE(4, 2)
-    TVG_KNN_CASE(2, 0) TVG_KNN_CASE(2, 1) TVG_KNN_CASE(2, 2)
-    TVG_KNN_CASE(8, 0) TVG_KNN_CASE(8, 1) TVG_KNN_CASE(8, 2)
+#define TVG_KNN_CASE(RR, VV, LZ) \
+    if (r == RR && variant == VV + (LZ ? 4 : 0)) return launch_cfg<RR, 128, 128, 3, VV, LZ>(p, batch, qtiles, stream);
+#define TVG_KNN_R(RR)                                                                                  \
+    TVG_KNN_CASE(RR, 0, false) TVG_KNN_CASE(RR, 1, false) TVG_KNN_CASE(RR, 2, false) TVG_KNN_CASE(RR, 3, false) \
+    TVG_KNN_CASE(RR, 1, true) TVG_KNN_CASE(RR, 3, true)
+    TVG_KNN_R(2) TVG_KNN_R(4) TVG_KNN_R(8)
+#undef TVG_KNN_R
 #undef TVG_KNN_CASE
     return cudaErrorInvalidValue;
 }

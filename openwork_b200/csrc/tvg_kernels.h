@@ -23,6 +23,7 @@ struct KnnParams {
     int32_t* dist;             // [batch][n_max][2]
     uint8_t* keep;             // [batch][n_max] ratio-test flag (may be NULL)
     double ratio;
+    uint32_t key_mul, w2;      // 1<<23 and 2, passed as data so the multiplies stay IMADs (FMA pipe)
 };
 cudaError_t launch_knn2(const KnnParams& p, int batch, int r, int variant, cudaStream_t stream);
 int knn2_block_queries(int r);

@@ -70,7 +70,8 @@ def test_knn2_empty(ops):
 
 
 @pytest.mark.parametrize("r,variant,ctas", [(2, 0, 6), (4, 0, 1), (4, 1, 6), (4, 2, 6), (8, 0, 4), (8, 1, 8),
-                                            (2, 1, 16), (2, 2, 3), (8, 2, 2)])
+                                            (2, 1, 16), (2, 2, 3), (8, 2, 2), (4, 3, 6), (2, 3, 2), (8, 3, 8),
+                                            (4, 5, 6), (2, 5, 1), (8, 5, 8), (4, 7, 6), (2, 7, 16), (8, 7, 3)])
 def test_knn2_every_config_is_bit_identical(ops, r, variant, ctas):
     q, t = synth.correlated_descriptors(3000, 2500, seed=r * 100 + variant * 10 + ctas)
     t[100:200] = t[300:400]
@@ -79,7 +80,7 @@ def test_knn2_every_config_is_bit_identical(ops, r, variant, ctas):
         ctx.set_matcher_config(r, variant, ctas)
         idx, dist, keep = ops.knn2_hamming256(q, t, return_keep=True)
     finally:
-        ctx.set_matcher_config(4, 0, 6)
+        ctx.set_matcher_config(4, 3, 6)
     ri, rd = tv.knn2_cv2(q, t)
     assert np.array_equal(idx.cpu().numpy(), ri) and np.array_equal(dist.cpu().numpy(), rd)
     qi, ti = tv.ratio_filter(ri, rd)
