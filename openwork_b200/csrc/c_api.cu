@@ -247,8 +247,8 @@ int tvg_ransac_essential(tvg_ctx* ctx, const tvg_ransac_io* io, void* stream) {
     p.sample_stride = io->sample_stride; p.samples_out = io->samples_out;
     p.thr = io->thr;
     p.band_rel = 2e-3f;  // |num^2 - thr^2 den| <= band_rel * thr^2 den  <=>  |r - thr| <~ 1e-3 thr = 5e-6
-    p.chunk = tvg::ransac_score_chunk_rows();
-    p.chunks = (io->n_max + p.chunk - 1) / p.chunk;
+    int score_mode = 0;
+    tvg::ransac_score_plan(io->batch, io->n_max, io->H, ctx->sm_count, &p.chunks, &p.chunk, &score_mode);
     TVG_OUT(ctx, io->models, S_E64, B * H * 9 * sizeof(double), p.E64, double*);
     TVG_GET(ctx, S_E32, B * H * 9 * sizeof(float), p.E32, float*);
     TVG_GET(ctx, S_VALID, B * H * sizeof(int32_t), p.valid, int32_t*);
@@ -278,7 +278,7 @@ int tvg_ransac_essential(tvg_ctx* ctx, const tvg_ransac_io* io, void* stream) {
     TVG_GET(ctx, S_REFITWS, B * tvg::ransac_refit_ws_doubles() * sizeof(double), p.refit_ws, double*);
     cudaStream_t st = (cudaStream_t)stream;
     TVG_CUDA(tvg::launch_ransac_fit(p, io->batch, st));
-    TVG_CUDA(tvg::launch_ransac_score(p, io->batch, st));
+    TVG_CUDA(tvg::launch_ransac_score(p, io->batch, score_mode, st));
     TVG_CUDA(tvg::launch_ransac_reduce(p, io->batch, st));
     TVG_CUDA(tvg::launch_ransac_rescore(p, io->batch, st));
     TVG_CUDA(tvg::launch_ransac_refit(p, io->batch, st));

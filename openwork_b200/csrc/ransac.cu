@@ -139,69 +139,121 @@ cudaError_t launch_ransac_fit(const RansacParams& p, int batch, cudaStream_t str
 }
 
 // ------------------------------------------------------------------------------------ score (fp32)
-constexpr int SCORE_THREADS = 128;   // hypotheses per CTA
-constexpr int SCORE_CHUNK = 256;     // correspondences resident in shared memory per CTA
-int ransac_score_chunk_rows() { return SCORE_CHUNK; }
+constexpr int SCORE_THREADS = 128;
 
-__global__ void __launch_bounds__(SCORE_THREADS) ransac_score_kernel(const RansacParams p) {
-    __shared__ alignas(128) float4 corr[SCORE_CHUNK];
-    __shared__ alignas(8) uint64_t bar;
-    const int b = blockIdx.z, chunk = blockIdx.y;
-    const int h = blockIdx.x * SCORE_THREADS + threadIdx.x;
+// One Sampson evaluation in fp32: 18 FFMA + 2 FMUL + 1 MUFU.RCP + 2 sign-bit adds.
+__device__ __forceinline__ void score_eval(const float (&e)[9], const float4 c, float thr2, float band,
+                                           unsigned& cnt, unsigned& unc, float& sse) {
+    // c = (x, y, u, v): x = src (last), u = dst (curr)
+    const float f0 = fmaf(e[0], c.x, fmaf(e[1], c.y, e[2]));
+    const float f1 = fmaf(e[3], c.x, fmaf(e[4], c.y, e[5]));
+    const float f2 = fmaf(e[6], c.x, fmaf(e[7], c.y, e[8]));
+    const float g0 = fmaf(e[0], c.z, fmaf(e[3], c.w, e[6]));
+    const float g1 = fmaf(e[1], c.z, fmaf(e[4], c.w, e[7]));
+    const float num = fmaf(c.z, f0, fmaf(c.w, f1, f2));
+    const float den = fmaf(f0, f0, fmaf(f1, f1, fmaf(g0, g0, g1 * g1)));
+    const float n2 = num * num;
+    const float t = fmaf(-thr2, den, n2);              // r < thr  <=>  num^2 - thr^2 den < 0
+    const float bt = fmaf(-band, den, fabsf(t));       // |t| < band*den : too close for fp32 to call
+    cnt += __float_as_uint(t) >> 31;                   // sign bit == (t < 0)
+    unc += __float_as_uint(bt) >> 31;
+    float rinv;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(rinv) : "f"(den));
+    sse = fmaf(n2, rinv, sse);
+}
+
+// thread = HPT hypotheses (E in registers); the CTA walks `cpc` chunks of CHUNK correspondences through a
+// two-stage shared-memory ring filled by TMA bulk copies; one broadcast LDS.128 feeds HPT evaluations.
+template <int HPT, int CHUNK>
+__global__ void __launch_bounds__(SCORE_THREADS) ransac_score_kernel(const RansacParams p, int cpc) {
+    __shared__ alignas(128) float4 corr[2][CHUNK];
+    __shared__ alignas(8) uint64_t bar[2];
+    const int b = blockIdx.z, slot = blockIdx.y;
     const int M = p.m_count ? min(p.m_count[b], p.n_max) : p.m;
-    const int r0 = chunk * SCORE_CHUNK;
-    const int rows = max(0, min(SCORE_CHUNK, M - r0));
-    const size_t oc = ((size_t)b * p.chunks + chunk) * p.H;
+    const int r_begin = slot * cpc * CHUNK;
+    const int r_end = min(M, r_begin + cpc * CHUNK);
+    const int n = (r_end > r_begin) ? (r_end - r_begin + CHUNK - 1) / CHUNK : 0;
+    const size_t oc = ((size_t)b * p.chunks + slot) * p.H;
+    const float4* __restrict__ src = p.corr32 + (size_t)b * p.n_max + r_begin;
 
     if (threadIdx.x == 0) {
-        mbar_init(&bar, 1);
+        mbar_init(&bar[0], 1);
+        mbar_init(&bar[1], 1);
         fence_mbar_init();
     }
     __syncthreads();
-    if (rows > 0 && threadIdx.x == 0) {
-        mbar_arrive_expect_tx(&bar, (uint32_t)rows * 16u);
-        tma_load_1d(corr, p.corr32 + (size_t)b * p.n_max + r0, (uint32_t)rows * 16u, &bar);
+    auto issue = [&](int i) {
+        const int rows = min(CHUNK, r_end - r_begin - i * CHUNK);
+        mbar_arrive_expect_tx(&bar[i & 1], (uint32_t)rows * 16u);
+        tma_load_1d(corr[i & 1], src + (size_t)i * CHUNK, (uint32_t)rows * 16u, &bar[i & 1]);
+    };
+    if (threadIdx.x == 0) {
+        if (n > 0) issue(0);
+        if (n > 1) issue(1);
     }
-    float e[9];
-    const bool live = h < p.H;
+    float e[HPT][9];
+    int h[HPT];
+    unsigned cnt[HPT], unc[HPT];
+    float sse[HPT];
 #pragma unroll
-    for (int i = 0; i < 9; ++i) e[i] = live ? p.E32[((size_t)b * 9 + i) * p.H + h] : 0.0f;
-
-    unsigned int cnt = 0, unc = 0;
-    float sse = 0.0f;
-    if (rows > 0) {
-        mbar_wait(&bar, 0);
-        const float thr2 = (float)(p.thr * p.thr);
-        const float band = p.band_rel * thr2;
+    for (int k = 0; k < HPT; ++k) {
+        h[k] = (blockIdx.x * HPT + k) * SCORE_THREADS + threadIdx.x;
+#pragma unroll
+        for (int i = 0; i < 9; ++i) e[k][i] = (h[k] < p.H) ? p.E32[((size_t)b * 9 + i) * p.H + h[k]] : 0.0f;
+        cnt[k] = 0; unc[k] = 0; sse[k] = 0.0f;
+    }
+    const float thr2 = (float)(p.thr * p.thr);
+    const float band = p.band_rel * thr2;
+    for (int i = 0; i < n; ++i) {
+        mbar_wait(&bar[i & 1], (uint32_t)((i >> 1) & 1));
+        const int rows = min(CHUNK, r_end - r_begin - i * CHUNK);
+        const float4* __restrict__ cp = corr[i & 1];
 #pragma unroll 4
         for (int j = 0; j < rows; ++j) {
-            const float4 c = corr[j];  // (x, y, u, v): x = src (last), u = dst (curr)
-            const float f0 = fmaf(e[0], c.x, fmaf(e[1], c.y, e[2]));
-            const float f1 = fmaf(e[3], c.x, fmaf(e[4], c.y, e[5]));
-            const float f2 = fmaf(e[6], c.x, fmaf(e[7], c.y, e[8]));
-            const float g0 = fmaf(e[0], c.z, fmaf(e[3], c.w, e[6]));
-            const float g1 = fmaf(e[1], c.z, fmaf(e[4], c.w, e[7]));
-            const float num = fmaf(c.z, f0, fmaf(c.w, f1, f2));
-            const float den = fmaf(f0, f0, fmaf(f1, f1, fmaf(g0, g0, g1 * g1)));
-            const float n2 = num * num;
-            const float t = fmaf(-thr2, den, n2);              // r < thr  <=>  num^2 - thr^2 den < 0
-            const float bt = fmaf(-band, den, fabsf(t));       // |t| < band*den : too close for fp32 to call
-            cnt += __float_as_uint(t) >> 31;                   // sign bit == (t < 0)
-            unc += __float_as_uint(bt) >> 31;
-            float rinv;
-            asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(rinv) : "f"(den));
-            sse = fmaf(n2, rinv, sse);
+            const float4 c = cp[j];
+#pragma unroll
+            for (int k = 0; k < HPT; ++k) score_eval(e[k], c, thr2, band, cnt[k], unc[k], sse[k]);
         }
+        __syncthreads();   // everyone is done with this stage before TMA refills it
+        if (threadIdx.x == 0 && i + 2 < n) issue(i + 2);
     }
-    if (live) {
-        p.part_cnt[oc + h] = make_int2((int)cnt, (int)unc);
-        p.part_sse[oc + h] = sse;
+#pragma unroll
+    for (int k = 0; k < HPT; ++k)
+        if (h[k] < p.H) {
+            p.part_cnt[oc + h[k]] = make_int2((int)cnt[k], (int)unc[k]);
+            p.part_sse[oc + h[k]] = sse[k];
+        }
+}
+
+// Partial slots per hypothesis (p.chunks) and correspondences per slot (p.chunk) for a batch: large
+// batches walk all correspondences in one CTA (no partial sums to merge), small ones split M for parallelism.
+void ransac_score_plan(int batch, int n_max, int H, int sm_count, int* slots, int* rows_per_slot, int* mode) {
+    const long long big = (long long)batch * ((H + 2 * SCORE_THREADS - 1) / (2 * SCORE_THREADS));
+    if (big >= 4LL * sm_count) {
+        *mode = 0;                         // <HPT 2, CHUNK 256>, one slot
+        *slots = 1;
+        *rows_per_slot = ((n_max + 255) / 256) * 256;
+    } else {
+        *mode = 1;                         // <HPT 1, CHUNK 128>, split M
+        const int chunks = (n_max + 127) / 128;
+        const long long hb = (long long)batch * ((H + SCORE_THREADS - 1) / SCORE_THREADS);
+        long long want = (4LL * sm_count + hb - 1) / hb;
+        if (want < 1) want = 1;
+        if (want > chunks) want = chunks;
+        const int cpc = (chunks + (int)want - 1) / (int)want;
+        *slots = (chunks + cpc - 1) / cpc;
+        *rows_per_slot = cpc * 128;
     }
 }
 
-cudaError_t launch_ransac_score(const RansacParams& p, int batch, cudaStream_t stream) {
-    dim3 grid((p.H + SCORE_THREADS - 1) / SCORE_THREADS, p.chunks, batch);
-    ransac_score_kernel<<<grid, SCORE_THREADS, 0, stream>>>(p);
+cudaError_t launch_ransac_score(const RansacParams& p, int batch, int mode, cudaStream_t stream) {
+    if (mode == 0) {
+        dim3 grid((p.H + 2 * SCORE_THREADS - 1) / (2 * SCORE_THREADS), p.chunks, batch);
+        ransac_score_kernel<2, 256><<<grid, SCORE_THREADS, 0, stream>>>(p, p.chunk / 256);
+    } else {
+        dim3 grid((p.H + SCORE_THREADS - 1) / SCORE_THREADS, p.chunks, batch);
+        ransac_score_kernel<1, 128><<<grid, SCORE_THREADS, 0, stream>>>(p, p.chunk / 128);
+    }
     return cudaGetLastError();
 }
 

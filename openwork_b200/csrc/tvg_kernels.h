@@ -65,7 +65,7 @@ struct RansacParams {
     double* E64;               // [batch][H][9]
     float* E32;                // [batch][9][H]  Frobenius-normalised, SoA
     int32_t* valid;            // [batch][H]
-    int chunks, chunk;         // correspondence chunks per pair, rows per chunk
+    int chunks, chunk;         // partial-sum slots per hypothesis, correspondences covered by one slot
     int2* part_cnt;            // [batch][chunks][H] (count, band)
     float* part_sse;           // [batch][chunks][H]
     int32_t* counts;           // [batch][H]  (-1 = failed fit)
@@ -96,11 +96,11 @@ struct RansacParams {
     double* refit_ws;          // [batch][ransac_refit_ws_doubles()] accumulate -> solve hand-off
 };
 cudaError_t launch_ransac_fit(const RansacParams& p, int batch, cudaStream_t stream);
-cudaError_t launch_ransac_score(const RansacParams& p, int batch, cudaStream_t stream);
+cudaError_t launch_ransac_score(const RansacParams& p, int batch, int mode, cudaStream_t stream);
+void ransac_score_plan(int batch, int n_max, int H, int sm_count, int* slots, int* rows_per_slot, int* mode);
 cudaError_t launch_ransac_reduce(const RansacParams& p, int batch, cudaStream_t stream);
 cudaError_t launch_ransac_rescore(const RansacParams& p, int batch, cudaStream_t stream);
 cudaError_t launch_ransac_refit(const RansacParams& p, int batch, cudaStream_t stream);
-int ransac_score_chunk_rows();
 int ransac_refit_ws_doubles();
 
 // ---------------------------------------------------------------- pose + triangulation (pose_tri.cu)
