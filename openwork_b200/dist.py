@@ -117,13 +117,13 @@ def huge_pair(curr_kps, curr_des, last_kps, last_des, K, words, ratio=0.75, resi
     if M <= 8:
         raise ValueError("`min_samples` must be in range (0, <number-of-samples>)")
 
-    # 3. RANSAC over this rank's block of hypotheses (same global sample table everywhere)
-    from .synth import samples_from_words
-    samples = samples_from_words(np.asarray(words), M)
+    # 3. RANSAC over this rank's block of hypotheses (rows of the same global word table everywhere;
+    #    the word -> index mapping depends only on the row and on M, so slices map identically)
+    words = np.ascontiguousarray(np.asarray(words, dtype=np.uint32))
     h_lo, h_hi = shard_range(H, rank, world)
     key = torch.zeros(1, dtype=torch.int64, device=src.device)
     if h_hi > h_lo:
-        r = backend.ransac_essential(src, dst, samples=samples[h_lo:h_hi], residual_threshold=residual_threshold)
+        r = backend.ransac_essential(src, dst, words=words[h_lo:h_hi], residual_threshold=residual_threshold)
         if r["best"] >= 0 and r["n_inl"] >= 0:
             key = pack_best_key(torch.tensor([r["n_inl"]]), torch.tensor([r["best_sse"]]),
                                 torch.tensor([r["best"] + h_lo])).to(src.device)
@@ -132,16 +132,18 @@ def huge_pair(curr_kps, curr_des, last_kps, last_des, K, words, ratio=0.75, resi
     count, best = unpack_best_key(key.item())
 
     # 5. every rank re-derives the winner from the shared table row: mask, refit, extract_Rt
-    w = backend.ransac_essential(src, dst, samples=samples[best:best + 1], residual_threshold=residual_threshold)
+    w = backend.ransac_essential(src, dst, words=words[best:best + 1], residual_threshold=residual_threshold)
     mask = w["mask"]
     # 6. triangulation of the inliers, split by points, gathered back in match order
-    ck = torch.as_tensor(np.asarray(curr_kps))[qidx.cpu().long()][mask.cpu()]
-    lk = torch.as_tensor(np.asarray(last_kps))[tidx.cpu().long()][mask.cpu()]
+    def _t(x):
+        return (x if isinstance(x, torch.Tensor) else torch.as_tensor(np.asarray(x))).to(src.device)
+    ck = _t(curr_kps)[qidx.long()][mask]
+    lk = _t(last_kps)[tidx.long()][mask]
     p_lo, p_hi = shard_range(ck.shape[0], rank, world)
     Rt = w["Rt"]
     pose0 = np.eye(4)
     pose1 = np.asarray(Rt.cpu()) @ pose0
-    X = backend.triangulate(lk[p_lo:p_hi].numpy(), ck[p_lo:p_hi].numpy(), pose0, pose1, K)
+    X = backend.triangulate(lk[p_lo:p_hi].contiguous(), ck[p_lo:p_hi].contiguous(), pose0, pose1, K)
     X = all_gather_varlen(X.to(src.device), group)
     return dict(qidx=qidx, tidx=tidx, M=M, best=best, count=count, E=w["E"], E_best=w["E_best"], mask=mask,
-                Rt=Rt, points4d=X, good=X[:, 2] > 0, samples=samples)
+                Rt=Rt, points4d=X, good=X[:, 2] > 0)

@@ -333,7 +333,7 @@ def _alloc_pair_outputs(B, N, H, nseq, want, factory):
 def process_pairs_device(des, kps, K, words=None, samples=None, H=None, frame_count=None, pair_q=None, pair_t=None,
                          seq_off=None, init_pose=None, ratio=RATIO, residual_threshold=RESIDUAL_THRESHOLD,
                          outputs=("m_count", "E", "n_inl", "Rt", "poses", "points4d", "good", "status"),
-                         out=None, ctx=None):
+                         out=None, ctx=None, batch=None):
     """The ``else`` branch of process_frame (slam.py:249-266) for a batch of pairs, all on the device,
     no host synchronisation.  des u8[F,N,32], kps f64[F,N,2] frame pools (CUDA tensors).  Without
     pair_q/pair_t, pair b is (curr = frame b+1+s, last = frame b+s) inside sequence s (``seq_off``).
@@ -355,7 +355,9 @@ def process_pairs_device(des, kps, K, words=None, samples=None, H=None, frame_co
         B = pq.shape[0]
     else:
         pq = pt = None
-        if seq_off is not None:
+        if batch is not None:
+            B = int(batch)
+        elif seq_off is not None:
             B = int(_np(seq_off)[-1])
         else:
             B = F - 1

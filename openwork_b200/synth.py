@@ -72,7 +72,7 @@ def make_sequence(n_frames, n_kpts, seed, K=K_640x480, width=640, height=480,
     frames = []
     # a scene deep enough that points stay in view for the whole track
     depth_hi = 40.0 + 0.7 * n_frames
-    n_pool = 8 * n_kpts
+    n_pool = (8 + n_frames // 6) * n_kpts
     pts = np.empty((n_pool, 3))
     pts[:, 2] = rng.uniform(4.0, depth_hi, n_pool)
     pts[:, 0] = rng.uniform(-1.1, 1.1, n_pool) * pts[:, 2] * (width / 2) / Kf[0, 0]

@@ -39,7 +39,9 @@ class OracleBackend:
                     dst=torch.from_numpy(dst))
 
     @staticmethod
-    def ransac_essential(src, dst, samples=None, residual_threshold=0.005):
+    def ransac_essential(src, dst, samples=None, words=None, residual_threshold=0.005):
+        if samples is None:
+            samples = synth.samples_from_words(words, len(src))
         r = tv.ransac_essential(src.numpy(), dst.numpy(), samples, residual_threshold)
         n = int(r["mask"].sum()) if r["mask"] is not None else -1
         return dict(E=torch.from_numpy(r["E"]), mask=torch.from_numpy(r["mask"]), best=r["best"], n_inl=n,
