@@ -180,6 +180,68 @@ def run_reference(args):
     return 0
 
 
+
+def single_pair_latency(ops, ctx, K, n, H, dev, reps=30):
+    """One frame pair (config C2: n=2048,H=1024 / C3: n=8192,H=4096) through the sync-free device pipeline:
+    microseconds per pair launched eagerly and replayed from a CUDA graph, plus the matcher alone."""
+    import ctypes as C
+    import torch
+    from openwork_b200 import synth
+    lk, ld, ck, cd = synth.make_pair_large(n, SEED + n)
+    des = torch.from_numpy(np.stack([ld, cd])).to(dev)
+    kps = torch.from_numpy(np.stack([lk, ck])).to(dev)
+    words = torch.from_numpy(synth.sample_words(H, SEED).view(np.int32)).to(dev)
+    pq = torch.tensor([1], dtype=torch.int32, device=dev)
+    pt = torch.tensor([0], dtype=torch.int32, device=dev)
+    so = torch.tensor([0, 1], dtype=torch.int32, device=dev)
+    outs = ("m_count", "E", "n_inl", "Rt", "poses", "points4d", "good", "status")
+    out = None
+
+    def call():
+        nonlocal out
+        out = ops.process_pairs_device(des, kps, K, words=words, pair_q=pq, pair_t=pt, seq_off=so, ratio=RATIO,
+                                       residual_threshold=THR, outputs=outs, out=out, ctx=ctx)
+
+    def timed(fn, reps):
+        for _ in range(3):
+            fn()
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(reps):
+            fn()
+        b.record()
+        b.synchronize()
+        return a.elapsed_time(b) / reps * 1e3
+    eager_us = timed(call, reps)
+    graph_us = None
+    try:
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            call()
+        torch.cuda.current_stream().wait_stream(side)
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            call()
+        graph_us = timed(g.replay, reps)
+    except Exception as e:  # pragma: no cover
+        graph_us = "capture failed: %r" % (e,)
+    idx = torch.empty((1, n, 2), dtype=torch.int32, device=dev)
+    dst = torch.empty((1, n, 2), dtype=torch.int32, device=dev)
+    keep = torch.empty((1, n), dtype=torch.uint8, device=dev)
+    P = lambda t: C.c_void_p(t.data_ptr())
+
+    def knn():
+        ops.check(ctx.lib.tvg_knn2_hamming256(ctx.handle, P(des), P(des), 1, n, n, n, P(pq), P(pt), None, None, RATIO,
+                                              P(idx), P(dst), P(keep),
+                                              C.c_void_p(torch.cuda.current_stream().cuda_stream)), "knn2")
+    knn_us = timed(knn, reps)
+    return {"kpts": n, "hypotheses": H, "matches": int(out["m_count"][0]), "inliers": int(out["n_inl"][0]),
+            "eager_us_per_pair": eager_us, "cuda_graph_us_per_pair": graph_us, "matcher_us": knn_us,
+            "matcher_gcmp_s": n * n / knn_us / 1e3}
+
+
 # ----------------------------------------------------------------------------------------- our arm
 def run_ours(args):
     import torch
@@ -294,6 +356,10 @@ def run_ours(args):
     barrier()
     e2e_s = time.perf_counter() - t0
 
+    single = None
+    if rank == 0 and not args.no_single_pair:
+        single = {"C2": single_pair_latency(ops, ctx, K, 2048, 1024, dev), "C3": single_pair_latency(ops, ctx, K, 8192, 4096, dev)}
+
     t = torch.tensor([ms, knn_ms, e2e_s], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -347,7 +413,7 @@ def run_ours(args):
         "hamming_gcmp_s": gcmp_s * world, "clocks": clocks, "gpu_launches": int(launches),
         "e2e": {"value": e2e_value, "unit": "pairs/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                 "steps": e2e_steps},
-        "roofline": roofline, "cpu_baseline": cpu,
+        "roofline": roofline, "cpu_baseline": cpu, "single_pair": single,
     }
     print(json.dumps(line))
     if world > 1:
@@ -367,6 +433,7 @@ def main():
     ap.add_argument("--knn-ctas", type=int, default=6)
     ap.add_argument("--host-chunk", type=int, default=256, help="pairs per chunk of the e2e host pipeline")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-single-pair", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)

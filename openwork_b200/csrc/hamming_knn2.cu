@@ -153,22 +153,40 @@ __device__ __forceinline__ void knn2_finish(const KnnParams& p, int b, int qt, i
     if (!*s_is_last) return;
     __threadfence();
 
+    // Each warp merges MB queries per iteration so that MB independent partial loads (and butterflies)
+    // are in flight: the merge is latency-bound, not throughput-bound.
+    constexpr int MB = 8;
     const int warp = tid >> 5, lane = tid & 31;
     const int qend = min(nq, q0 + BQ);
-    for (int qi = q0 + warp; qi < qend; qi += THREADS / 32) {
-        uint32_t a1 = TVG_SENTINEL_KEY, a2 = TVG_SENTINEL_KEY;
-        const uint2* pp = p.partial + (size_t)(ob + qi) * p.splits;
+    for (int qb = q0 + warp * MB; qb < qend; qb += (THREADS / 32) * MB) {
+        uint32_t a1[MB], a2[MB];
+#pragma unroll
+        for (int u = 0; u < MB; ++u) {
+            a1[u] = TVG_SENTINEL_KEY;
+            a2[u] = TVG_SENTINEL_KEY;
+        }
         for (int s = lane; s < p.splits; s += 32) {
-            const uint2 v = __ldcg(pp + s);
-            top2_merge(a1, a2, v.x, v.y);
+            uint2 v[MB];
+#pragma unroll
+            for (int u = 0; u < MB; ++u) {
+                const int qi = min(qb + u, qend - 1);
+                v[u] = __ldcg(p.partial + (size_t)(ob + qi) * p.splits + s);
+            }
+#pragma unroll
+            for (int u = 0; u < MB; ++u) top2_merge(a1[u], a2[u], v[u].x, v[u].y);
         }
 #pragma unroll
-        for (int m = 16; m > 0; m >>= 1) {  // warp-shuffle top-2 butterfly
-            const uint32_t b1 = __shfl_xor_sync(0xffffffffu, a1, m);
-            const uint32_t b2 = __shfl_xor_sync(0xffffffffu, a2, m);
-            top2_merge(a1, a2, b1, b2);
+        for (int m = 16; m > 0; m >>= 1) {  // warp-shuffle top-2 butterfly, MB queries interleaved
+#pragma unroll
+            for (int u = 0; u < MB; ++u) {
+                const uint32_t b1 = __shfl_xor_sync(0xffffffffu, a1[u], m);
+                const uint32_t b2 = __shfl_xor_sync(0xffffffffu, a2[u], m);
+                top2_merge(a1[u], a2[u], b1, b2);
+            }
         }
-        if (lane == 0) knn2_emit(p, (size_t)(ob + qi), a1, a2);
+#pragma unroll
+        for (int u = 0; u < MB; ++u)
+            if (lane == u && qb + u < qend) knn2_emit(p, (size_t)(ob + qb + u), a1[u], a2[u]);
     }
 }
 

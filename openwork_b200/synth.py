@@ -123,6 +123,35 @@ def make_pair(n_kpts, seed, **kw):
     return lk, ld, ck, cd
 
 
+def make_pair_large(n, seed):
+    """(last_kps, last_des, curr_kps, curr_des) with n keypoints per side: one two-view scene like
+    make_pair, sized for the 8k / 64k keyframe configs (80 % true points, 30 % geometric outliers)."""
+    rng = np.random.default_rng(seed)
+    K = K_640x480.astype(float)
+    n_true = int(n * 0.8)
+    X = np.stack([rng.uniform(-1, 1, n_true), rng.uniform(-1, 1, n_true), rng.uniform(4, 40, n_true)], axis=1)
+    X[:, 0] *= X[:, 2] * 320 / 270
+    X[:, 1] *= X[:, 2] * 240 / 270
+    R = _small_rotation(rng, 0.01)
+    t = np.array([0.02, -0.01, -0.5])
+    def proj(P):
+        return np.stack([K[0, 0] * P[:, 0] / P[:, 2] + K[0, 2], K[1, 1] * P[:, 1] / P[:, 2] + K[1, 2]], axis=1)
+    k1 = proj(X) + rng.normal(0, 0.3, (n_true, 2))
+    k2 = proj(X @ R.T + t) + rng.normal(0, 0.3, (n_true, 2))
+    bad = rng.random(n_true) < 0.3
+    k2[bad] += rng.normal(0, 25, (int(bad.sum()), 2))
+    d1 = rng.integers(0, 256, (n_true, 32), dtype=np.uint8)
+    d2 = d1 ^ _flip_masks(rng, n_true, 49)
+    nc = n - n_true
+    k1 = np.concatenate([k1, rng.uniform(0, 640, (nc, 2))])
+    k2 = np.concatenate([k2, rng.uniform(0, 640, (nc, 2))])
+    d1 = np.concatenate([d1, rng.integers(0, 256, (nc, 32), dtype=np.uint8)])
+    d2 = np.concatenate([d2, rng.integers(0, 256, (nc, 32), dtype=np.uint8)])
+    p1, p2 = rng.permutation(n), rng.permutation(n)
+    return (np.ascontiguousarray(k1[p1]), np.ascontiguousarray(d1[p1]), np.ascontiguousarray(k2[p2]),
+            np.ascontiguousarray(d2[p2]))
+
+
 def random_descriptors(n, seed):
     return np.random.default_rng(seed).integers(0, 256, (n, 32), dtype=np.uint8)
 

@@ -21,34 +21,6 @@ from openwork_b200 import dist as tdist  # noqa: E402
 from openwork_b200 import ops, synth  # noqa: E402
 
 
-def make_huge_pair(n, seed):
-    """n keypoints per side: a two-view scene like synth.make_pair but vectorised for 64k points."""
-    rng = np.random.default_rng(seed)
-    K = synth.K_640x480.astype(float)
-    n_true = int(n * 0.8)
-    X = np.stack([rng.uniform(-1, 1, n_true), rng.uniform(-1, 1, n_true), rng.uniform(4, 40, n_true)], axis=1)
-    X[:, 0] *= X[:, 2] * 320 / 270
-    X[:, 1] *= X[:, 2] * 240 / 270
-    R = synth._small_rotation(rng, 0.01)
-    t = np.array([0.02, -0.01, -0.5])
-    def proj(P):
-        return np.stack([K[0, 0] * P[:, 0] / P[:, 2] + K[0, 2], K[1, 1] * P[:, 1] / P[:, 2] + K[1, 2]], axis=1)
-    k1 = proj(X) + rng.normal(0, 0.3, (n_true, 2))
-    k2 = proj(X @ R.T + t) + rng.normal(0, 0.3, (n_true, 2))
-    bad = rng.random(n_true) < 0.3
-    k2[bad] += rng.normal(0, 25, (int(bad.sum()), 2))
-    d1 = rng.integers(0, 256, (n_true, 32), dtype=np.uint8)
-    d2 = d1 ^ synth._flip_masks(rng, n_true, 49)
-    nc = n - n_true
-    k1 = np.concatenate([k1, rng.uniform(0, 640, (nc, 2))])
-    k2 = np.concatenate([k2, rng.uniform(0, 640, (nc, 2))])
-    d1 = np.concatenate([d1, rng.integers(0, 256, (nc, 32), dtype=np.uint8)])
-    d2 = np.concatenate([d2, rng.integers(0, 256, (nc, 32), dtype=np.uint8)])
-    p1, p2 = rng.permutation(n), rng.permutation(n)
-    return (np.ascontiguousarray(k1[p1]), np.ascontiguousarray(d1[p1]), np.ascontiguousarray(k2[p2]),
-            np.ascontiguousarray(d2[p2]))
-
-
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--kpts", type=int, default=65536)
@@ -63,7 +35,7 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     K = synth.K_640x480
-    lk, ld, ck, cd = make_huge_pair(a.kpts, 5005)
+    lk, ld, ck, cd = synth.make_pair_large(a.kpts, 5005)
     words = synth.sample_words(a.hyp, 5005)
     # replicated device copies (descriptor sets are <= 2 MiB)
     ldd, cdd = torch.from_numpy(ld).cuda(), torch.from_numpy(cd).cuda()
