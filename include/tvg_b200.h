@@ -187,6 +187,10 @@ typedef struct tvg_pairs_io {
     double* points4d;   /* [batch][n_max][4] */
     uint8_t* good;      /* [batch][n_max] */
     int32_t* status;    /* [batch] */
+    /* 0: Rt by the reference's heuristics (extract_Rt, slam.py:167-186; default, parity path);
+     * 1: Rt by a cheirality vote over the inliers among the four decompositions of E (north-star extra) */
+    int pose_mode;
+    int32_t* pose_votes; /* [batch][4], pose_mode 1 only (optional) */
 } tvg_pairs_io;
 TVG_API int tvg_pairs_device(tvg_ctx* ctx, const tvg_pairs_io* io, void* stream);
 

@@ -42,6 +42,7 @@ class PairsIO(C.Structure):
         ("idx", c_vp), ("dist", c_vp), ("qidx", c_vp), ("tidx", c_vp), ("m_count", c_vp), ("E", c_vp),
         ("E_best", c_vp), ("best", c_vp), ("counts", c_vp), ("mask", c_vp), ("n_inl", c_vp), ("inl_idx", c_vp),
         ("Rt", c_vp), ("poses", c_vp), ("points4d", c_vp), ("good", c_vp), ("status", c_vp),
+        ("pose_mode", C.c_int), ("pose_votes", c_vp),
     ]
 
 

@@ -340,7 +340,7 @@ int tvg_cheirality(tvg_ctx* ctx, const double* E, const double* src, const doubl
     if (batch == 0) return 0;
     if (!E || !src || !dst || !votes || !Rts || !choice) return fail(-3, "tvg_cheirality: NULL array");
     DeviceGuard g(ctx->device);
-    tvg::CheiralityParams p{E, src, dst, mask, m_count, n_max, m, votes, Rts, choice};
+    tvg::CheiralityParams p{E, src, dst, mask, m_count, n_max, m, votes, Rts, choice, nullptr};
     TVG_CUDA(tvg::launch_cheirality(p, batch, (cudaStream_t)stream));
     ctx->launches += 1;
     return 0;
@@ -416,6 +416,23 @@ static int pairs_device_impl(tvg_ctx* ctx, const tvg_pairs_io* io, const double*
     r.n_inl = n_inl; r.Rt = Rt; r.pix_last = pix_last; r.pix_curr = pix_curr;
     rc = tvg_ransac_essential(ctx, &r, stream);
     if (rc) return rc;
+    if (io->pose_mode == 1) {
+        // north-star option: pick (R, t) among the four decompositions of E by a cheirality vote over the
+        // inliers instead of the reference's trace / t_z heuristics (slam.py:174-181)
+        int32_t *votes, *choice;
+        double *Rts, *Eref;
+        uint8_t* mask;
+        TVG_OUT(ctx, io->pose_votes, S_VOTES, B * 4 * sizeof(int32_t), votes, int32_t*);
+        TVG_GET(ctx, S_RTS, B * 64 * sizeof(double), Rts, double*);
+        TVG_GET(ctx, S_CHOICE, B * sizeof(int32_t), choice, int32_t*);
+        TVG_OUT(ctx, io->E, S_E, B * 9 * sizeof(double), Eref, double*);
+        TVG_OUT(ctx, io->mask, S_MASK, B * N, mask, uint8_t*);
+        tvg::CheiralityParams cp{Eref, src, dst, mask, m_count, io->n_max, io->n_max, votes, Rts, choice, Rt};
+        TVG_CUDA(tvg::launch_cheirality(cp, io->batch, st));
+        ctx->launches += 1;
+    } else if (io->pose_mode != 0) {
+        return fail(-2, "tvg_pairs_device: pose_mode must be 0 (reference heuristics) or 1 (cheirality vote)");
+    }
 
     double *poses, *pinv, *points;
     uint8_t* good;

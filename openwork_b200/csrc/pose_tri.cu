@@ -176,6 +176,8 @@ __global__ void __launch_bounds__(CHEIR_THREADS) cheirality_kernel(const Cheiral
             for (int i = 0; i < 16; ++i) p.Rts[((size_t)b * 4 + cand) * 16 + i] = sRt[cand][i];
         }
         p.choice[b] = best;
+        if (p.Rt_out)
+            for (int i = 0; i < 16; ++i) p.Rt_out[(size_t)b * 16 + i] = sRt[best][i];
     }
 }
 

@@ -144,6 +144,7 @@ struct CheiralityParams {
     int32_t* votes;            // [batch][4]
     double* Rts;               // [batch][4][16]
     int32_t* choice;           // [batch]
+    double* Rt_out;            // [batch][16] the chosen candidate (may be NULL)
 };
 cudaError_t launch_cheirality(const CheiralityParams& p, int batch, cudaStream_t stream);
 

@@ -326,14 +326,15 @@ def _alloc_pair_outputs(B, N, H, nseq, want, factory):
                   E_best=((B, 3, 3), torch.float64), best=((B,), torch.int32), counts=((B, H), torch.int32),
                   mask=((B, N), torch.uint8), n_inl=((B,), torch.int32), inl_idx=((B, N), torch.int32),
                   Rt=((B, 4, 4), torch.float64), poses=((B + nseq, 4, 4), torch.float64),
-                  points4d=((B, N, 4), torch.float64), good=((B, N), torch.uint8), status=((B,), torch.int32))
+                  points4d=((B, N, 4), torch.float64), good=((B, N), torch.uint8), status=((B,), torch.int32),
+                  pose_votes=((B, 4), torch.int32))
     return {k: factory(*shapes[k]) for k in want}
 
 
 def process_pairs_device(des, kps, K, words=None, samples=None, H=None, frame_count=None, pair_q=None, pair_t=None,
                          seq_off=None, init_pose=None, ratio=RATIO, residual_threshold=RESIDUAL_THRESHOLD,
                          outputs=("m_count", "E", "n_inl", "Rt", "poses", "points4d", "good", "status"),
-                         out=None, ctx=None, batch=None):
+                         out=None, ctx=None, batch=None, pose_mode=0):
     """The ``else`` branch of process_frame (slam.py:249-266) for a batch of pairs, all on the device,
     no host synchronisation.  des u8[F,N,32], kps f64[F,N,2] frame pools (CUDA tensors).  Without
     pair_q/pair_t, pair b is (curr = frame b+1+s, last = frame b+s) inside sequence s (``seq_off``).
@@ -390,6 +391,7 @@ def process_pairs_device(des, kps, K, words=None, samples=None, H=None, frame_co
     for i in range(9):
         io.kinv[i] = float(kinv.flat[i])
     io.ratio, io.thr = float(ratio), float(residual_threshold)
+    io.pose_mode = int(pose_mode)
     for k, v in out.items():
         setattr(io, k, v.data_ptr())
     check(ctx.lib.tvg_pairs_device(ctx.handle, C.byref(io), _stream()), "tvg_pairs_device")

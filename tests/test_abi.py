@@ -40,14 +40,14 @@ def test_ctypes_structs_mirror_the_c_structs(lib_built, tmp_path):
     prog.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "tvg_b200.h"\n'
                     'int main(void){printf("%zu %zu %zu %zu %zu %zu\\n", sizeof(tvg_ransac_io), sizeof(tvg_pairs_io),'
                     ' offsetof(tvg_ransac_io, thr), offsetof(tvg_ransac_io, n_cand), offsetof(tvg_pairs_io, kinv),'
-                    ' offsetof(tvg_pairs_io, status)); return 0;}\n')
+                    ' offsetof(tvg_pairs_io, pose_votes)); return 0;}\n')
     exe = tmp_path / "sz"
     subprocess.run(["gcc", "-I", os.path.join(ROOT, "include"), str(prog), "-o", str(exe)], check=True)
     vals = [int(v) for v in subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.split()]
     assert vals[0] == ctypes.sizeof(_lib.RansacIO)
     assert vals[1] == ctypes.sizeof(_lib.PairsIO)
     assert vals[2] == _lib.RansacIO.thr.offset and vals[3] == _lib.RansacIO.n_cand.offset
-    assert vals[4] == _lib.PairsIO.kinv.offset and vals[5] == _lib.PairsIO.status.offset
+    assert vals[4] == _lib.PairsIO.kinv.offset and vals[5] == _lib.PairsIO.pose_votes.offset
 
 
 def test_sass_shows_tma_and_integer_pipe(lib_built):

@@ -373,3 +373,108 @@ def test_pairs_two_sequences(ops):
     o1 = {k: (v[3:7] if k == "poses" else v[2:5]) for k, v in out.items()}
     _check_sequence(ops, o0, frames, words, H, [(0, 1), (1, 2)])
     _check_sequence(ops, o1, frames, words, H, [(3, 4), (4, 5), (5, 6)])
+
+
+# ------------------------------------------------------------------------------ BASELINE.json configs
+def test_config_c1_reference_sequence_100_frames(ops):
+    """C1: synthetic 640x480 sequence, 100 frames, 2k keypoints, the reference's max_trials=200 -- every one
+    of the 99 pairs against the oracle (matches bit-exact, same best hypothesis and mask, E, pose chain)."""
+    F, N, H = 100, 2048, 200
+    frames, _ = synth.make_sequence(F, N, seed=1000)
+    des = np.stack([f[1] for f in frames])
+    kps = np.stack([f[0] for f in frames])
+    words = synth.sample_words(H, 1000)
+    out = ops.process_pairs_device(torch.from_numpy(des).cuda(), torch.from_numpy(kps).cuda(), K, words=words,
+                                   residual_threshold=THR, outputs=ALL_OUT)
+    out = {k: v.cpu().numpy() for k, v in out.items()}
+    assert (out["status"] == 0).all()
+    _check_sequence(ops, out, frames, words, H, [(i, i + 1) for i in range(F - 1)])
+
+
+def test_config_c3_keyframe_pair_8k_4096_hypotheses(ops):
+    """C3: 8192 x 8192 descriptors, 4096 hypotheses, full pipeline against the oracle."""
+    N, H = 8192, 4096
+    lk, ld, ck, cd = synth.make_pair_large(N, 3003)
+    words = synth.sample_words(H, 3003)
+    des = torch.from_numpy(np.stack([ld, cd])).cuda()
+    kps = torch.from_numpy(np.stack([lk, ck])).cuda()
+    out = ops.process_pairs_device(des, kps, K, words=words, residual_threshold=THR, outputs=ALL_OUT)
+    out = {k: v.cpu().numpy() for k, v in out.items()}
+    ref = tv.process_pair(lk, ld, ck, cd, np.eye(4), K, words=words, residual_threshold=THR)
+    M = len(ref["idx1"])
+    ri, rd = tv.knn2_cv2(cd, ld)
+    assert np.array_equal(out["idx"][0], ri) and np.array_equal(out["dist"][0], rd)
+    assert int(out["m_count"][0]) == M
+    assert np.array_equal(out["qidx"][0, :M], ref["idx1"]) and np.array_equal(out["tidx"][0, :M], ref["idx2"])
+    assert int(out["best"][0]) == ref["ransac"]["best"]
+    # per-hypothesis counts: exact except points within 1e-5 of the threshold
+    src, dst = tv.normalize(K, ref["match_kps"][:, 1]), tv.normalize(K, ref["match_kps"][:, 0])
+    samples = synth.samples_from_words(words, M)
+    cond = tv.sample_conditioning(src, dst, samples)
+    rc, gc = ref["ransac"]["counts"], out["counts"][0]
+    ok = (cond > 1e-7) & (rc >= 0)
+    assert ok.mean() > 0.95
+    assert (gc[ok] == rc[ok]).mean() > 0.98 and np.abs(gc[ok] - rc[ok]).max() <= 8
+    assert np.array_equal(out["mask"][0, :M].astype(bool), ref["inliers"])
+    assert _fro_diff(out["E"][0], ref["E"]) < E_TOL
+    np.testing.assert_allclose(out["Rt"][0], ref["Rt"], atol=1e-6)
+    n_in = int(ref["inliers"].sum())
+    X, Xr = out["points4d"][0, :n_in], ref["points4d"]
+    rel = np.linalg.norm(X[:, :3] - Xr[:, :3], axis=1) / np.maximum(np.linalg.norm(Xr[:, :3], axis=1), 1e-12)
+    assert np.median(rel) < X_TOL and (rel < 1e-3).mean() > 0.99
+
+
+def test_matcher_64k_properties(ops):
+    """C5-size matcher (65536 x 65536): too big for the oracle in seconds, so check size-independent
+    properties: planted true matches are found at distance <= 49 with a strictly larger runner-up, results do
+    not depend on the split / variant configuration, and a 4096-row slice equals cv2 bit-for-bit."""
+    N = 65536
+    q, t = synth.correlated_descriptors(N, N, seed=64, clutter=0.0)
+    idx, dist = ops.knn2_hamming256(q, t)
+    idx, dist = idx.cpu().numpy(), dist.cpu().numpy()
+    assert (dist[:, 0] <= 49).all() and (dist[:, 1] >= dist[:, 0]).all()
+    assert len(np.unique(idx[:, 0])) == N                      # planted matches are a permutation
+    d_true = tv.hamming_matrix(q[:512], t[idx[:512, 0]]).diagonal()
+    assert np.array_equal(d_true, dist[:512, 0])
+    ri, rd = tv.knn2_cv2(q[1000:5096], t)
+    assert np.array_equal(idx[1000:5096], ri) and np.array_equal(dist[1000:5096], rd)
+    ctx = ops.context(0)
+    try:
+        ctx.set_matcher_config(8, 1, 2)
+        i2, d2 = ops.knn2_hamming256(q, t)
+    finally:
+        ctx.set_matcher_config(4, 3, 6)
+    assert np.array_equal(i2.cpu().numpy(), idx) and np.array_equal(d2.cpu().numpy(), dist)
+
+
+def test_pairs_pose_mode_cheirality(ops):
+    """pose_mode=1: Rt comes from the cheirality vote (true motion has t_z < 0 here, which the reference's
+    t_z >= 0 heuristic flips); everything before the pose is unchanged."""
+    F, N, H = 3, 1024, 128
+    frames, Ts = synth.make_sequence(F, N, seed=808)
+    des = np.stack([f[1] for f in frames])
+    kps = np.stack([f[0] for f in frames])
+    words = synth.sample_words(H, 2)
+    outs = ("E", "Rt", "mask", "m_count", "n_inl", "pose_votes", "poses", "points4d", "good", "qidx", "tidx")
+    a = ops.process_pairs_device(torch.from_numpy(des).cuda(), torch.from_numpy(kps).cuda(), K, words=words,
+                                 outputs=outs, pose_mode=1)
+    b = ops.process_pairs_device(torch.from_numpy(des).cuda(), torch.from_numpy(kps).cuda(), K, words=words,
+                                 outputs=("E", "Rt", "mask"), pose_mode=0)
+    a = {k: v.cpu().numpy() for k, v in a.items()}
+    assert np.array_equal(a["E"], b["E"].cpu().numpy())
+    for i in range(F - 1):
+        M = int(a["m_count"][i])
+        assert np.array_equal(a["mask"][i, :M], b["mask"].cpu().numpy()[i, :M])
+        (lk, ld), (ck, cd) = frames[i], frames[i + 1]
+        src = tv.normalize(K, lk[a["tidx"][i, :M]])
+        dst = tv.normalize(K, ck[a["qidx"][i, :M]])
+        inl = a["mask"][i, :M].astype(bool)
+        rv, rRts = tv.cheirality_votes(a["E"][i], src[inl], dst[inl])
+        assert np.abs(np.sort(a["pose_votes"][i]) - np.sort(rv)).max() <= 2
+        np.testing.assert_allclose(a["Rt"][i], rRts[int(np.argmax(rv))], atol=1e-8)
+        # ground truth relative motion x_curr = R x_last + t (up to the scale of t)
+        T = Ts[i + 1] @ np.linalg.inv(Ts[i])
+        np.testing.assert_allclose(a["Rt"][i][:3, :3], T[:3, :3], atol=2e-2)
+        t = T[:3, 3] / np.linalg.norm(T[:3, 3])
+        assert a["Rt"][i][:3, 3] @ t > 0.8          # right sign (the t_z heuristic would give < 0), roughly right direction
+        assert a["pose_votes"][i].max() > 0.9 * int(a["n_inl"][i])
