@@ -386,7 +386,9 @@ def run_ours(args):
         "peak_note": "POPC-pipe bound of the plain 8xPOPC form: 2 cmp/clk/SM x %d SMs x sm_max_mhz (%s); the "
                      "Harley-Seal variant needs 4 POPC/cmp so it may exceed 1.0" % (n_sm, peak_kind),
         "ms_per_launch": knn_ms, "cmp_per_launch": cmp_per_launch, "sm_mhz_during_run": f_mhz,
-        "traffic": None,
+        # dram__bytes_read.sum + dram__bytes_write.sum of this kernel at P=1024 from the committed ncu capture
+        # (profiles/r1_kernels_matcher_score.md: 135.37 MB + 19.37 MB), scaled to this run's P
+        "traffic": 154.74e6 * P / 1024,
         "hbm": {"achieved": hbm_gbs, "peak": peaks.get("hbm_gbs"), "unit": "GB/s",
                 "frac": hbm_gbs / peaks.get("hbm_gbs", 6650.0), "algorithmic_bytes_per_launch": alg_bytes,
                 "note": "matcher is integer-pipe bound, far below the HBM roofline"},

@@ -182,7 +182,9 @@ int tvg_knn2_hamming256(tvg_ctx* ctx, const uint8_t* q_des, const uint8_t* t_des
     p.idx = idx; p.dist = dist; p.keep = keep; p.ratio = ratio;
     p.key_mul = 1u << TVG_KEY_SHIFT; p.w2 = 2u;
     const int bq = tvg::knn2_block_queries(ctx->knn_r);
-    const int qtiles = (n_max + bq - 1) / bq;
+    // query tiles: from nq when it is known on the host (n_max is only the stride then)
+    const int q_rows = q_count ? n_max : nq;
+    const int qtiles = (q_rows + bq - 1) / bq > 0 ? (q_rows + bq - 1) / bq : 1;
     const long long slots = (long long)ctx->sm_count * ctx->knn_ctas_per_sm;
     const long long base = (long long)qtiles * batch;
     int splits = (int)(slots / base);
@@ -198,7 +200,7 @@ int tvg_knn2_hamming256(tvg_ctx* ctx, const uint8_t* q_des, const uint8_t* t_des
         if (rc) return rc;
         p.tile_counters = reinterpret_cast<unsigned int*>(v);
     }
-    TVG_CUDA(tvg::launch_knn2(p, batch, ctx->knn_r, ctx->knn_variant, (cudaStream_t)stream));
+    TVG_CUDA(tvg::launch_knn2(p, batch, qtiles, ctx->knn_r, ctx->knn_variant, (cudaStream_t)stream));
     ctx->launches += 1;
     return 0;
 }

@@ -340,9 +340,7 @@ static cudaError_t launch_cfg(const KnnParams& p, int batch, int qtiles, cudaStr
 int knn2_block_queries(int r) { return r * 128; }
 
 // variant: 0..3 popcount form, +4 = lazy top-2 insertion (variants 1 and 3 only)
-cudaError_t launch_knn2(const KnnParams& p, int batch, int r, int variant, cudaStream_t stream) {
-    const int bq = knn2_block_queries(r);
-    const int qtiles = (p.n_max + bq - 1) / bq;
+cudaError_t launch_knn2(const KnnParams& p, int batch, int qtiles, int r, int variant, cudaStream_t stream) {
 #define TVG_KNN_CASE(RR, VV, LZ) \
     if (r == RR && variant == VV + (LZ ? 4 : 0)) return launch_cfg<RR, 128, 128, 3, VV, LZ>(p, batch, qtiles, stream);
 #define TVG_KNN_R(RR)                                                                                  \

@@ -25,7 +25,7 @@ struct KnnParams {
     double ratio;
     uint32_t key_mul, w2;      // 1<<23 and 2, passed as data so the multiplies stay IMADs (FMA pipe)
 };
-cudaError_t launch_knn2(const KnnParams& p, int batch, int r, int variant, cudaStream_t stream);
+cudaError_t launch_knn2(const KnnParams& p, int batch, int qtiles, int r, int variant, cudaStream_t stream);
 int knn2_block_queries(int r);
 
 // ---------------------------------------------------------------- ratio compaction (compact.cu)

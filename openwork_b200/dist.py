@@ -9,8 +9,8 @@ Two levels shard naturally:
   steps are (1) an all-gather of the per-rank match slices -- concatenation in rank order preserves the
   reference's ascending-query order -- and (2) ONE all-reduce(MAX) of a 63-bit packed key
   ``count | ~sse | ~hypothesis`` that implements the reference's selection rule (most inliers, then
-  smallest sum of squared residuals, then earliest trial).  Every rank then
-  re-derives the winner from the shared sample table, so no model broadcast is needed.
+  smallest sum of squared residuals, then earliest trial).  The rank that owns
+  the winning hypothesis then broadcasts its inlier mask, refit E and Rt (one small message).
 
 The compute calls go through a ``backend`` (default: ``openwork_b200.ops``, i.e. the CUDA kernels).
 Tests inject a CPU stand-in to exercise this host logic over gloo without a GPU.
@@ -108,11 +108,15 @@ def huge_pair(curr_kps, curr_des, last_kps, last_des, K, words, ratio=0.75, resi
     q_lo, q_hi = shard_range(nq, rank, world)
     idx, dist_, keep = backend.knn2_hamming256(curr_des[q_lo:q_hi], last_des, ratio=ratio, return_keep=True)
     loc = backend.ratio_compact(idx, keep, curr_kps[q_lo:q_hi], last_kps, K)
-    # 2. exchange step 1: all-gather the match slices (rank order == ascending query order)
-    qidx = all_gather_varlen(loc["qidx"] + q_lo, group)
-    tidx = all_gather_varlen(loc["tidx"], group)
-    src = all_gather_varlen(loc["src"], group)
-    dst = all_gather_varlen(loc["dst"], group)
+    # 2. exchange step 1: all-gather the match slices (rank order == ascending query order), packed into
+    #    one buffer per rank: [qidx+q_lo, tidx] as two f64-exact columns next to src / dst  -> f64[M_loc, 6]
+    packed = torch.cat([(loc["qidx"] + q_lo).to(torch.float64)[:, None], loc["tidx"].to(torch.float64)[:, None],
+                        loc["src"], loc["dst"]], dim=1)
+    packed = all_gather_varlen(packed, group)
+    qidx = packed[:, 0].to(torch.int32)
+    tidx = packed[:, 1].to(torch.int32)
+    src = packed[:, 2:4].contiguous()
+    dst = packed[:, 4:6].contiguous()
     M = src.shape[0]
     if M <= 8:
         raise ValueError("`min_samples` must be in range (0, <number-of-samples>)")
@@ -131,9 +135,20 @@ def huge_pair(curr_kps, curr_des, last_kps, last_des, K, words, ratio=0.75, resi
     key = allreduce_best(key, group)
     count, best = unpack_best_key(key.item())
 
-    # 5. every rank re-derives the winner from the shared table row: mask, refit, extract_Rt
-    w = backend.ransac_essential(src, dst, words=words[best:best + 1], residual_threshold=residual_threshold)
-    mask = w["mask"]
+    # 5. the rank that owns the winning hypothesis already holds its mask / refit E / Rt (its local best IS
+    #    the global best); it broadcasts them in one message.  (world == 1: nothing to do.)
+    owner = next(rk for rk in range(world) if shard_range(H, rk, world)[0] <= best < shard_range(H, rk, world)[1])
+    if world > 1:
+        msg = torch.empty(M + 8 * (9 + 9 + 16), dtype=torch.uint8, device=src.device)
+        if rank == owner:
+            msg[:M] = r["mask"].to(torch.uint8)
+            msg[M:] = torch.cat([r["E"].reshape(-1), r["E_best"].reshape(-1), r["Rt"].reshape(-1)]).view(torch.uint8)
+        dist.broadcast(msg, src=dist.get_global_rank(group, owner) if group is not None else owner, group=group)
+        mask = msg[:M].bool()
+        tail = msg[M:].clone().view(torch.float64)
+        w = dict(E=tail[:9].view(3, 3), E_best=tail[9:18].view(3, 3), Rt=tail[18:34].view(4, 4))
+    else:
+        w, mask = r, r["mask"]
     # 6. triangulation of the inliers, split by points, gathered back in match order
     def _t(x):
         return (x if isinstance(x, torch.Tensor) else torch.as_tensor(np.asarray(x))).to(src.device)
