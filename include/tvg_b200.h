@@ -77,7 +77,8 @@ TVG_API int tvg_ratio_compact(tvg_ctx* ctx, const uint8_t* keep, const int32_t* 
  * All outputs are optional (NULL -> internal scratch):
  *   E f64[batch][9] (refit on the inliers), mask u8[batch][n_max] (PRE-refit best model's inliers),
  *   n_inl, best int32[batch], E_best f64[batch][9], counts int32[batch][H] (-1 = failed fit; exact fp64
- *   count for the finalists, fp32 count otherwise), sse32 f32[batch][H], models f64[batch][H][9],
+ *   count for the finalists, fp32 count otherwise), sse32 f32[batch][H] (fp32 sum r^2, diagnostic: computed only
+ *   when requested), models f64[batch][H][9],
  *   Rt f64[batch][16] (extract_Rt of the refit E), status int32[batch] (0 ok, 1: M <= 8, 2: no model),
  *   inl_idx int32[batch][n_max] (match indices of the inliers), samples_out int32[batch][H][8].
  * Optional inlier gather for triangulation: when qidx/tidx and pixel keypoint pools are given,

@@ -248,7 +248,9 @@ int tvg_ransac_essential(tvg_ctx* ctx, const tvg_ransac_io* io, void* stream) {
     p.samples = io->samples; p.words = io->samples ? nullptr : io->words;
     p.sample_stride = io->sample_stride; p.samples_out = io->samples_out;
     p.thr = io->thr;
-    p.band_rel = 2e-3f;  // |num^2 - thr^2 den| <= band_rel * thr^2 den  <=>  |r - thr| <~ 1e-3 thr = 5e-6
+    p.band_rel = 2e-3f;     // |num^2 - thr^2 den| <= band_rel * thr^2 den  <=>  |r - thr| <~ 1e-3 thr = 5e-6
+    p.want_sse = io->sse32 ? 1 : 0;
+    p.band_floor = 9e-11f;  // delta^2 / (band_rel / 2), delta = 3e-7: fp32 cancellation error of num
     int score_mode = 0;
     tvg::ransac_score_plan(io->batch, io->n_max, io->H, ctx->sm_count, &p.chunks, &p.chunk, &score_mode);
     TVG_OUT(ctx, io->models, S_E64, B * H * 9 * sizeof(double), p.E64, double*);

@@ -141,9 +141,10 @@ cudaError_t launch_ransac_fit(const RansacParams& p, int batch, cudaStream_t str
 // ------------------------------------------------------------------------------------ score (fp32)
 constexpr int SCORE_THREADS = 128;
 
-// One Sampson evaluation in fp32: 18 FFMA + 2 FMUL + 1 MUFU.RCP + 2 sign-bit adds.
+// One Sampson evaluation in fp32: 18 FFMA + 2 FMUL (+ 1 MUFU.RCP + 1 FFMA when sum r^2 is wanted) + 2 sign-bit adds.
+template <bool SSE>
 __device__ __forceinline__ void score_eval(const float (&e)[9], const float4 c, float thr2, float band,
-                                           unsigned& cnt, unsigned& unc, float& sse) {
+                                           float floor_, unsigned& cnt, unsigned& unc, float& sse) {
     // c = (x, y, u, v): x = src (last), u = dst (curr)
     const float f0 = fmaf(e[0], c.x, fmaf(e[1], c.y, e[2]));
     const float f1 = fmaf(e[3], c.x, fmaf(e[4], c.y, e[5]));
@@ -154,17 +155,23 @@ __device__ __forceinline__ void score_eval(const float (&e)[9], const float4 c, 
     const float den = fmaf(f0, f0, fmaf(f1, f1, fmaf(g0, g0, g1 * g1)));
     const float n2 = num * num;
     const float t = fmaf(-thr2, den, n2);              // r < thr  <=>  num^2 - thr^2 den < 0
-    const float bt = fmaf(-band, den, fabsf(t));       // |t| < band*den : too close for fp32 to call
+    // too close for fp32 to call:  |t| < band*den + floor.  The relative part covers rounding of num^2 and
+    // thr^2*den; the absolute floor covers cancellation in num for points near the epipole (den -> 0):
+    // 2*thr*sqrt(den)*delta <= (band_rel/2)*thr^2*den + delta^2/(band_rel/2)  with  delta ~ 3e-7 (|E|_F = 1,
+    // |x| <~ 1); the other half of band_rel is the rounding allowance.
+    const float bt = fmaf(-band, den, fabsf(t)) - floor_;
     cnt += __float_as_uint(t) >> 31;                   // sign bit == (t < 0)
     unc += __float_as_uint(bt) >> 31;
-    float rinv;
-    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(rinv) : "f"(den));
-    sse = fmaf(n2, rinv, sse);
+    if (SSE) {
+        float rinv;
+        asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(rinv) : "f"(den));
+        sse = fmaf(n2, rinv, sse);
+    }
 }
 
 // thread = HPT hypotheses (E in registers); the CTA walks `cpc` chunks of CHUNK correspondences through a
 // two-stage shared-memory ring filled by TMA bulk copies; one broadcast LDS.128 feeds HPT evaluations.
-template <int HPT, int CHUNK>
+template <int HPT, int CHUNK, bool SSE>
 __global__ void __launch_bounds__(SCORE_THREADS) ransac_score_kernel(const RansacParams p, int cpc) {
     __shared__ alignas(128) float4 corr[2][CHUNK];
     __shared__ alignas(8) uint64_t bar[2];
@@ -204,6 +211,7 @@ __global__ void __launch_bounds__(SCORE_THREADS) ransac_score_kernel(const Ransa
     }
     const float thr2 = (float)(p.thr * p.thr);
     const float band = p.band_rel * thr2;
+    const float floor_ = p.band_floor;
     for (int i = 0; i < n; ++i) {
         mbar_wait(&bar[i & 1], (uint32_t)((i >> 1) & 1));
         const int rows = min(CHUNK, r_end - r_begin - i * CHUNK);
@@ -212,7 +220,7 @@ __global__ void __launch_bounds__(SCORE_THREADS) ransac_score_kernel(const Ransa
         for (int j = 0; j < rows; ++j) {
             const float4 c = cp[j];
 #pragma unroll
-            for (int k = 0; k < HPT; ++k) score_eval(e[k], c, thr2, band, cnt[k], unc[k], sse[k]);
+            for (int k = 0; k < HPT; ++k) score_eval<SSE>(e[k], c, thr2, band, floor_, cnt[k], unc[k], sse[k]);
         }
         __syncthreads();   // everyone is done with this stage before TMA refills it
         if (threadIdx.x == 0 && i + 2 < n) issue(i + 2);
@@ -247,12 +255,16 @@ void ransac_score_plan(int batch, int n_max, int H, int sm_count, int* slots, in
 }
 
 cudaError_t launch_ransac_score(const RansacParams& p, int batch, int mode, cudaStream_t stream) {
+    // the fp32 sum of squared residuals is diagnostic (selection uses the exact fp64 re-score): computed
+    // only when the caller asked for it
     if (mode == 0) {
         dim3 grid((p.H + 2 * SCORE_THREADS - 1) / (2 * SCORE_THREADS), p.chunks, batch);
-        ransac_score_kernel<2, 256><<<grid, SCORE_THREADS, 0, stream>>>(p, p.chunk / 256);
+        if (p.want_sse) ransac_score_kernel<2, 256, true><<<grid, SCORE_THREADS, 0, stream>>>(p, p.chunk / 256);
+        else ransac_score_kernel<2, 256, false><<<grid, SCORE_THREADS, 0, stream>>>(p, p.chunk / 256);
     } else {
         dim3 grid((p.H + SCORE_THREADS - 1) / SCORE_THREADS, p.chunks, batch);
-        ransac_score_kernel<1, 128><<<grid, SCORE_THREADS, 0, stream>>>(p, p.chunk / 128);
+        if (p.want_sse) ransac_score_kernel<1, 128, true><<<grid, SCORE_THREADS, 0, stream>>>(p, p.chunk / 128);
+        else ransac_score_kernel<1, 128, false><<<grid, SCORE_THREADS, 0, stream>>>(p, p.chunk / 128);
     }
     return cudaGetLastError();
 }

@@ -61,6 +61,8 @@ struct RansacParams {
     int32_t* samples_out;      // [batch][H][8] indices actually used (may be NULL)
     double thr;
     float band_rel;            // fp32 uncertainty band, relative to thr^2*den
+    int want_sse;              // compute the fp32 sum r^2 per hypothesis (diagnostic output)
+    float band_floor;          // ... plus an absolute floor (cancellation in num when den -> 0)
     // outputs / scratch
     double* E64;               // [batch][H][9]
     float* E32;                // [batch][9][H]  Frobenius-normalised, SoA

@@ -28,7 +28,7 @@ __device__ __forceinline__ void jacobi_onesided(double (&G)[N][MR], double (&V)[
                     beta = fma(G[q][i], G[q][i], beta);
                     gamma = fma(G[p][i], G[q][i], gamma);
                 }
-                if (gamma * gamma > 1e-30 * alpha * beta && gamma != 0.0) {
+                if (gamma * gamma > 1e-26 * alpha * beta && gamma != 0.0) {
                     rotated = true;
                     const double zeta = (beta - alpha) / (2.0 * gamma);
                     const double t = copysign(1.0, zeta) / (fabs(zeta) + sqrt(fma(zeta, zeta, 1.0)));
