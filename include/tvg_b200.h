@@ -207,6 +207,14 @@ TVG_API int tvg_set_host_chunk(tvg_ctx* ctx, int pairs);
 TVG_API int tvg_pairs_host(tvg_ctx* ctx, const tvg_pairs_io* io, int frames, long long* bytes_h2d,
                    long long* bytes_d2h, void* stream);
 
+/* Streaming form of tvg_pairs_host: _submit enqueues the copies and kernels and returns; _wait blocks until
+ * every requested result is in the host buffers.  One batch may be in flight per context: alternate two
+ * contexts to overlap the copies of batch k+1 with the kernels of batch k.  Host buffers must stay
+ * untouched between _submit and _wait. */
+TVG_API int tvg_pairs_host_submit(tvg_ctx* ctx, const tvg_pairs_io* io, int frames, long long* bytes_h2d,
+                          long long* bytes_d2h, void* stream);
+TVG_API int tvg_pairs_host_wait(tvg_ctx* ctx);
+
 #ifdef __cplusplus
 }
 #endif

@@ -69,6 +69,9 @@ SIGNATURES = {
     "tvg_set_host_chunk": (C.c_int, [c_vp, C.c_int]),
     "tvg_pairs_host": (C.c_int, [c_vp, C.POINTER(PairsIO), C.c_int, C.POINTER(C.c_longlong),
                                  C.POINTER(C.c_longlong), c_vp]),
+    "tvg_pairs_host_submit": (C.c_int, [c_vp, C.POINTER(PairsIO), C.c_int, C.POINTER(C.c_longlong),
+                                        C.POINTER(C.c_longlong), c_vp]),
+    "tvg_pairs_host_wait": (C.c_int, [c_vp]),
 }
 
 _lib = None

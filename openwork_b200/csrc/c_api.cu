@@ -48,7 +48,32 @@ struct tvg_ctx {
     long long launches = 0;
     int host_chunk_pairs = 256;
     cudaStream_t s_in = nullptr, s_out = nullptr;
+    cudaEvent_t done_event = nullptr;
     std::vector<cudaEvent_t> events;
+    unsigned char* pin = nullptr;   // pinned host staging for the small uploads of the host entry
+    size_t pin_bytes = 0, pin_used = 0;
+
+    // copy `bytes` of pageable caller memory into pinned staging; returns the pinned address (or nullptr)
+    void* stage(const void* src, size_t bytes) {
+        const size_t need = (pin_used + bytes + 255) & ~size_t(255);
+        if (need > pin_bytes) return nullptr;
+        void* dst = pin + pin_used;
+        memcpy(dst, src, bytes);
+        pin_used = need;
+        return dst;
+    }
+    int reserve_pinned(size_t bytes) {
+        pin_used = 0;
+        if (bytes <= pin_bytes) return 0;
+        cudaError_t e = cudaDeviceSynchronize();
+        if (e != cudaSuccess) return cuda_fail(e, "cudaDeviceSynchronize");
+        if (pin) cudaFreeHost(pin);
+        pin = nullptr; pin_bytes = 0;
+        e = cudaMallocHost((void**)&pin, bytes + bytes / 2 + 4096);
+        if (e != cudaSuccess) return cuda_fail(e, "cudaMallocHost(staging)");
+        pin_bytes = bytes + bytes / 2 + 4096;
+        return 0;
+    }
     void* slot[S_NUM] = {};
     size_t slot_bytes[S_NUM] = {};
 
@@ -148,6 +173,8 @@ void tvg_ctx_destroy(tvg_ctx* ctx) {
     for (cudaEvent_t e : ctx->events) cudaEventDestroy(e);
     if (ctx->s_in) cudaStreamDestroy(ctx->s_in);
     if (ctx->s_out) cudaStreamDestroy(ctx->s_out);
+    if (ctx->pin) cudaFreeHost(ctx->pin);
+    if (ctx->done_event) cudaEventDestroy(ctx->done_event);
     delete ctx;
 }
 
@@ -465,8 +492,8 @@ int tvg_set_host_chunk(tvg_ctx* ctx, int pairs) {
     return 0;
 }
 
-int tvg_pairs_host(tvg_ctx* ctx, const tvg_pairs_io* hio, int frames, long long* bytes_h2d,
-                   long long* bytes_d2h, void* stream) {
+int tvg_pairs_host_submit(tvg_ctx* ctx, const tvg_pairs_io* hio, int frames, long long* bytes_h2d,
+                          long long* bytes_d2h, void* stream) {
     if (!ctx || !hio) return fail(-1, "ctx / io is NULL");
     if (hio->batch < 0 || hio->n_max <= 0 || hio->H <= 0 || frames <= 0) return fail(-2, "tvg_pairs_host: bad sizes");
     if (!hio->des || !hio->kps) return fail(-3, "tvg_pairs_host: NULL frame pools");
@@ -477,12 +504,27 @@ int tvg_pairs_host(tvg_ctx* ctx, const tvg_pairs_io* hio, int frames, long long*
     const int nseq = hio->seq_off ? hio->nseq : 1;
     long long h2d = 0, d2h = 0;
     tvg_pairs_io d = *hio;
+    // Small arrays go through pinned staging so that cudaMemcpyAsync never has to synchronise with the
+    // caller's stream (it may for pageable memory), which would serialise consecutive batches.
+    const size_t tab = (hio->sample_stride ? B : 1) * H * 8 * 4;
+    const size_t small_limit = 1u << 20;
+    {
+        size_t want = (F + 2 * B + 4 * ((size_t)nseq + 1 + B / 16 + 64)) * sizeof(int32_t) + (size_t)nseq * 16 * 8 + 8192;
+        if (tab <= small_limit) want += 2 * tab;
+        int rc0 = ctx->reserve_pinned(want);
+        if (rc0) return rc0;
+    }
 #define TVG_UP(slot, hptr, bytes, field, type)                                              \
     do {                                                                                    \
         if (hptr) {                                                                         \
             type dp__;                                                                      \
             TVG_GET(ctx, slot, (bytes), dp__, type);                                        \
-            TVG_CUDA(cudaMemcpyAsync((void*)dp__, (hptr), (bytes), cudaMemcpyHostToDevice, st)); \
+            const void* src__ = (hptr);                                                     \
+            if ((size_t)(bytes) <= small_limit) {                                           \
+                void* st__ = ctx->stage(src__, (bytes));                                    \
+                if (st__) src__ = st__;                                                     \
+            }                                                                               \
+            TVG_CUDA(cudaMemcpyAsync((void*)dp__, src__, (bytes), cudaMemcpyHostToDevice, st)); \
             h2d += (long long)(bytes);                                                      \
             field = dp__;                                                                   \
         }                                                                                   \
@@ -498,7 +540,6 @@ int tvg_pairs_host(tvg_ctx* ctx, const tvg_pairs_io* hio, int frames, long long*
     TVG_UP(S_H_PAIRQ, hio->pair_q, B * sizeof(int32_t), d.pair_q, int32_t*);
     TVG_UP(S_H_PAIRT, hio->pair_t, B * sizeof(int32_t), d.pair_t, int32_t*);
     TVG_UP(S_H_INIT, hio->init_pose, (size_t)nseq * 16 * sizeof(double), d.init_pose, double*);
-    const size_t tab = (hio->sample_stride ? B : 1) * H * 8 * 4;
     TVG_UP(S_H_WORDS, hio->words, tab, d.words, uint32_t*);
     TVG_UP(S_H_SAMPLES, hio->samples, tab, d.samples, int32_t*);
 #undef TVG_UP
@@ -530,9 +571,13 @@ int tvg_pairs_host(tvg_ctx* ctx, const tvg_pairs_io* hio, int frames, long long*
     // ---- chunked schedule: frame copies (stream s_in), kernels (caller's stream), result copies (s_out)
     if (!ctx->s_in) TVG_CUDA(cudaStreamCreateWithFlags(&ctx->s_in, cudaStreamNonBlocking));
     if (!ctx->s_out) TVG_CUDA(cudaStreamCreateWithFlags(&ctx->s_out, cudaStreamNonBlocking));
+    // chunk boundaries: ramp up (C/4, C/2, C, C, ...) so the first kernels start after a short first copy
     const int C = ctx->host_chunk_pairs;
-    const int nchunks = (hio->batch + C - 1) / C;
-    while ((int)ctx->events.size() < 2 * nchunks + 1) {
+    std::vector<int> cb(1, 0);
+    for (int sz = C >= 128 ? C / 4 : C; cb.back() < hio->batch; sz = (sz * 2 < C) ? sz * 2 : C)
+        cb.push_back(cb.back() + sz < hio->batch ? cb.back() + sz : hio->batch);
+    const int nchunks = (int)cb.size() - 1;
+    while ((int)ctx->events.size() < 2 * nchunks) {
         cudaEvent_t e;
         TVG_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
         ctx->events.push_back(e);
@@ -548,7 +593,7 @@ int tvg_pairs_host(tvg_ctx* ctx, const tvg_pairs_io* hio, int frames, long long*
     {
         int s = 0;
         for (int c = 0; c < nchunks; ++c) {
-            const int b0 = c * C, b1 = (b0 + C < hio->batch) ? b0 + C : hio->batch;
+            const int b0 = cb[c], b1 = cb[c + 1];
             while (so_h[s + 1] <= b0) ++s;
             int s1 = s;
             while (so_h[s1 + 1] < b1) ++s1;
@@ -561,18 +606,18 @@ int tvg_pairs_host(tvg_ctx* ctx, const tvg_pairs_io* hio, int frames, long long*
     }
     int32_t* so_d;
     TVG_GET(ctx, S_H_SEQOFF, so_all.size() * sizeof(int32_t), so_d, int32_t*);
-    TVG_CUDA(cudaMemcpyAsync(so_d, so_all.data(), so_all.size() * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+    {
+        const void* src = ctx->stage(so_all.data(), so_all.size() * sizeof(int32_t));
+        TVG_CUDA(cudaMemcpyAsync(so_d, src ? src : so_all.data(), so_all.size() * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+    }
     h2d += (long long)((size_t)(nseq + 1) * sizeof(int32_t));
-    // the copy streams must not start before the caller's stream reaches this call
-    cudaEvent_t ev_start = ctx->events[2 * nchunks];
-    TVG_CUDA(cudaEventRecord(ev_start, st));
-    TVG_CUDA(cudaStreamWaitEvent(ctx->s_in, ev_start, 0));
-    TVG_CUDA(cudaStreamWaitEvent(ctx->s_out, ev_start, 0));
-
+    // The frame copies read HOST buffers and write this context's private staging pool, which nothing else
+    // touches while a batch is in flight (one batch per context), so they need not wait for earlier work on
+    // the caller's stream: with two contexts alternating they overlap the previous batch's kernels.
     long long copied_upto = 0;   // frames [0, copied_upto) are on the device (or queued on s_in)
     int rc = 0;
     for (int c = 0; c < nchunks; ++c) {
-        const int b0 = c * C, b1 = (b0 + C < hio->batch) ? b0 + C : hio->batch, nb = b1 - b0;
+        const int b0 = cb[c], b1 = cb[c + 1], nb = b1 - b0;
         // frames this chunk needs
         long long need = 0;
         if (hio->pair_q) {
@@ -655,11 +700,26 @@ int tvg_pairs_host(tvg_ctx* ctx, const tvg_pairs_io* hio, int frames, long long*
         TVG_DOWN(hio->poses, poses, prow * 16, (pend - prow) * 16 * sizeof(double));
 #undef TVG_DOWN
     }
-    TVG_CUDA(cudaStreamSynchronize(ctx->s_out));
-    TVG_CUDA(cudaStreamSynchronize(st));
+    // completion marker of THIS batch on the caller's stream (later work on that stream is not waited for)
+    if (!ctx->done_event) TVG_CUDA(cudaEventCreateWithFlags(&ctx->done_event, cudaEventDisableTiming));
+    TVG_CUDA(cudaEventRecord(ctx->done_event, st));
     if (bytes_h2d) *bytes_h2d = h2d;
     if (bytes_d2h) *bytes_d2h = d2h;
     return 0;
+}
+
+int tvg_pairs_host_wait(tvg_ctx* ctx) {
+    if (!ctx) return fail(-1, "ctx is NULL");
+    DeviceGuard g(ctx->device);
+    if (ctx->s_out) TVG_CUDA(cudaStreamSynchronize(ctx->s_out));
+    if (ctx->done_event) TVG_CUDA(cudaEventSynchronize(ctx->done_event));
+    return 0;
+}
+
+int tvg_pairs_host(tvg_ctx* ctx, const tvg_pairs_io* hio, int frames, long long* bytes_h2d,
+                   long long* bytes_d2h, void* stream) {
+    const int rc = tvg_pairs_host_submit(ctx, hio, frames, bytes_h2d, bytes_d2h, stream);
+    return rc ? rc : tvg_pairs_host_wait(ctx);
 }
 
 }  // extern "C"

@@ -400,10 +400,15 @@ def process_pairs_device(des, kps, K, words=None, samples=None, H=None, frame_co
 
 def process_pairs_host(des, kps, K, words=None, samples=None, frame_count=None, pair_q=None, pair_t=None,
                        seq_off=None, init_pose=None, ratio=RATIO, residual_threshold=RESIDUAL_THRESHOLD,
-                       outputs=("m_count", "E", "n_inl", "Rt", "poses", "status"), out=None, ctx=None, device=None):
+                       outputs=("m_count", "E", "n_inl", "Rt", "poses", "status"), out=None, ctx=None, device=None,
+                       wait=True):
     """Same pipeline behind HOST buffers (numpy arrays or pinned CPU tensors): host->device copies,
     kernels, device->host copies of the requested outputs and one synchronise happen inside the call
-    (``tvg_pairs_host``).  Returns (dict of CPU tensors, h2d_bytes, d2h_bytes)."""
+    (``tvg_pairs_host``).  Returns (dict of CPU tensors, h2d_bytes, d2h_bytes).
+
+    ``wait=False`` only enqueues (``tvg_pairs_host_submit``): call :func:`wait_pairs_host` on the same context
+    before reading the outputs or touching the inputs.  Alternating two contexts overlaps the copies of one
+    batch with the kernels of the previous one."""
     def host(x, dt):
         if x is None:
             return None
@@ -451,6 +456,14 @@ def process_pairs_host(des, kps, K, words=None, samples=None, frame_count=None, 
         setattr(io, k, v.data_ptr())
     h2d, d2h = C.c_longlong(0), C.c_longlong(0)
     with torch.cuda.device(ctx.device):
-        check(ctx.lib.tvg_pairs_host(ctx.handle, C.byref(io), F, C.byref(h2d), C.byref(d2h), _stream()),
-              "tvg_pairs_host")
+        fn = ctx.lib.tvg_pairs_host if wait else ctx.lib.tvg_pairs_host_submit
+        check(fn(ctx.handle, C.byref(io), F, C.byref(h2d), C.byref(d2h), _stream()), "tvg_pairs_host")
+    if not wait:
+        ctx._inflight = (des, kps, tab, pq, pt, so, fc, ip, out)      # keep the host buffers alive
     return out, int(h2d.value), int(d2h.value)
+
+
+def wait_pairs_host(ctx):
+    """Block until the batch submitted with ``process_pairs_host(..., wait=False)`` on ``ctx`` is complete."""
+    check(ctx.lib.tvg_pairs_host_wait(ctx.handle), "tvg_pairs_host_wait")
+    ctx._inflight = None

@@ -478,3 +478,34 @@ def test_pairs_pose_mode_cheirality(ops):
         t = T[:3, 3] / np.linalg.norm(T[:3, 3])
         assert a["Rt"][i][:3, 3] @ t > 0.8          # right sign (the t_z heuristic would give < 0), roughly right direction
         assert a["pose_votes"][i].max() > 0.9 * int(a["n_inl"][i])
+
+
+def test_pairs_host_submit_wait_two_contexts(ops):
+    """Streaming form: two contexts alternate submit / wait; results equal the blocking call."""
+    from openwork_b200 import _lib
+    N, H = 512, 64
+    batches = []
+    for s in range(3):
+        frames, _ = synth.make_sequence(5, N, seed=40 + s)
+        batches.append((np.stack([f[1] for f in frames]), np.stack([f[0] for f in frames])))
+    words = synth.sample_words(H, 4)
+    outs = ("m_count", "E", "n_inl", "Rt", "poses", "status", "best")
+    ref = [ops.process_pairs_host(d, k, K, words=words, outputs=outs)[0] for d, k in batches]
+    ref = [{k: v.clone() for k, v in r.items()} for r in ref]
+    ctxs = [_lib.Context(0), _lib.Context(0)]
+    for c in ctxs:
+        c.set_host_chunk(2)
+    got = []
+    pending = None
+    for i, (d, k) in enumerate(batches):
+        o, _, _ = ops.process_pairs_host(d, k, K, words=words, outputs=outs, ctx=ctxs[i % 2], wait=False)
+        if pending is not None:
+            ops.wait_pairs_host(ctxs[(i - 1) % 2])
+            got.append({kk: v.clone() for kk, v in pending.items()})
+        pending = o
+    ops.wait_pairs_host(ctxs[(len(batches) - 1) % 2])
+    got.append({kk: v.clone() for kk, v in pending.items()})
+    for r, g in zip(ref, got):
+        for kk in outs:
+            assert torch.equal(r[kk], g[kk]) or (kk in ("E", "Rt", "poses") and
+                                                 np.array_equal(r[kk].numpy(), g[kk].numpy(), equal_nan=True)), kk
