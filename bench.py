@@ -258,7 +258,8 @@ def run_ours(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     ctx = ops.context(local)
-    ctx.set_matcher_config(args.knn_r, args.knn_variant, args.knn_ctas)
+    if args.knn_r is not None:
+        ctx.set_matcher_config(args.knn_r, args.knn_variant, args.knn_ctas)
     ctx.set_host_chunk(args.host_chunk)
     K = synth.K_640x480
     P = args.pairs
@@ -340,7 +341,8 @@ def run_ours(args):
     e2e_outs = ("m_count", "E", "n_inl", "Rt", "poses", "status")
     ctxs = [ctx, _lib.Context(local)]
     for c in ctxs:
-        c.set_matcher_config(args.knn_r, args.knn_variant, args.knn_ctas)
+        if args.knn_r is not None:
+            c.set_matcher_config(args.knn_r, args.knn_variant, args.knn_ctas)
         c.set_host_chunk(args.host_chunk)
     host_out = [None, None]
     h2d = d2h = 0
@@ -423,7 +425,8 @@ def run_ours(args):
                                "triangulate inliers", "pairs_per_step_per_gpu": P, "kpts": N_KPTS, "hypotheses": N_HYP,
                    "l2_policy": "inputs larger than L2 (%.0f MB of descriptors+keypoints per step)" %
                                 ((des_h.nbytes + kps_h.nbytes) / 1e6),
-                   "matcher": {"r": args.knn_r, "variant": args.knn_variant, "ctas_per_sm": args.knn_ctas}},
+                   "matcher": {"r": args.knn_r or "auto (4 batched / 2 when train rows are split)",
+                               "variant": args.knn_variant, "ctas_per_sm": args.knn_ctas}},
         "hamming_gcmp_s": gcmp_s * world, "clocks": clocks, "gpu_launches": int(launches),
         "e2e": {"value": e2e_value, "unit": "pairs/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                 "steps": e2e_steps, "mode": "tvg_pairs_host_submit/_wait, 2 contexts alternating"},
@@ -442,7 +445,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--pairs", type=int, default=1024, help="frame pairs per step per GPU")
-    ap.add_argument("--knn-r", type=int, default=4)
+    ap.add_argument("--knn-r", type=int, default=None, help="matcher queries/thread (default: library auto)")
     ap.add_argument("--knn-variant", type=int, default=3)
     ap.add_argument("--knn-ctas", type=int, default=6)
     ap.add_argument("--host-chunk", type=int, default=4096,

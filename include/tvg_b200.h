@@ -44,7 +44,8 @@ TVG_API int tvg_abi_version(void);
 TVG_API long long tvg_launch_count(const tvg_ctx* ctx);
 /* Matcher tuning: queries per thread r in {2,4,8}; popcount variant 0 = 8xPOPC, 1 = Harley-Seal 4xPOPC,
  * 2 = 5xPOPC, 3 = Harley-Seal with query/train-shared XOR combos (14 LOP3 + 4 POPC); +4 (variants 5, 7) =
- * lazy top-2 insertion; ctas_per_sm sizes the split-Nt grid.  Results are bit-identical for every setting. */
+ * lazy top-2 insertion, +8 (variants 9, 11) = two queries' chunk-local 16-bit keys packed per register
+ * (VIMNMX.U16x2 top-2 updates); ctas_per_sm sizes the split-Nt grid.  Results are bit-identical for every setting. */
 TVG_API int tvg_set_matcher_config(tvg_ctx* ctx, int r, int variant, int ctas_per_sm);
 
 /* cv2.BFMatcher(cv2.NORM_HAMMING).knnMatch(q, t, k=2)  (slam.py:126-127) + the Lowe ratio flag
@@ -141,6 +142,25 @@ TVG_API int tvg_triangulate(tvg_ctx* ctx, const double* pix1, const double* pix2
                     const int32_t* n_pts, const double* P1, long long p1_stride, const double* P2,
                     long long p2_stride, const double* kinv_host, double* points4d, uint8_t* good,
                     void* stream);
+
+/* tvg_triangulate plus the two point filters slam.py:236 leaves as TODO ("parallax, reprojection error"):
+ * reproj f64[batch][n_max] = max over both views of the reprojection error in pixels (focal = K[0][0]),
+ * parallax_cos f64[batch][n_max] = cosine of the angle between the two viewing rays.  No reference behaviour
+ * exists for these; their spec is oracle/two_view.py:point_quality.  Either may be NULL. */
+TVG_API int tvg_point_quality(tvg_ctx* ctx, const double* pix1, const double* pix2, int batch, int n_max, int n,
+                      const int32_t* n_pts, const double* P1, long long p1_stride, const double* P2,
+                      long long p2_stride, const double* kinv_host, double focal, double* points4d, uint8_t* good,
+                      double* reproj, double* parallax_cos, void* stream);
+
+/* Map.add_observation's point-cloud append (slam.py:37-40) for whole sequences: per sequence s,
+ * map_points[s] = [(0,0,0,1) if include_origin (the first frame's entry, slam.py:248)] followed by every pair's
+ * points4d rows with good != 0, in pair order -- the `points` half of the (poses, points) tuple Map.display()
+ * sends to the viewer (slam.py:81-84; the `poses` half is tvg_pose_chain's output).
+ * map_points f64[nseq][cap][4]; map_count int32[nseq] = rows needed (rows beyond cap are dropped);
+ * pair_off int32[batch] (optional) = first row of each pair inside its sequence. */
+TVG_API int tvg_map_accumulate(tvg_ctx* ctx, const double* points4d, const uint8_t* good, const int32_t* n_pts,
+                       const int32_t* seq_off, int nseq, int n_max, long long cap, int include_origin,
+                       double* map_points, int32_t* map_count, int32_t* pair_off, void* stream);
 
 /* Cheirality vote over the four (R, +-t) decompositions of E (north-star extra; the reference uses the
  * trace / t_z heuristics of slam.py:174-181 instead).  votes int32[batch][4], Rts f64[batch][4][16],

@@ -63,6 +63,10 @@ SIGNATURES = {
     "tvg_pose_chain": (C.c_int, [c_vp, c_vp, c_vp, C.c_int, c_vp, c_vp, c_vp, c_vp]),
     "tvg_triangulate": (C.c_int, [c_vp, c_vp, c_vp, C.c_int, C.c_int, C.c_int, c_vp, c_vp, C.c_longlong, c_vp,
                                   C.c_longlong, c_f64p, c_vp, c_vp, c_vp]),
+    "tvg_point_quality": (C.c_int, [c_vp, c_vp, c_vp, C.c_int, C.c_int, C.c_int, c_vp, c_vp, C.c_longlong, c_vp,
+                                    C.c_longlong, c_f64p, C.c_double, c_vp, c_vp, c_vp, c_vp, c_vp]),
+    "tvg_map_accumulate": (C.c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, C.c_int, C.c_int, C.c_longlong, C.c_int, c_vp,
+                                     c_vp, c_vp, c_vp]),
     "tvg_cheirality": (C.c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, C.c_int, C.c_int, C.c_int, c_vp, c_vp,
                                  c_vp, c_vp]),
     "tvg_pairs_device": (C.c_int, [c_vp, C.POINTER(PairsIO), c_vp]),

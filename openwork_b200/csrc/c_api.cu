@@ -45,6 +45,7 @@ struct tvg_ctx {
     int device = 0;
     int sm_count = 148;
     int knn_r = 4, knn_variant = 3, knn_ctas_per_sm = 6;
+    bool knn_auto = true;      // until tvg_set_matcher_config is called: r = 2 when the train rows get split
     long long launches = 0;
     int host_chunk_pairs = 256;
     cudaStream_t s_in = nullptr, s_out = nullptr;
@@ -182,8 +183,9 @@ long long tvg_launch_count(const tvg_ctx* ctx) { return ctx ? ctx->launches : 0;
 
 int tvg_set_matcher_config(tvg_ctx* ctx, int r, int variant, int ctas_per_sm) {
     if (!ctx) return fail(-1, "ctx is NULL");
-    if (!(r == 2 || r == 4 || r == 8) || !(variant >= 0 && variant <= 3 || variant == 5 || variant == 7) || ctas_per_sm < 1 || ctas_per_sm > 16)
-        return fail(-2, "tvg_set_matcher_config: r in {2,4,8}, variant in {0,1,2,3,5,7}, ctas_per_sm in [1,16]");
+    if (!(r == 2 || r == 4 || r == 8) || !((variant >= 0 && variant <= 3) || variant == 5 || variant == 7 || variant == 9 || variant == 11) || ctas_per_sm < 1 || ctas_per_sm > 16)
+        return fail(-2, "tvg_set_matcher_config: r in {2,4,8}, variant in {0,1,2,3,5,7,9,11}, ctas_per_sm in [1,16]");
+    ctx->knn_auto = false;
     ctx->knn_r = r;
     ctx->knn_variant = variant;
     ctx->knn_ctas_per_sm = ctas_per_sm;
@@ -207,12 +209,19 @@ int tvg_knn2_hamming256(tvg_ctx* ctx, const uint8_t* q_des, const uint8_t* t_des
     p.q_count = q_count; p.t_count = t_count;
     p.n_max = n_max; p.nq = nq; p.nt = nt;
     p.idx = idx; p.dist = dist; p.keep = keep; p.ratio = ratio;
-    p.key_mul = 1u << TVG_KEY_SHIFT; p.w2 = 2u;
-    const int bq = tvg::knn2_block_queries(ctx->knn_r);
-    // query tiles: from nq when it is known on the host (n_max is only the stride then)
-    const int q_rows = q_count ? n_max : nq;
-    const int qtiles = (q_rows + bq - 1) / bq > 0 ? (q_rows + bq - 1) / bq : 1;
+    p.key_mul = 1u << TVG_KEY_SHIFT; p.w2 = 2u; p.w128 = 128u; p.w65536 = 65536u;
+    // queries per thread: 4 for big batches; when the grid has to be filled by splitting the train rows
+    // (one or few pairs) 2 queries per thread give twice the CTAs per query tile and measure ~6 % faster
+    int knn_r = ctx->knn_r;
+    const int q_rows = q_count ? n_max : nq;   // query tiles from nq when it is known on the host
     const long long slots = (long long)ctx->sm_count * ctx->knn_ctas_per_sm;
+    if (ctx->knn_auto) {
+        const int bq4 = tvg::knn2_block_queries(4);
+        const long long base4 = (long long)((q_rows + bq4 - 1) / bq4) * batch;
+        knn_r = (slots / (base4 > 0 ? base4 : 1) >= 2) ? 2 : 4;
+    }
+    const int bq = tvg::knn2_block_queries(knn_r);
+    const int qtiles = (q_rows + bq - 1) / bq > 0 ? (q_rows + bq - 1) / bq : 1;
     const long long base = (long long)qtiles * batch;
     int splits = (int)(slots / base);
     const int max_splits = (n_max + 63) / 64;
@@ -227,7 +236,7 @@ int tvg_knn2_hamming256(tvg_ctx* ctx, const uint8_t* q_des, const uint8_t* t_des
         if (rc) return rc;
         p.tile_counters = reinterpret_cast<unsigned int*>(v);
     }
-    TVG_CUDA(tvg::launch_knn2(p, batch, qtiles, ctx->knn_r, ctx->knn_variant, (cudaStream_t)stream));
+    TVG_CUDA(tvg::launch_knn2(p, batch, qtiles, knn_r, ctx->knn_variant, (cudaStream_t)stream));
     ctx->launches += 1;
     return 0;
 }
@@ -359,6 +368,44 @@ int tvg_triangulate(tvg_ctx* ctx, const double* pix1, const double* pix2, int ba
     memcpy(p.kinv, kinv_host, sizeof(p.kinv));
     p.points4d = points4d; p.good = good;
     TVG_CUDA(tvg::launch_triangulate(p, batch, (cudaStream_t)stream));
+    ctx->launches += 1;
+    return 0;
+}
+
+int tvg_point_quality(tvg_ctx* ctx, const double* pix1, const double* pix2, int batch, int n_max, int n,
+                      const int32_t* n_pts, const double* P1, long long p1_stride, const double* P2,
+                      long long p2_stride, const double* kinv_host, double focal, double* points4d, uint8_t* good,
+                      double* reproj, double* parallax_cos, void* stream) {
+    if (!ctx) return fail(-1, "ctx is NULL");
+    if (batch < 0 || n_max < 0 || n < 0 || n > n_max) return fail(-2, "tvg_point_quality: bad sizes");
+    if (batch == 0 || n_max == 0) return 0;
+    if (!pix1 || !pix2 || !P1 || !P2 || !kinv_host || !points4d) return fail(-3, "tvg_point_quality: NULL array");
+    if (!aligned16(pix1) || !aligned16(pix2) || (reinterpret_cast<uintptr_t>(points4d) & 31u))
+        return fail(-4, "tvg_point_quality: pix arrays must be 16-byte, points4d 32-byte aligned");
+    DeviceGuard g(ctx->device);
+    tvg::TriParams p{};
+    p.pix1 = pix1; p.pix2 = pix2; p.n_pts = n_pts; p.n_max = n_max; p.n = n;
+    p.P1 = P1; p.P2 = P2; p.p1_stride = p1_stride; p.p2_stride = p2_stride;
+    memcpy(p.kinv, kinv_host, sizeof(p.kinv));
+    p.points4d = points4d; p.good = good; p.reproj = reproj; p.parallax_cos = parallax_cos; p.focal = focal;
+    TVG_CUDA(tvg::launch_triangulate(p, batch, (cudaStream_t)stream));
+    ctx->launches += 1;
+    return 0;
+}
+
+int tvg_map_accumulate(tvg_ctx* ctx, const double* points4d, const uint8_t* good, const int32_t* n_pts,
+                       const int32_t* seq_off, int nseq, int n_max, long long cap, int include_origin,
+                       double* map_points, int32_t* map_count, int32_t* pair_off, void* stream) {
+    if (!ctx) return fail(-1, "ctx is NULL");
+    if (nseq < 0 || n_max < 0 || cap < 0) return fail(-2, "tvg_map_accumulate: bad sizes");
+    if (nseq == 0) return 0;
+    if (!points4d || !good || !n_pts || !seq_off || !map_points || !map_count)
+        return fail(-3, "tvg_map_accumulate: NULL array");
+    if ((reinterpret_cast<uintptr_t>(points4d) & 31u) || (reinterpret_cast<uintptr_t>(map_points) & 31u))
+        return fail(-4, "tvg_map_accumulate: point arrays must be 32-byte aligned");
+    DeviceGuard g(ctx->device);
+    tvg::MapParams p{points4d, good, n_pts, seq_off, n_max, cap, include_origin, map_points, map_count, pair_off};
+    TVG_CUDA(tvg::launch_map_accumulate(p, nseq, (cudaStream_t)stream));
     ctx->launches += 1;
     return 0;
 }

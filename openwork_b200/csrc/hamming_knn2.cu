@@ -205,8 +205,9 @@ __device__ __forceinline__ void top2_insert4(uint32_t& m1, uint32_t& m2, uint32_
     top2_insert(m1, m2, k3);
 }
 
-template <int R, int THREADS, int CH, int STAGES, int VARIANT, bool LAZY>
+template <int R, int THREADS, int CH, int STAGES, int VARIANT, bool LAZY, bool PACK>
 __global__ void __launch_bounds__(THREADS) knn2_kernel(const KnnParams p) {
+    static_assert(!PACK || (R % 2 == 0 && CH == 128), "packed top-2 pairs queries and needs 7-bit row indices");
     constexpr int BQ = R * THREADS;
     constexpr bool X = (VARIANT == 3);
     constexpr int QW = X ? 10 : 8;
@@ -274,23 +275,50 @@ __global__ void __launch_bounds__(THREADS) knn2_kernel(const KnnParams p) {
         for (int c = 0; c < STAGES - 1 && c < nchunks; ++c) issue(c);
     }
 
-    // distance + key of query r against row j of the current chunk
-    auto key_of = [&](const uint4* __restrict__ tp, int j, int r, uint32_t jg) -> uint32_t {
-        uint32_t d;
+    // distance of query r against row j of the current chunk
+    auto dist_of = [&](const uint4* __restrict__ tp, int j, int r) -> uint32_t {
         if (X) {
             const uint4 e0 = xtile[3 * j], e1 = xtile[3 * j + 1];
             const uint4 e2 = xtile[3 * j + 2];
             uint32_t qc[10];
 #pragma unroll
             for (int i = 0; i < 10; ++i) qc[i] = qd[r][i < QW ? i : 0];
-            d = hamming256_x(qc, e0, e1, make_uint2(e2.x, e2.y), w2);
+            return hamming256_x(qc, e0, e1, make_uint2(e2.x, e2.y), w2);
         } else {
             uint32_t q8[8];
 #pragma unroll
             for (int i = 0; i < 8; ++i) q8[i] = qd[r][i];
-            d = hamming256<VARIANT>(q8, tp[2 * j], tp[2 * j + 1]);
+            return hamming256<VARIANT>(q8, tp[2 * j], tp[2 * j + 1]);
         }
-        return imad(d, key_mul, jg);
+    };
+    auto key_of = [&](const uint4* __restrict__ tp, int j, int r, uint32_t jg) -> uint32_t {
+        return imad(dist_of(tp, j, r), key_mul, jg);
+    };
+    // PACK: chunk-local 16-bit keys  dist<<7 | row-in-chunk  of two queries share one register, so one
+    // VIMNMX.U16x2 updates two top-2 lists; flushed into the 32-bit global keys at the end of every chunk.
+    uint32_t mp1[PACK ? R / 2 : 1], mp2[PACK ? R / 2 : 1];
+#pragma unroll
+    for (int i = 0; i < (PACK ? R / 2 : 1); ++i) { mp1[i] = 0xFFFFFFFFu; mp2[i] = 0xFFFFFFFFu; }
+    auto pack_insert = [&](const uint4* __restrict__ tp, int j, int rp) {
+        const uint32_t da = dist_of(tp, j, 2 * rp), db = dist_of(tp, j, 2 * rp + 1);
+        const uint32_t kp = imad(imad(db, p.w65536, da), p.w128, (uint32_t)j * 0x10001u);
+        mp2[rp] = __vminu2(mp2[rp], __vmaxu2(mp1[rp], kp));
+        mp1[rp] = __vminu2(mp1[rp], kp);
+    };
+    auto pack_flush = [&](uint32_t jbase) {
+#pragma unroll
+        for (int rp = 0; rp < (PACK ? R / 2 : 0); ++rp) {
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const uint32_t k1 = h ? (mp1[rp] >> 16) : (mp1[rp] & 0xFFFFu);
+                const uint32_t k2 = h ? (mp2[rp] >> 16) : (mp2[rp] & 0xFFFFu);
+                const uint32_t g1 = (k1 == 0xFFFFu) ? TVG_SENTINEL_KEY : (((k1 >> 7) << TVG_KEY_SHIFT) | (jbase + (k1 & 127u)));
+                const uint32_t g2 = (k2 == 0xFFFFu) ? TVG_SENTINEL_KEY : (((k2 >> 7) << TVG_KEY_SHIFT) | (jbase + (k2 & 127u)));
+                top2_merge(m1[2 * rp + h], m2[2 * rp + h], g1, g2);
+            }
+            mp1[rp] = 0xFFFFFFFFu;
+            mp2[rp] = 0xFFFFFFFFu;
+        }
     };
 
     for (int c = 0; c < nchunks; ++c) {
@@ -311,41 +339,60 @@ __global__ void __launch_bounds__(THREADS) knn2_kernel(const KnnParams p) {
         }
         const uint32_t jbase = (uint32_t)(row0 + c * CH);
         int j = 0;
-        for (; j + 4 <= rows; j += 4) {
+        if (PACK) {
+            for (; j + 4 <= rows; j += 4) {
 #pragma unroll
-            for (int r = 0; r < R; ++r) {
-                const uint32_t k0 = key_of(tp, j, r, jbase + j);
-                const uint32_t k1 = key_of(tp, j + 1, r, jbase + j + 1);
-                const uint32_t k2 = key_of(tp, j + 2, r, jbase + j + 2);
-                const uint32_t k3 = key_of(tp, j + 3, r, jbase + j + 3);
-                top2_insert4<LAZY>(m1[r], m2[r], k0, k1, k2, k3);
+                for (int rp = 0; rp < R / 2; ++rp) {
+                    pack_insert(tp, j, rp);
+                    pack_insert(tp, j + 1, rp);
+                    pack_insert(tp, j + 2, rp);
+                    pack_insert(tp, j + 3, rp);
+                }
             }
-        }
-        for (; j < rows; ++j) {
+            for (; j < rows; ++j) {
 #pragma unroll
-            for (int r = 0; r < R; ++r) top2_insert(m1[r], m2[r], key_of(tp, j, r, jbase + j));
+                for (int rp = 0; rp < R / 2; ++rp) pack_insert(tp, j, rp);
+            }
+            pack_flush(jbase);
+        } else {
+            for (; j + 4 <= rows; j += 4) {
+#pragma unroll
+                for (int r = 0; r < R; ++r) {
+                    const uint32_t k0 = key_of(tp, j, r, jbase + j);
+                    const uint32_t k1 = key_of(tp, j + 1, r, jbase + j + 1);
+                    const uint32_t k2 = key_of(tp, j + 2, r, jbase + j + 2);
+                    const uint32_t k3 = key_of(tp, j + 3, r, jbase + j + 3);
+                    top2_insert4<LAZY>(m1[r], m2[r], k0, k1, k2, k3);
+                }
+            }
+            for (; j < rows; ++j) {
+#pragma unroll
+                for (int r = 0; r < R; ++r) top2_insert(m1[r], m2[r], key_of(tp, j, r, jbase + j));
+            }
         }
         __syncthreads();  // every warp is done with stage st (and xtile) before they are refilled
     }
     knn2_finish<R, THREADS>(p, b, qt, split, q0, nq, m1, m2, &s_is_last);
 }
 
-template <int R, int THREADS, int CH, int STAGES, int VARIANT, bool LAZY>
+template <int R, int THREADS, int CH, int STAGES, int VARIANT, bool LAZY, bool PACK>
 static cudaError_t launch_cfg(const KnnParams& p, int batch, int qtiles, cudaStream_t stream) {
     dim3 grid(qtiles, p.splits, batch);
-    knn2_kernel<R, THREADS, CH, STAGES, VARIANT, LAZY><<<grid, THREADS, 0, stream>>>(p);
+    knn2_kernel<R, THREADS, CH, STAGES, VARIANT, LAZY, PACK><<<grid, THREADS, 0, stream>>>(p);
     return cudaGetLastError();
 }
 
 int knn2_block_queries(int r) { return r * 128; }
 
-// variant: 0..3 popcount form, +4 = lazy top-2 insertion (variants 1 and 3 only)
+// variant: 0..3 popcount form; +4 = lazy top-2 insertion (1, 3 only); +8 = packed 16-bit top-2 (1, 3 only)
 cudaError_t launch_knn2(const KnnParams& p, int batch, int qtiles, int r, int variant, cudaStream_t stream) {
-#define TVG_KNN_CASE(RR, VV, LZ) \
-    if (r == RR && variant == VV + (LZ ? 4 : 0)) return launch_cfg<RR, 128, 128, 3, VV, LZ>(p, batch, qtiles, stream);
-#define TVG_KNN_R(RR)                                                                                  \
-    TVG_KNN_CASE(RR, 0, false) TVG_KNN_CASE(RR, 1, false) TVG_KNN_CASE(RR, 2, false) TVG_KNN_CASE(RR, 3, false) \
-    TVG_KNN_CASE(RR, 1, true) TVG_KNN_CASE(RR, 3, true)
+#define TVG_KNN_CASE(RR, VV, LZ, PK) \
+    if (r == RR && variant == VV + (LZ ? 4 : 0) + (PK ? 8 : 0))  \
+        return launch_cfg<RR, 128, 128, 3, VV, LZ, PK>(p, batch, qtiles, stream);
+#define TVG_KNN_R(RR)                                                                                       \
+    TVG_KNN_CASE(RR, 0, false, false) TVG_KNN_CASE(RR, 1, false, false) TVG_KNN_CASE(RR, 2, false, false)   \
+    TVG_KNN_CASE(RR, 3, false, false) TVG_KNN_CASE(RR, 1, true, false) TVG_KNN_CASE(RR, 3, true, false)     \
+    TVG_KNN_CASE(RR, 1, false, true) TVG_KNN_CASE(RR, 3, false, true)
     TVG_KNN_R(2) TVG_KNN_R(4) TVG_KNN_R(8)
 #undef TVG_KNN_R
 #undef TVG_KNN_CASE

@@ -113,11 +113,93 @@ __global__ void __launch_bounds__(TRI_THREADS) triangulate_kernel(const TriParam
     double4* out = reinterpret_cast<double4*>(p.points4d);
     out[o] = make_double4(X[0], X[1], X[2], X[3]);
     if (p.good) p.good[o] = (X[2] > 0.0) ? 1 : 0;  // check_points: world z > 0
+    if (p.reproj || p.parallax_cos) {
+        // The filters slam.py:236 leaves as TODO (no reference behaviour; spec: oracle/two_view.py point_quality).
+        const double* P1 = sP;
+        const double* P2 = sP + 16;
+        double c1[3], c2[3];
+#pragma unroll
+        for (int r = 0; r < 3; ++r) {
+            c1[r] = P1[r * 4] * X[0] + P1[r * 4 + 1] * X[1] + P1[r * 4 + 2] * X[2] + P1[r * 4 + 3];
+            c2[r] = P2[r * 4] * X[0] + P2[r * 4 + 1] * X[1] + P2[r * 4 + 2] * X[2] + P2[r * 4 + 3];
+        }
+        if (p.reproj) {
+            const double e1 = hypot(c1[0] / c1[2] - x1, c1[1] / c1[2] - y1);
+            const double e2 = hypot(c2[0] / c2[2] - x2, c2[1] / c2[2] - y2);
+            p.reproj[o] = p.focal * fmax(e1, e2);
+        }
+        if (p.parallax_cos) {
+            // rays from the two camera centres to X, in the world frame: R^T * (camera-frame point)
+            double r1[3], r2[3];
+#pragma unroll
+            for (int k = 0; k < 3; ++k) {
+                r1[k] = P1[k] * c1[0] + P1[4 + k] * c1[1] + P1[8 + k] * c1[2];
+                r2[k] = P2[k] * c2[0] + P2[4 + k] * c2[1] + P2[8 + k] * c2[2];
+            }
+            const double d = r1[0] * r2[0] + r1[1] * r2[1] + r1[2] * r2[2];
+            const double n1 = r1[0] * r1[0] + r1[1] * r1[1] + r1[2] * r1[2];
+            const double n2 = r2[0] * r2[0] + r2[1] * r2[1] + r2[2] * r2[2];
+            p.parallax_cos[o] = d * rsqrt(n1 * n2);
+        }
+    }
 }
 
 cudaError_t launch_triangulate(const TriParams& p, int batch, cudaStream_t stream) {
     dim3 grid((p.n_max + TRI_THREADS - 1) / TRI_THREADS, batch);
     triangulate_kernel<<<grid, TRI_THREADS, 0, stream>>>(p);
+    return cudaGetLastError();
+}
+
+// Point-cloud append of Map.add_observation (slam.py:37-40) for whole sequences on the device: per sequence,
+// (0,0,0,1) for the first frame (slam.py:248) followed by every pair's points with z > 0, in frame order --
+// the `points` half of the (poses, points) tuple Map.display() hands to the viewer (slam.py:81-84).
+constexpr int MAP_THREADS = 256;
+
+__global__ void __launch_bounds__(MAP_THREADS) map_accumulate_kernel(const MapParams p) {
+    __shared__ int s_cnt[MAP_THREADS / 32];
+    const int s = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    double4* out = reinterpret_cast<double4*>(p.map_points) + (size_t)s * p.cap;
+    long long base = 0;
+    if (p.include_origin) {
+        if (tid == 0 && p.cap > 0) out[0] = make_double4(0.0, 0.0, 0.0, 1.0);
+        base = 1;
+    }
+    for (int b = p.seq_off[s]; b < p.seq_off[s + 1]; ++b) {
+        const int n = min(p.n_pts[b], p.n_max);
+        const size_t ob = (size_t)b * p.n_max;
+        const int per = (n + MAP_THREADS - 1) / MAP_THREADS;
+        const int lo = min(n, tid * per), hi = min(n, lo + per);
+        int cnt = 0;
+        for (int i = lo; i < hi; ++i) cnt += p.good[ob + i] ? 1 : 0;
+        int incl = cnt;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const int v = __shfl_up_sync(0xffffffffu, incl, d);
+            if (lane >= d) incl += v;
+        }
+        __syncthreads();   // s_cnt reuse across iterations
+        if (lane == 31) s_cnt[warp] = incl;
+        __syncthreads();
+        int off = 0, total = 0;
+#pragma unroll
+        for (int w = 0; w < MAP_THREADS / 32; ++w) {
+            if (w < warp) off += s_cnt[w];
+            total += s_cnt[w];
+        }
+        long long pos = base + off + incl - cnt;
+        for (int i = lo; i < hi; ++i) {
+            if (!p.good[ob + i]) continue;
+            if (pos < p.cap) out[pos] = reinterpret_cast<const double4*>(p.points4d)[ob + i];
+            ++pos;
+        }
+        if (tid == 0 && p.pair_off) p.pair_off[b] = (int32_t)base;
+        base += total;
+    }
+    if (tid == 0) p.map_count[s] = (int32_t)base;
+}
+
+cudaError_t launch_map_accumulate(const MapParams& p, int nseq, cudaStream_t stream) {
+    map_accumulate_kernel<<<nseq, MAP_THREADS, 0, stream>>>(p);
     return cudaGetLastError();
 }
 

@@ -23,7 +23,7 @@ struct KnnParams {
     int32_t* dist;             // [batch][n_max][2]
     uint8_t* keep;             // [batch][n_max] ratio-test flag (may be NULL)
     double ratio;
-    uint32_t key_mul, w2;      // 1<<23 and 2, passed as data so the multiplies stay IMADs (FMA pipe)
+    uint32_t key_mul, w2, w128, w65536;  // 1<<23, 2, 128, 65536 passed as data so the multiplies stay IMADs (FMA pipe)
 };
 cudaError_t launch_knn2(const KnnParams& p, int batch, int qtiles, int r, int variant, cudaStream_t stream);
 int knn2_block_queries(int r);
@@ -127,8 +127,25 @@ struct TriParams {
     double kinv[9];
     double* points4d;          // [batch][n_max][4]
     uint8_t* good;             // [batch][n_max]  z > 0   (may be NULL)
+    double* reproj;            // [batch][n_max] max reprojection error over both views, pixels (may be NULL)
+    double* parallax_cos;      // [batch][n_max] cosine of the angle between the two viewing rays (may be NULL)
+    double focal;              // pixels per normalised unit for `reproj` (K[0][0])
 };
 cudaError_t launch_triangulate(const TriParams& p, int batch, cudaStream_t stream);
+
+struct MapParams {
+    const double* points4d;    // [batch][n_max][4]
+    const uint8_t* good;       // [batch][n_max]
+    const int32_t* n_pts;      // [batch]
+    const int32_t* seq_off;    // [nseq+1]
+    int n_max;
+    long long cap;             // rows available per sequence in map_points
+    int include_origin;        // prepend (0,0,0,1): what the first frame hands to the map (slam.py:248)
+    double* map_points;        // [nseq][cap][4]
+    int32_t* map_count;        // [nseq] rows the sequence needs (may exceed cap: the excess is dropped)
+    int32_t* pair_off;         // [batch] row of each pair's first point inside its sequence (may be NULL)
+};
+cudaError_t launch_map_accumulate(const MapParams& p, int nseq, cudaStream_t stream);
 
 struct ExtractRtParams {
     const double* E;           // [batch][9]

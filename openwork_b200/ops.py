@@ -288,6 +288,75 @@ def triangulate_batched(pix1, pix2, n_pts, pair_pinv, K, ctx=None):
     return X, good.bool()
 
 
+def point_quality(pts1, pts2, pose1, pose2, K, ctx=None):
+    """Triangulation plus the filters slam.py:236 leaves as TODO (spec: oracle.two_view.point_quality):
+    returns (points4d f64[M,4], reproj_px f64[M], parallax_cos f64[M])."""
+    dev = _device_of(pts1, pts2)
+    p1 = _dev(pts1, torch.float64, dev)
+    p2 = _dev(pts2, torch.float64, dev)
+    M = p1.shape[0]
+    ctx = ctx or context(dev.index)
+    P = np.stack([np.linalg.inv(np.asarray(_np(pose1), dtype=np.float64)),
+                  np.linalg.inv(np.asarray(_np(pose2), dtype=np.float64))])
+    Pd = _dev(P, torch.float64, dev)
+    kinv, kinv_p = _kinv(K)
+    X = torch.empty((max(M, 1), 4), dtype=torch.float64, device=dev)
+    rep = torch.empty(max(M, 1), dtype=torch.float64, device=dev)
+    par = torch.empty(max(M, 1), dtype=torch.float64, device=dev)
+    if M > 0:
+        check(ctx.lib.tvg_point_quality(ctx.handle, _p(p1), _p(p2), 1, M, M, None, C.c_void_p(Pd.data_ptr()), 32,
+                                        C.c_void_p(Pd.data_ptr() + 128), 32, kinv_p, float(np.asarray(K)[0, 0]),
+                                        _p(X), None, _p(rep), _p(par), _stream()), "tvg_point_quality")
+    return X[:M], rep[:M], par[:M]
+
+
+def map_accumulate(points4d, good, n_pts, seq_off=None, cap=None, include_origin=True, ctx=None):
+    """Point-cloud append of ``Map.add_observation`` (slam.py:37-40) for whole sequences on the device.
+
+    points4d f64[B,N,4], good bool/u8[B,N], n_pts int32[B] (outputs of process_pairs_device).  Returns
+    (map_points f64[nseq,cap,4], map_count int32[nseq], pair_off int32[B]): per sequence the origin point of
+    the first frame (slam.py:248) followed by every pair's z>0 points in pair order."""
+    dev = _device_of(points4d)
+    pts = _dev(points4d, torch.float64, dev)
+    B, N, _ = pts.shape
+    g8 = _dev(good, None, dev).to(torch.uint8).contiguous()
+    n = _dev(n_pts, torch.int32, dev)
+    if seq_off is None:
+        seq_off = np.array([0, B], dtype=np.int32)
+    so = seq_off if isinstance(seq_off, torch.Tensor) else np.asarray(seq_off, dtype=np.int32)
+    so = _dev(so, torch.int32, dev)
+    nseq = so.shape[0] - 1
+    if cap is None:
+        so_h = _np(so)
+        cap = int(max(so_h[1:] - so_h[:-1])) * N + 1
+    ctx = ctx or context(dev.index)
+    mp = torch.empty((nseq, cap, 4), dtype=torch.float64, device=dev)
+    cnt = torch.zeros(nseq, dtype=torch.int32, device=dev)
+    off = torch.zeros(B, dtype=torch.int32, device=dev)
+    check(ctx.lib.tvg_map_accumulate(ctx.handle, _p(pts), _p(g8), _p(n), _p(so), nseq, N, cap,
+                                     1 if include_origin else 0, _p(mp), _p(cnt), _p(off), _stream()),
+          "tvg_map_accumulate")
+    return mp, cnt, off
+
+
+def run_sequences(des, kps, K, words, seq_off=None, residual_threshold=RESIDUAL_THRESHOLD, ratio=RATIO, ctx=None):
+    """Whole sequences without host round-trips: what the reference's ``__main__`` loop accumulates in ``Map``
+    (slam.py:283-293, 37-40, 81-84).  des u8[F,N,32], kps f64[F,N,2] with the frames of sequence s stored
+    consecutively.  Returns a list of (poses f64[F_s,4,4], points f64[P_s,4]) per sequence (CUDA tensors)."""
+    out = process_pairs_device(des, kps, K, words=words, seq_off=seq_off, ratio=ratio,
+                               residual_threshold=residual_threshold,
+                               outputs=("n_inl", "poses", "points4d", "good", "status"), ctx=ctx)
+    B = out["n_inl"].shape[0]
+    so = np.array([0, B], dtype=np.int32) if seq_off is None else np.asarray(_np(seq_off), dtype=np.int32)
+    mp, cnt, _ = map_accumulate(out["points4d"], out["good"], out["n_inl"], so, ctx=ctx)
+    cnt = cnt.cpu().numpy()
+    res = []
+    for s in range(len(so) - 1):
+        p0 = so[s] + s
+        res.append((out["poses"][p0:p0 + (so[s + 1] - so[s]) + 1], mp[s, :cnt[s]]))
+    return res
+
+
 def check_points(points4d):
     """``check_points`` (slam.py:233-237): world z > 0 (elementwise on the device tensor)."""
     return points4d[:, 2] > 0

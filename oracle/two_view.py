@@ -345,6 +345,33 @@ def check_points(points4d):
     return points4d[:, 2] > 0
 
 
+def point_quality(pts1, pts2, pose1, pose2, K):
+    """SPEC (no reference behaviour: slam.py:236 only says "TODO: parallax, reprojection error filters").
+    For each triangulated point: the larger of the two reprojection errors, in pixels (focal = K[0,0]), and
+    the cosine of the angle between the two viewing rays (parallax).  Returns (points4d, reproj_px, cos)."""
+    X = triangulate_batched(pts1, pts2, pose1, pose2, K)
+    P1, P2 = np.linalg.inv(pose1), np.linalg.inv(pose2)
+    n1, n2 = normalize(K, pts1), normalize(K, pts2)
+    c1 = X @ P1[:3].T
+    c2 = X @ P2[:3].T
+    with np.errstate(divide="ignore", invalid="ignore"):
+        e1 = np.hypot(c1[:, 0] / c1[:, 2] - n1[:, 0], c1[:, 1] / c1[:, 2] - n1[:, 1])
+        e2 = np.hypot(c2[:, 0] / c2[:, 2] - n2[:, 0], c2[:, 1] / c2[:, 2] - n2[:, 1])
+        r1 = c1 @ P1[:3, :3]          # R1^T c1 : ray in the world frame
+        r2 = c2 @ P2[:3, :3]
+        cos = np.sum(r1 * r2, axis=1) / (np.linalg.norm(r1, axis=1) * np.linalg.norm(r2, axis=1))
+    return X, float(np.asarray(K)[0, 0]) * np.maximum(e1, e2), cos
+
+
+def map_points(pairs_points4d, pairs_good):
+    """Map.add_observation's append (slam.py:37-40, 248, 266): origin for the first frame, then each pair's
+    z>0 points in order.  Returns f64[P,4]."""
+    rows = [np.array([[0.0, 0.0, 0.0, 1.0]])]
+    for X, g in zip(pairs_points4d, pairs_good):
+        rows.append(X[g])
+    return np.concatenate(rows, axis=0)
+
+
 def cheirality_votes(E, src, dst):
     """Votes for the four (R, +-t) decompositions of E: number of correspondences whose
     DLT-triangulated point has positive depth in BOTH cameras (x_dst = R x_src + t).

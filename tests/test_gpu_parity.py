@@ -71,7 +71,8 @@ def test_knn2_empty(ops):
 
 @pytest.mark.parametrize("r,variant,ctas", [(2, 0, 6), (4, 0, 1), (4, 1, 6), (4, 2, 6), (8, 0, 4), (8, 1, 8),
                                             (2, 1, 16), (2, 2, 3), (8, 2, 2), (4, 3, 6), (2, 3, 2), (8, 3, 8),
-                                            (4, 5, 6), (2, 5, 1), (8, 5, 8), (4, 7, 6), (2, 7, 16), (8, 7, 3)])
+                                            (4, 5, 6), (2, 5, 1), (8, 5, 8), (4, 7, 6), (2, 7, 16), (8, 7, 3),
+                                            (4, 9, 6), (2, 9, 3), (8, 9, 8), (4, 11, 6), (2, 11, 16), (8, 11, 1)])
 def test_knn2_every_config_is_bit_identical(ops, r, variant, ctas):
     q, t = synth.correlated_descriptors(3000, 2500, seed=r * 100 + variant * 10 + ctas)
     t[100:200] = t[300:400]
@@ -509,3 +510,49 @@ def test_pairs_host_submit_wait_two_contexts(ops):
         for kk in outs:
             assert torch.equal(r[kk], g[kk]) or (kk in ("E", "Rt", "poses") and
                                                  np.array_equal(r[kk].numpy(), g[kk].numpy(), equal_nan=True)), kk
+
+
+# ------------------------------------------------------------------------------ "next" rows
+def test_point_quality_matches_spec(ops):
+    src, dst, (lk, ck, i1, i2) = _pair_correspondences(1500, 61)
+    ref = tv.ransac_essential(src, dst, synth.sample_table(len(src), 128, 3), THR)
+    inl = ref["mask"]
+    pose0 = np.eye(4)
+    pose1 = tv.extract_Rt(ref["E"]) @ pose0
+    p1, p2 = lk[i2][inl], ck[i1][inl]
+    Xr, er, cr = tv.point_quality(p1, p2, pose0, pose1, K)
+    X, e, c = ops.point_quality(p1, p2, pose0, pose1, K)
+    X, e, c = X.cpu().numpy(), e.cpu().numpy(), c.cpu().numpy()
+    rel = np.linalg.norm(X[:, :3] - Xr[:, :3], axis=1) / np.maximum(np.linalg.norm(Xr[:, :3], axis=1), 1e-12)
+    ok = rel < 1e-6
+    assert ok.mean() > 0.99
+    np.testing.assert_allclose(e[ok], er[ok], rtol=1e-3, atol=1e-6)
+    np.testing.assert_allclose(c[ok], cr[ok], atol=1e-7)
+    assert (c <= 1.0 + 1e-12).all() and np.median(e) < 5.0
+
+
+def test_run_sequences_map_accumulation(ops):
+    """Device-resident sequence driver: (poses, points) per sequence == what the reference's loop would have
+    accumulated in Map (origin point, then every pair's z>0 points in order)."""
+    N, H = 700, 96
+    fa, _ = synth.make_sequence(4, N, seed=71)
+    fb, _ = synth.make_sequence(3, N, seed=72)
+    frames = fa + fb
+    des = np.stack([f[1] for f in frames])
+    kps = np.stack([f[0] for f in frames])
+    words = synth.sample_words(H, 6)
+    seq_off = np.array([0, 3, 5], dtype=np.int32)
+    res = ops.run_sequences(torch.from_numpy(des).cuda(), torch.from_numpy(kps).cuda(), K, words, seq_off=seq_off)
+    for s, fr in enumerate((fa, fb)):
+        poses, pts = res[s][0].cpu().numpy(), res[s][1].cpu().numpy()
+        pose = np.eye(4)
+        Xs, gs, ref_poses = [], [], [pose]
+        for i in range(len(fr) - 1):
+            r = tv.process_pair(fr[i][0], fr[i][1], fr[i + 1][0], fr[i + 1][1], pose, K, words=words)
+            Xs.append(r["points4d"]); gs.append(r["good"]); pose = r["curr_pose"]; ref_poses.append(pose)
+        ref_pts = tv.map_points(Xs, gs)
+        assert poses.shape == (len(fr), 4, 4) and pts.shape == ref_pts.shape
+        np.testing.assert_allclose(poses, np.stack(ref_poses), atol=1e-5)
+        assert np.array_equal(pts[0], [0, 0, 0, 1])
+        rel = np.linalg.norm(pts[1:, :3] - ref_pts[1:, :3], axis=1) / np.linalg.norm(ref_pts[1:, :3], axis=1)
+        assert np.median(rel) < X_TOL and (rel < 1e-3).mean() > 0.99
