@@ -215,6 +215,12 @@ typedef struct tvg_pairs_io {
 } tvg_pairs_io;
 TVG_API int tvg_pairs_device(tvg_ctx* ctx, const tvg_pairs_io* io, void* stream);
 
+/* Stage timing of tvg_pairs_device: with profiling on, CUDA events are recorded at the stage boundaries on the
+ * caller's stream; tvg_get_stage_ms waits for the last profiled call and returns the 9 stage durations in ms:
+ * knn2, compact, fit, score, reduce, rescore, refit+solve, pose (cheirality + pose chain), triangulate. */
+TVG_API int tvg_set_profile(tvg_ctx* ctx, int on);
+TVG_API int tvg_get_stage_ms(tvg_ctx* ctx, float* ms, int n);
+
 /* Pairs per chunk of tvg_pairs_host's copy/compute pipeline (default 256). */
 TVG_API int tvg_set_host_chunk(tvg_ctx* ctx, int pairs);
 

@@ -71,6 +71,8 @@ SIGNATURES = {
                                  c_vp, c_vp]),
     "tvg_pairs_device": (C.c_int, [c_vp, C.POINTER(PairsIO), c_vp]),
     "tvg_set_host_chunk": (C.c_int, [c_vp, C.c_int]),
+    "tvg_set_profile": (C.c_int, [c_vp, C.c_int]),
+    "tvg_get_stage_ms": (C.c_int, [c_vp, c_f32p, C.c_int]),
     "tvg_pairs_host": (C.c_int, [c_vp, C.POINTER(PairsIO), C.c_int, C.POINTER(C.c_longlong),
                                  C.POINTER(C.c_longlong), c_vp]),
     "tvg_pairs_host_submit": (C.c_int, [c_vp, C.POINTER(PairsIO), C.c_int, C.POINTER(C.c_longlong),
@@ -133,6 +135,17 @@ class Context:
     @property
     def launches(self):
         return int(self.lib.tvg_launch_count(self.handle))
+
+    STAGES = ("knn2", "compact", "fit", "score", "reduce", "rescore", "refit_solve", "pose", "triangulate")
+
+    def set_profile(self, on=True):
+        check(self.lib.tvg_set_profile(self.handle, 1 if on else 0), "tvg_set_profile")
+
+    def stage_ms(self):
+        """Durations (ms) of the 9 stages of the last profiled tvg_pairs_device call."""
+        buf = (C.c_float * 9)()
+        check(self.lib.tvg_get_stage_ms(self.handle, buf, 9), "tvg_get_stage_ms")
+        return dict(zip(self.STAGES, [float(v) for v in buf]))
 
     def set_host_chunk(self, pairs=256):
         check(self.lib.tvg_set_host_chunk(self.handle, int(pairs)), "tvg_set_host_chunk")

@@ -41,6 +41,10 @@ enum Slot {
 
 }  // namespace
 
+// stage marks of the pair pipeline: before knn, compact, fit, score, reduce, rescore, refit+solve,
+// pose stage (cheirality + pose chain), triangulate, and after triangulate
+#define TVG_PROF_MARKS 10
+
 struct tvg_ctx {
     int device = 0;
     int sm_count = 148;
@@ -50,6 +54,18 @@ struct tvg_ctx {
     int host_chunk_pairs = 256;
     cudaStream_t s_in = nullptr, s_out = nullptr;
     cudaEvent_t done_event = nullptr;
+    // optional stage timing of tvg_pairs_device (tvg_set_profile): events at the stage boundaries
+    bool profile = false;
+    cudaEvent_t prof[TVG_PROF_MARKS] = {};
+    int mark(int i, cudaStream_t st) {
+        if (!profile) return 0;
+        if (!prof[i]) {
+            cudaError_t e = cudaEventCreate(&prof[i]);
+            if (e != cudaSuccess) return cuda_fail(e, "cudaEventCreate");
+        }
+        cudaError_t e = cudaEventRecord(prof[i], st);
+        return e == cudaSuccess ? 0 : cuda_fail(e, "cudaEventRecord");
+    }
     std::vector<cudaEvent_t> events;
     unsigned char* pin = nullptr;   // pinned host staging for the small uploads of the host entry
     size_t pin_bytes = 0, pin_used = 0;
@@ -176,6 +192,8 @@ void tvg_ctx_destroy(tvg_ctx* ctx) {
     if (ctx->s_out) cudaStreamDestroy(ctx->s_out);
     if (ctx->pin) cudaFreeHost(ctx->pin);
     if (ctx->done_event) cudaEventDestroy(ctx->done_event);
+    for (int i = 0; i < TVG_PROF_MARKS; ++i)
+        if (ctx->prof[i]) cudaEventDestroy(ctx->prof[i]);
     delete ctx;
 }
 
@@ -317,11 +335,18 @@ int tvg_ransac_essential(tvg_ctx* ctx, const tvg_ransac_io* io, void* stream) {
     TVG_OUT(ctx, io->status, S_STATUS, B * sizeof(int32_t), p.status, int32_t*);
     TVG_GET(ctx, S_REFITWS, B * tvg::ransac_refit_ws_doubles() * sizeof(double), p.refit_ws, double*);
     cudaStream_t st = (cudaStream_t)stream;
+    int mrc = ctx->mark(2, st);
+    if (mrc) return mrc;
     TVG_CUDA(tvg::launch_ransac_fit(p, io->batch, st));
+    if ((mrc = ctx->mark(3, st))) return mrc;
     TVG_CUDA(tvg::launch_ransac_score(p, io->batch, score_mode, st));
+    if ((mrc = ctx->mark(4, st))) return mrc;
     TVG_CUDA(tvg::launch_ransac_reduce(p, io->batch, st));
+    if ((mrc = ctx->mark(5, st))) return mrc;
     TVG_CUDA(tvg::launch_ransac_rescore(p, io->batch, st));
+    if ((mrc = ctx->mark(6, st))) return mrc;
     TVG_CUDA(tvg::launch_ransac_refit(p, io->batch, st));
+    if ((mrc = ctx->mark(7, st))) return mrc;
     ctx->launches += 6;
     return 0;
 }
@@ -471,9 +496,12 @@ static int pairs_device_impl(tvg_ctx* ctx, const tvg_pairs_io* io, const double*
     TVG_GET(ctx, S_DST, B * N * 2 * sizeof(double), dst, double*);
     TVG_GET(ctx, S_CORR32, B * N * 4 * sizeof(float), corr32, float*);
 
-    int rc = tvg_knn2_hamming256(ctx, io->des, io->des, io->batch, io->n_max, io->n_max, io->n_max, pair_q, pair_t,
-                                 io->frame_count, io->frame_count, io->ratio, idx, dist, keep, stream);
+    int rc = ctx->mark(0, st);
     if (rc) return rc;
+    rc = tvg_knn2_hamming256(ctx, io->des, io->des, io->batch, io->n_max, io->n_max, io->n_max, pair_q, pair_t,
+                             io->frame_count, io->frame_count, io->ratio, idx, dist, keep, stream);
+    if (rc) return rc;
+    if ((rc = ctx->mark(1, st))) return rc;
     rc = tvg_ratio_compact(ctx, keep, idx, io->batch, io->n_max, io->n_max, pair_q, pair_t, io->frame_count,
                            io->kps, io->kps, io->kinv, qidx, tidx, m_count, src, dst, corr32, stream);
     if (rc) return rc;
@@ -523,13 +551,33 @@ static int pairs_device_impl(tvg_ctx* ctx, const tvg_pairs_io* io, const double*
         TVG_CUDA(tvg::launch_pose_chain(pc, nseq, st));
         ctx->launches += 1;
     }
+    if ((rc = ctx->mark(8, st))) return rc;
     // triangulate(frame.last_kps, frame.curr_kps, frame.last_pose, frame.curr_pose)  (slam.py:263)
-    return tvg_triangulate(ctx, pix_last, pix_curr, io->batch, io->n_max, io->n_max, n_inl, pinv, 32, pinv + 16,
-                           32, io->kinv, points, good, stream);
+    rc = tvg_triangulate(ctx, pix_last, pix_curr, io->batch, io->n_max, io->n_max, n_inl, pinv, 32, pinv + 16, 32,
+                         io->kinv, points, good, stream);
+    if (rc) return rc;
+    return ctx->mark(9, st);
 }
 
 int tvg_pairs_device(tvg_ctx* ctx, const tvg_pairs_io* io, void* stream) {
     return pairs_device_impl(ctx, io, nullptr, stream);
+}
+
+int tvg_set_profile(tvg_ctx* ctx, int on) {
+    if (!ctx) return fail(-1, "ctx is NULL");
+    ctx->profile = on != 0;
+    return 0;
+}
+
+int tvg_get_stage_ms(tvg_ctx* ctx, float* ms, int n) {
+    if (!ctx || !ms) return fail(-1, "ctx / ms is NULL");
+    if (n < TVG_PROF_MARKS - 1) return fail(-2, "tvg_get_stage_ms: need room for 9 stages");
+    for (int i = 0; i < TVG_PROF_MARKS; ++i)
+        if (!ctx->prof[i]) return fail(-5, "tvg_get_stage_ms: no profiled tvg_pairs_device call yet");
+    DeviceGuard g(ctx->device);
+    TVG_CUDA(cudaEventSynchronize(ctx->prof[TVG_PROF_MARKS - 1]));
+    for (int i = 0; i + 1 < TVG_PROF_MARKS; ++i) TVG_CUDA(cudaEventElapsedTime(&ms[i], ctx->prof[i], ctx->prof[i + 1]));
+    return 0;
 }
 
 int tvg_set_host_chunk(tvg_ctx* ctx, int pairs) {

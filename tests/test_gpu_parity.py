@@ -556,3 +556,36 @@ def test_run_sequences_map_accumulation(ops):
         assert np.array_equal(pts[0], [0, 0, 0, 1])
         rel = np.linalg.norm(pts[1:, :3] - ref_pts[1:, :3], axis=1) / np.linalg.norm(ref_pts[1:, :3], axis=1)
         assert np.median(rel) < X_TOL and (rel < 1e-3).mean() > 0.99
+
+
+def test_pairs_with_degenerate_members_do_not_disturb_the_batch(ops):
+    """A pair with < 9 surviving matches (the reference would raise AssertionError / ValueError, slam.py:138 and
+    skimage) reports status 1 with NaN E and no points; an empty frame likewise; healthy pairs are untouched."""
+    N, H = 600, 64
+    fa, _ = synth.make_sequence(2, N, seed=91)
+    fb, _ = synth.make_sequence(2, N, seed=92)
+    rnd = (np.random.default_rng(0).uniform(0, 480, (N, 2)), synth.random_descriptors(N, 5))
+    rnd2 = (np.random.default_rng(1).uniform(0, 480, (N, 2)), synth.random_descriptors(N, 6))
+    frames = [fa[0], fa[1], rnd, rnd2, fb[0], fb[1], fb[0], fb[1]]
+    des = np.stack([f[1] for f in frames])
+    kps = np.stack([f[0] for f in frames])
+    cnt = np.array([N, N, N, N, N, N, 0, N], dtype=np.int32)       # frame 6 is empty
+    words = synth.sample_words(H, 1)
+    pq = np.array([1, 3, 5, 7], dtype=np.int32)
+    pt = np.array([0, 2, 4, 6], dtype=np.int32)
+    so = np.arange(5, dtype=np.int32)
+    outs = ("m_count", "E", "n_inl", "Rt", "poses", "status", "best", "points4d", "good")
+    out = ops.process_pairs_device(torch.from_numpy(des).cuda(), torch.from_numpy(kps).cuda(), K, words=words,
+                                   frame_count=cnt, pair_q=pq, pair_t=pt, seq_off=so, outputs=outs)
+    out = {k: v.cpu().numpy() for k, v in out.items()}
+    assert out["status"].tolist() == [0, 1, 0, 1]
+    assert out["m_count"][1] <= 8 and out["m_count"][3] == 0
+    assert out["n_inl"][1] == 0 and out["n_inl"][3] == 0 and np.isnan(out["E"][1]).all() and np.isnan(out["E"][3]).all()
+    for b, fr in ((0, fa), (2, fb)):
+        ref = tv.process_pair(fr[0][0], fr[0][1], fr[1][0], fr[1][1], np.eye(4), K, words=words)
+        assert int(out["best"][b]) == ref["ransac"]["best"] and int(out["n_inl"][b]) == int(ref["inliers"].sum())
+        assert _fro_diff(out["E"][b], ref["E"]) < E_TOL
+        np.testing.assert_allclose(out["poses"][2 * b + 1], ref["curr_pose"], atol=1e-5)
+    host, _, _ = ops.process_pairs_host(des, kps, K, words=words, frame_count=cnt, pair_q=pq, pair_t=pt, seq_off=so,
+                                        outputs=("status", "n_inl", "m_count"))
+    assert host["status"].tolist() == [0, 1, 0, 1]
