@@ -52,7 +52,7 @@ def make_batch(pairs, seed=SEED):
 
 
 class ClockSampler(threading.Thread):
-    """Samples SM clock + throttle reasons during the timed region (NVML, 50 ms period)."""
+    """Samples SM clock + throttle reasons during the timed region (NVML, 10 ms period)."""
 
     def __init__(self, index):
         super().__init__(daemon=True)
@@ -90,7 +90,7 @@ class ClockSampler(threading.Thread):
                         self.reasons.add(k)
             except Exception:
                 pass
-            self.stop_evt.wait(0.05)
+            self.stop_evt.wait(0.01)
 
     def summary(self):
         if not self.ok or not self.sm:

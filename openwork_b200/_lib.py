@@ -92,10 +92,15 @@ def load():
     global _lib
     if _lib is not None:
         return _lib
-    if not os.path.isfile(LIB_PATH):
-        raise ImportError(
-            "openwork_b200: %s is missing -- build it with `python -m openwork_b200.build` "
-            "(or __graft_entry__.build()). There is no CPU fallback." % LIB_PATH)
+    # Build (or rebuild after a source change) with nvcc; this compiles the extension, it is not a fallback.
+    try:
+        from . import build as _build
+        _build.build()
+    except Exception as e:
+        if not os.path.isfile(LIB_PATH):
+            raise ImportError(
+                "openwork_b200: %s is missing and could not be built (%s) -- run `python -m openwork_b200.build`. "
+                "There is no CPU fallback." % (LIB_PATH, e))
     lib = C.CDLL(LIB_PATH)
     for name, (res, args) in SIGNATURES.items():
         fn = getattr(lib, name)
