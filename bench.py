@@ -478,7 +478,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--pairs", type=int, default=1024, help="frame pairs per step per GPU")
     ap.add_argument("--knn-r", type=int, default=None, help="matcher queries/thread (default: library auto)")
-    ap.add_argument("--knn-variant", type=int, default=3)
+    ap.add_argument("--knn-variant", type=int, default=11)
     ap.add_argument("--knn-ctas", type=int, default=6)
     ap.add_argument("--host-chunk", type=int, default=4096,
                     help="pairs per chunk of the e2e host pipeline (streaming mode overlaps across batches, so large)")

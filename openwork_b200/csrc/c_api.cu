@@ -48,7 +48,7 @@ enum Slot {
 struct tvg_ctx {
     int device = 0;
     int sm_count = 148;
-    int knn_r = 4, knn_variant = 3, knn_ctas_per_sm = 6;
+    int knn_r = 4, knn_variant = 11, knn_ctas_per_sm = 6;
     bool knn_auto = true;      // until tvg_set_matcher_config is called: r = 2 when the train rows get split
     long long launches = 0;
     int host_chunk_pairs = 256;

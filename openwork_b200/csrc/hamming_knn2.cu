@@ -205,8 +205,8 @@ __device__ __forceinline__ void top2_insert4(uint32_t& m1, uint32_t& m2, uint32_
     top2_insert(m1, m2, k3);
 }
 
-template <int R, int THREADS, int CH, int STAGES, int VARIANT, bool LAZY, bool PACK>
-__global__ void __launch_bounds__(THREADS) knn2_kernel(const KnnParams p) {
+template <int R, int THREADS, int CH, int STAGES, int VARIANT, bool LAZY, bool PACK, int MINB = 1>
+__global__ void __launch_bounds__(THREADS, MINB) knn2_kernel(const KnnParams p) {
     static_assert(!PACK || (R % 2 == 0 && CH == 128), "packed top-2 pairs queries and needs 7-bit row indices");
     constexpr int BQ = R * THREADS;
     constexpr bool X = (VARIANT == 3);
@@ -375,10 +375,10 @@ __global__ void __launch_bounds__(THREADS) knn2_kernel(const KnnParams p) {
     knn2_finish<R, THREADS>(p, b, qt, split, q0, nq, m1, m2, &s_is_last);
 }
 
-template <int R, int THREADS, int CH, int STAGES, int VARIANT, bool LAZY, bool PACK>
+template <int R, int THREADS, int CH, int STAGES, int VARIANT, bool LAZY, bool PACK, int MINB = 1>
 static cudaError_t launch_cfg(const KnnParams& p, int batch, int qtiles, cudaStream_t stream) {
     dim3 grid(qtiles, p.splits, batch);
-    knn2_kernel<R, THREADS, CH, STAGES, VARIANT, LAZY, PACK><<<grid, THREADS, 0, stream>>>(p);
+    knn2_kernel<R, THREADS, CH, STAGES, VARIANT, LAZY, PACK, MINB><<<grid, THREADS, 0, stream>>>(p);
     return cudaGetLastError();
 }
 

@@ -81,7 +81,7 @@ def test_knn2_every_config_is_bit_identical(ops, r, variant, ctas):
         ctx.set_matcher_config(r, variant, ctas)
         idx, dist, keep = ops.knn2_hamming256(q, t, return_keep=True)
     finally:
-        ctx.set_matcher_config(4, 3, 6)
+        ctx.set_matcher_config(4, 11, 6)
     ri, rd = tv.knn2_cv2(q, t)
     assert np.array_equal(idx.cpu().numpy(), ri) and np.array_equal(dist.cpu().numpy(), rd)
     qi, ti = tv.ratio_filter(ri, rd)
@@ -444,7 +444,7 @@ def test_matcher_64k_properties(ops):
         ctx.set_matcher_config(8, 1, 2)
         i2, d2 = ops.knn2_hamming256(q, t)
     finally:
-        ctx.set_matcher_config(4, 3, 6)
+        ctx.set_matcher_config(4, 11, 6)
     assert np.array_equal(i2.cpu().numpy(), idx) and np.array_equal(d2.cpu().numpy(), dist)
 
 

@@ -22,7 +22,7 @@ for variant, r in ((0, 2), (1, 4), (2, 8), (3, 4), (5, 2), (7, 8)):
                                                              "good", "status", "mask", "counts"), pose_mode=variant & 1)
     torch.cuda.synchronize()
     print(variant, r, out["m_count"].tolist(), out["n_inl"].tolist(), out["status"].tolist())
-ctx.set_matcher_config(4, 3, 6)
+ctx.set_matcher_config(4, 11, 6)
 # single-pair ops incl. split-Nt merge path and tiny / degenerate shapes
 for nq, nt in ((1, 2), (3, 1), (130, 77), (700, 1500)):
     q, t = synth.random_descriptors(nq, 1), synth.random_descriptors(nt, 2)

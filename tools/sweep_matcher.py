@@ -50,7 +50,10 @@ def main():
                 for ctas in ((4, 6, 8) if batch == 1 else (6,)):
                     if name == "64k" and (r == 2 or ctas != 6):
                         continue
-                    ctx.set_matcher_config(r, variant, ctas)
+                    try:
+                        ctx.set_matcher_config(r, variant, ctas)
+                    except Exception:
+                        continue
                     ms = time_it(fn, iters=5 if name in ("64k", "2k_x1024") else 50)
                     cur = (idx.clone(), dist.clone(), keep.clone())
                     if ref is None:
@@ -60,7 +63,7 @@ def main():
                                identical=same)
                     print(rec, flush=True)
                     res.append(rec)
-    ctx.set_matcher_config(4, 3, 6)
+    ctx.set_matcher_config(4, 11, 6)
     os.makedirs("gpurun_out", exist_ok=True)
     json.dump(res, open("gpurun_out/sweep_matcher.json", "w"), indent=1)
 
