@@ -589,3 +589,25 @@ def test_pairs_with_degenerate_members_do_not_disturb_the_batch(ops):
     host, _, _ = ops.process_pairs_host(des, kps, K, words=words, frame_count=cnt, pair_q=pq, pair_t=pt, seq_off=so,
                                         outputs=("status", "n_inl", "m_count"))
     assert host["status"].tolist() == [0, 1, 0, 1]
+
+
+def test_knn2_randomised_shapes_and_configs(ops):
+    """Seeded sweep over ragged (Nq, Nt), low-entropy descriptors (many exact ties) and matcher configurations:
+    always equal to the stable-argsort oracle."""
+    rng = np.random.default_rng(20261019)
+    ctx = ops.context(0)
+    variants = [0, 1, 2, 3, 5, 7, 9, 11]
+    try:
+        for trial in range(24):
+            nq = int(rng.integers(1, 1400))
+            nt = int(rng.integers(2, 3000))
+            bits = int(rng.choice([2, 16, 256]))
+            q = rng.integers(0, bits, (nq, 32), dtype=np.uint8)
+            t = rng.integers(0, bits, (nt, 32), dtype=np.uint8)
+            ctx.set_matcher_config(int(rng.choice([2, 4, 8])), int(rng.choice(variants)), int(rng.integers(1, 17)))
+            idx, dist, keep = ops.knn2_hamming256(q, t, return_keep=True)
+            ri, rd = tv.knn2_numpy(q, t)
+            assert np.array_equal(idx.cpu().numpy(), ri) and np.array_equal(dist.cpu().numpy(), rd), (trial, nq, nt)
+            assert np.array_equal(np.flatnonzero(keep.cpu().numpy()), tv.ratio_filter(ri, rd)[0])
+    finally:
+        ctx.set_matcher_config(4, 11, 6)
