@@ -141,10 +141,12 @@ cudaError_t launch_ransac_fit(const RansacParams& p, int batch, cudaStream_t str
 // ------------------------------------------------------------------------------------ score (fp32)
 constexpr int SCORE_THREADS = 128;
 
-// One Sampson evaluation in fp32: 18 FFMA + 2 FMUL (+ 1 MUFU.RCP + 1 FFMA when sum r^2 is wanted) + 2 sign-bit adds.
+// One Sampson evaluation in fp32: 19 FFMA (+ 1 MUFU.RCP + 1 FFMA when sum r^2 is wanted) + 2 sign-bit adds.
+// (Packed fma.rn.f32x2 / FFMA2 over the two hypotheses of a thread was measured: same time -- FFMA2 issues at
+// half the FFMA rate on B200, tools/microbench/fp32_pipes.cu -- so the scalar form stays.)
 template <bool SSE>
 __device__ __forceinline__ void score_eval(const float (&e)[9], const float4 c, float thr2, float band,
-                                           float floor_, unsigned& cnt, unsigned& unc, float& sse) {
+                                           float c1, float k1, unsigned& cnt, unsigned& unc, float& sse) {
     // c = (x, y, u, v): x = src (last), u = dst (curr)
     const float f0 = fmaf(e[0], c.x, fmaf(e[1], c.y, e[2]));
     const float f1 = fmaf(e[3], c.x, fmaf(e[4], c.y, e[5]));
@@ -152,20 +154,22 @@ __device__ __forceinline__ void score_eval(const float (&e)[9], const float4 c, 
     const float g0 = fmaf(e[0], c.z, fmaf(e[3], c.w, e[6]));
     const float g1 = fmaf(e[1], c.z, fmaf(e[4], c.w, e[7]));
     const float num = fmaf(c.z, f0, fmaf(c.w, f1, f2));
-    const float den = fmaf(f0, f0, fmaf(f1, f1, fmaf(g0, g0, g1 * g1)));
-    const float n2 = num * num;
-    const float t = fmaf(-thr2, den, n2);              // r < thr  <=>  num^2 - thr^2 den < 0
     // too close for fp32 to call:  |t| < band*den + floor.  The relative part covers rounding of num^2 and
     // thr^2*den; the absolute floor covers cancellation in num for points near the epipole (den -> 0):
     // 2*thr*sqrt(den)*delta <= (band_rel/2)*thr^2*den + delta^2/(band_rel/2)  with  delta ~ 3e-7 (|E|_F = 1,
-    // |x| <~ 1); the other half of band_rel is the rounding allowance.
-    const float bt = fmaf(-band, den, fabsf(t)) - floor_;
+    // |x| <~ 1); the other half of band_rel is the rounding allowance.  The floor costs no instruction: with
+    // c1 = floor/band added to den and thr^2*c1 added to num^2 (two FMULs become FFMAs), t is unchanged and
+    // band*den' = band*den + floor.
+    const float den = fmaf(f0, f0, fmaf(f1, f1, fmaf(g0, g0, fmaf(g1, g1, c1))));
+    const float n2 = fmaf(num, num, k1);
+    const float t = fmaf(-thr2, den, n2);              // r < thr  <=>  num^2 - thr^2 den < 0
+    const float bt = fmaf(-band, den, fabsf(t));
     cnt += __float_as_uint(t) >> 31;                   // sign bit == (t < 0)
     unc += __float_as_uint(bt) >> 31;
     if (SSE) {
         float rinv;
-        asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(rinv) : "f"(den));
-        sse = fmaf(n2, rinv, sse);
+        asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(rinv) : "f"(den - c1));
+        sse = fmaf(n2 - k1, rinv, sse);
     }
 }
 
@@ -211,7 +215,8 @@ __global__ void __launch_bounds__(SCORE_THREADS) ransac_score_kernel(const Ransa
     }
     const float thr2 = (float)(p.thr * p.thr);
     const float band = p.band_rel * thr2;
-    const float floor_ = p.band_floor;
+    const float c1 = p.band_floor / band;   // den offset that realises the absolute floor
+    const float k1 = thr2 * c1;             // matching num^2 offset: t stays num^2 - thr^2 den
     for (int i = 0; i < n; ++i) {
         mbar_wait(&bar[i & 1], (uint32_t)((i >> 1) & 1));
         const int rows = min(CHUNK, r_end - r_begin - i * CHUNK);
@@ -220,7 +225,7 @@ __global__ void __launch_bounds__(SCORE_THREADS) ransac_score_kernel(const Ransa
         for (int j = 0; j < rows; ++j) {
             const float4 c = cp[j];
 #pragma unroll
-            for (int k = 0; k < HPT; ++k) score_eval<SSE>(e[k], c, thr2, band, floor_, cnt[k], unc[k], sse[k]);
+            for (int k = 0; k < HPT; ++k) score_eval<SSE>(e[k], c, thr2, band, c1, k1, cnt[k], unc[k], sse[k]);
         }
         __syncthreads();   // everyone is done with this stage before TMA refills it
         if (threadIdx.x == 0 && i + 2 < n) issue(i + 2);
