@@ -162,6 +162,18 @@ TVG_API int tvg_map_accumulate(tvg_ctx* ctx, const double* points4d, const uint8
                        const int32_t* seq_off, int nseq, int n_max, long long cap, int include_origin,
                        double* map_points, int32_t* map_count, int32_t* pair_off, void* stream);
 
+/* extract_points(frame) (slam.py:112-122):  cv2.cvtColor(BGR2GRAY) -> cv2.goodFeaturesToTrack(image, max_corners,
+ * qualityLevel, minDistance) -> cv2.ORB_create().compute(image, [KeyPoint(x, y, size=20)]).  SURVEY §8f rank 1; outside
+ * the north-star path (the benchmark feeds synthetic keypoints), provided so that a whole frame can stay on the GPU.
+ * images u8[batch][H][W][channels] (device; channels 3 = BGR, 1 = already gray).  pattern_host = int8[512][2], the ORB
+ * test pattern rotated by the KeyPoint default angle and rounded (HOST pointer; openwork_b200/orb_pattern.npy).
+ * Outputs (device): kps f64[batch][max_corners][2] pixel (x, y) of the keypoints that survive ORB's 31-pixel border
+ * filter, in goodFeaturesToTrack order; des u8[batch][max_corners][32]; n_kps int32[batch];
+ * n_candidates int32[batch] (optional) = local maxima found before the min-distance filter. */
+TVG_API int tvg_extract_points(tvg_ctx* ctx, const uint8_t* images, int batch, int height, int width, int channels,
+                       int max_corners, double quality_level, double min_distance, const int8_t* pattern_host,
+                       double* kps, uint8_t* des, int32_t* n_kps, int32_t* n_candidates, void* stream);
+
 /* Cheirality vote over the four (R, +-t) decompositions of E (north-star extra; the reference uses the
  * trace / t_z heuristics of slam.py:174-181 instead).  votes int32[batch][4], Rts f64[batch][4][16],
  * choice int32[batch].  mask may be NULL. */

@@ -67,6 +67,8 @@ SIGNATURES = {
                                     C.c_longlong, c_f64p, C.c_double, c_vp, c_vp, c_vp, c_vp, c_vp]),
     "tvg_map_accumulate": (C.c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, C.c_int, C.c_int, C.c_longlong, C.c_int, c_vp,
                                      c_vp, c_vp, c_vp]),
+    "tvg_extract_points": (C.c_int, [c_vp, c_vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_double, C.c_double,
+                                     c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
     "tvg_cheirality": (C.c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, C.c_int, C.c_int, C.c_int, c_vp, c_vp,
                                  c_vp, c_vp]),
     "tvg_pairs_device": (C.c_int, [c_vp, C.POINTER(PairsIO), c_vp]),

@@ -33,7 +33,8 @@ enum Slot {
     S_PARTIAL, S_COUNTERS, S_IDX, S_DIST, S_KEEP, S_QIDX, S_TIDX, S_MCOUNT, S_SRC, S_DST, S_CORR32,
     S_E64, S_E32, S_VALID, S_PARTCNT, S_PARTSSE, S_COUNTS, S_BAND, S_SSE32, S_CAND, S_NCAND, S_CANDSSE,
     S_CANDCNT, S_BEST, S_BESTSSE, S_EBEST, S_MASK, S_NINL, S_INLIDX, S_PIXLAST, S_PIXCURR, S_E, S_RT,
-    S_STATUS, S_POSES, S_POSESINV, S_POINTS, S_GOOD, S_PAIRQ, S_PAIRT, S_SEQOFF, S_VOTES, S_RTS, S_CHOICE, S_REFITWS,
+    S_STATUS, S_POSES, S_POSESINV, S_POINTS, S_GOOD, S_PAIRQ, S_PAIRT, S_SEQOFF, S_VOTES, S_RTS, S_CHOICE, S_REFITWS, S_FE_IMG, S_FE_GRAY, S_FE_COV, S_FE_EIG, S_FE_MAX, S_FE_KEYS, S_FE_NCAND,
+    S_FE_CORNERS, S_FE_NCORNERS, S_FE_BLURTMP, S_FE_BLUR,
     // host-entry staging
     S_H_DES, S_H_KPS, S_H_FCOUNT, S_H_PAIRQ, S_H_PAIRT, S_H_SEQOFF, S_H_INIT, S_H_WORDS, S_H_SAMPLES,
     S_NUM
@@ -432,6 +433,52 @@ int tvg_map_accumulate(tvg_ctx* ctx, const double* points4d, const uint8_t* good
     tvg::MapParams p{points4d, good, n_pts, seq_off, n_max, cap, include_origin, map_points, map_count, pair_off};
     TVG_CUDA(tvg::launch_map_accumulate(p, nseq, (cudaStream_t)stream));
     ctx->launches += 1;
+    return 0;
+}
+
+int tvg_extract_points(tvg_ctx* ctx, const uint8_t* images, int batch, int height, int width, int channels,
+                       int max_corners, double quality_level, double min_distance, const int8_t* pattern_host,
+                       double* kps, uint8_t* des, int32_t* n_kps, int32_t* n_candidates, void* stream) {
+    if (!ctx) return fail(-1, "ctx is NULL");
+    if (batch < 0 || height < 64 || width < 64 || height > 32767 || width > 32767 || (channels != 1 && channels != 3) ||
+        max_corners < 1)
+        return fail(-2, "tvg_extract_points: bad sizes (64 <= H, W <= 32767; channels 1 or 3; max_corners >= 1)");
+    if (batch == 0) return 0;
+    if (!images || !pattern_host || !kps || !des || !n_kps) return fail(-3, "tvg_extract_points: NULL array");
+    if (!(quality_level > 0.0) || !(min_distance >= 1.0)) return fail(-2, "tvg_extract_points: quality_level > 0, min_distance >= 1");
+    const int cell = (int)__builtin_rint(min_distance);
+    // one kept corner per grid cell when even the cell diagonal is shorter than min_distance; else at most 4
+    // (min_distance >= cell - 0.5 >= 2/3 of the cell side for cell >= 2: five points that far apart do not fit)
+    const int slots = ((double)(cell - 1) * (cell - 1) * 2.0 < min_distance * min_distance) ? 1 : 4;
+    const int gw = (width + cell - 1) / cell, gh = (height + cell - 1) / cell;
+    if (cell > 15 || (size_t)gw * gh * slots > 200u * 1024u)
+        return fail(-2, "tvg_extract_points: min_distance > 15.5 or image too large for the shared-memory corner grid");
+    DeviceGuard g(ctx->device);
+    cudaStream_t st = (cudaStream_t)stream;
+    const size_t B = (size_t)batch, HW = (size_t)height * width;
+    tvg::FrontendParams p{};
+    p.images = images; p.batch = batch; p.H = height; p.W = width; p.channels = channels;
+    p.max_corners = max_corners; p.cell = cell; p.slots = slots; p.cap = (int)(HW / 2); p.quality = quality_level;
+    p.min_distance = (float)min_distance;
+    TVG_GET(ctx, S_FE_GRAY, B * HW, p.gray, uint8_t*);
+    TVG_GET(ctx, S_FE_COV, B * 3 * HW * sizeof(float), p.cov, float*);
+    TVG_GET(ctx, S_FE_EIG, B * HW * sizeof(float), p.eig, float*);
+    TVG_GET(ctx, S_FE_MAX, B * sizeof(int), p.max_bits, int*);
+    TVG_GET(ctx, S_FE_KEYS, B * (size_t)p.cap * sizeof(unsigned long long), p.keys, unsigned long long*);
+    TVG_OUT(ctx, n_candidates, S_FE_NCAND, B * sizeof(int), p.n_cand, int*);
+    TVG_GET(ctx, S_FE_CORNERS, B * (size_t)max_corners * sizeof(float2), p.corners, float2*);
+    TVG_GET(ctx, S_FE_NCORNERS, B * sizeof(int), p.n_corners, int*);
+    TVG_GET(ctx, S_FE_BLURTMP, B * HW * sizeof(float), p.blur_tmp, float*);
+    TVG_GET(ctx, S_FE_BLUR, B * HW, p.blur, uint8_t*);
+    p.kps = kps; p.des = des; p.n_kps = n_kps;
+    // cv::getGaussianKernel(7, 2, CV_32F): exp(-x^2/8) normalised in double, rounded to float
+    static const uint32_t gauss_bits[7] = {0x3d8fafb1u, 0x3e06387eu, 0x3e434a39u, 0x3e5d4ae0u, 0x3e434a39u, 0x3e06387eu,
+                                           0x3d8fafb1u};
+    float gauss[7];
+    memcpy(gauss, gauss_bits, sizeof(gauss));
+    TVG_CUDA(tvg::frontend_set_tables(pattern_host, gauss, st));
+    TVG_CUDA(tvg::launch_frontend(p, st));
+    ctx->launches += 10;
     return 0;
 }
 

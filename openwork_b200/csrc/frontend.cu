@@ -1,0 +1,310 @@
+// Feature front-end  --  replaces extract_points of
+// /root/reference/MonocularSlam/slam.py:112-122:
+//     image = cv2.cvtColor(frame.image, cv2.COLOR_BGR2GRAY)
+//     pts   = cv2.goodFeaturesToTrack(image, 3000, qualityLevel=0.01, minDistance=3)
+//     kps, des = cv2.ORB_create().compute(image, [cv2.KeyPoint(x, y, size=20) ...])
+// Every float operation below follows the order (and the fused / unfused form) that was found to reproduce
+// opencv-python 4.13 bit for bit on the CPU (tests/test_frontend.py documents the probes):
+//   gray      = (B*3735 + G*19235 + R*9798 + 2^14) >> 15
+//   Sobel 3x3 with scale s = 1/(255*4*3), BORDER_REFLECT_101:
+//       Dx = fma(s, r(y-1) + r(y+1), (2s) * r(y)),  r(y') = p[y'][x+1] - p[y'][x-1]
+//       Dy = q(y+1) - q(y-1),  q(y') = fma(s, p[y'][x+1], fma(2s, p[y'][x], s * p[y'][x-1]))
+//   cov       = 3x3 unnormalised box sums (accumulated in double) of Dx*Dx, Dx*Dy, Dy*Dy
+//   minEig    = (a + c) - sqrt((a - c)^2 + b^2),  a = cov_xx/2, b = cov_xy, c = cov_yy/2   (no FMA)
+//   corners   = pixels > max*quality that equal their 3x3 maximum, sorted by (value, address) descending,
+//               greedily kept when no kept corner lies closer than minDistance (grid of cells), first 3000
+//   ORB       = keypoints inside the 31-pixel border; image blurred 7x7 sigma 2 in fp32 (rows: sequential
+//               FMAs, columns: centre-first symmetric FMAs), rounded to u8; 256 pairwise tests on the learned
+//               pattern rotated by the KeyPoint default angle (-1 degree: no orientation is computed by
+//               ORB.compute for user-supplied keypoints)
+// (OpenCV's boxFilter keeps double running sums along rows and columns; a direct double 9-sum differs from it
+//  in the last bit of cov_xy for ~1e-5 of the pixels, which has never changed a keypoint in the tests.)
+#include "tvg_common.cuh"
+#include "tvg_kernels.h"
+
+namespace tvg {
+
+__constant__ int8_t c_orb_pattern[512 * 2];
+__constant__ float c_gauss7[7];
+
+__device__ __forceinline__ int reflect101(int i, int n) {
+    if (i < 0) i = -i;
+    if (i >= n) i = 2 * n - 2 - i;
+    return i;
+}
+
+__global__ void gray_kernel(const uint8_t* __restrict__ img, uint8_t* __restrict__ gray, size_t npix, int channels) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= npix) return;
+    if (channels == 1) {
+        gray[i] = img[i];
+    } else {
+        const uint32_t b = img[3 * i], g = img[3 * i + 1], r = img[3 * i + 2];
+        gray[i] = (uint8_t)((b * 3735u + g * 19235u + r * 9798u + (1u << 14)) >> 15);
+    }
+}
+
+// Sobel derivatives and their products: cov[b][3][H][W] = (Dx*Dx, Dx*Dy, Dy*Dy)
+__global__ void cov_kernel(const uint8_t* __restrict__ gray, float* __restrict__ cov, int H, int W) {
+    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y, b = blockIdx.z;
+    if (x >= W) return;
+    const uint8_t* g = gray + (size_t)b * H * W;
+    const float s = (float)(1.0 / (255.0 * 4 * 3)), s2 = (float)(2.0 / (255.0 * 4 * 3));
+    const int xm = reflect101(x - 1, W), xp = reflect101(x + 1, W);
+    float r[3], q[3];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        const int yy = reflect101(y - 1 + k, H);
+        const float pm = (float)g[(size_t)yy * W + xm], p0 = (float)g[(size_t)yy * W + x], pp = (float)g[(size_t)yy * W + xp];
+        r[k] = __fsub_rn(pp, pm);
+        q[k] = __fmaf_rn(s, pp, __fmaf_rn(s2, p0, __fmul_rn(s, pm)));
+    }
+    const float dx = __fmaf_rn(s, __fadd_rn(r[0], r[2]), __fmul_rn(s2, r[1]));
+    const float dy = __fsub_rn(q[2], q[0]);
+    float* c = cov + (size_t)b * 3 * H * W + (size_t)y * W + x;
+    c[0] = __fmul_rn(dx, dx);
+    c[(size_t)H * W] = __fmul_rn(dx, dy);
+    c[(size_t)2 * H * W] = __fmul_rn(dy, dy);
+}
+
+__global__ void eig_kernel(const float* __restrict__ cov, float* __restrict__ eig, int* __restrict__ max_bits, int H,
+                           int W) {
+    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y, b = blockIdx.z;
+    float e = 0.0f;
+    if (x < W) {
+        const float* c = cov + (size_t)b * 3 * H * W;
+        double sum[3] = {0.0, 0.0, 0.0};
+#pragma unroll
+        for (int dy = -1; dy <= 1; ++dy) {
+            const int yy = reflect101(y + dy, H);
+#pragma unroll
+            for (int dx = -1; dx <= 1; ++dx) {
+                const int xx = reflect101(x + dx, W);
+#pragma unroll
+                for (int k = 0; k < 3; ++k) sum[k] += (double)c[(size_t)k * H * W + (size_t)yy * W + xx];
+            }
+        }
+        const float a = __fmul_rn((float)sum[0], 0.5f), bb = (float)sum[1], cc = __fmul_rn((float)sum[2], 0.5f);
+        const float d = __fsub_rn(a, cc);
+        e = __fsub_rn(__fadd_rn(a, cc), __fsqrt_rn(__fadd_rn(__fmul_rn(d, d), __fmul_rn(bb, bb))));
+        eig[(size_t)b * H * W + (size_t)y * W + x] = e;
+    }
+    // image maximum (cv::minMaxLoc): positive floats order like their bit patterns
+    float m = e > 0.0f ? e : 0.0f;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if ((threadIdx.x & 31) == 0 && m > 0.0f) atomicMax(max_bits + b, __float_as_int(m));
+}
+
+// threshold + 3x3 non-maximum suppression; candidates are appended as sortable 64-bit keys
+__global__ void collect_kernel(const float* __restrict__ eig, const int* __restrict__ max_bits, double quality,
+                               unsigned long long* __restrict__ keys, int* __restrict__ n_cand, int cap, int H, int W) {
+    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y, b = blockIdx.z;
+    if (x < 1 || x >= W - 1 || y < 1 || y >= H - 1) return;
+    const float* e = eig + (size_t)b * H * W;
+    const float thr = (float)((double)__int_as_float(max_bits[b]) * quality);
+    const float v = e[(size_t)y * W + x];
+    if (!(v > thr)) return;           // THRESH_TOZERO: values <= thr become 0 and are never candidates
+    float mx = v;
+#pragma unroll
+    for (int dy = -1; dy <= 1; ++dy)
+#pragma unroll
+        for (int dx = -1; dx <= 1; ++dx) {
+            const float w = e[(size_t)(y + dy) * W + (x + dx)];
+            mx = fmaxf(mx, w > thr ? w : 0.0f);
+        }
+    if (v != mx) return;
+    const int slot = atomicAdd(n_cand + b, 1);
+    if (slot < cap)
+        keys[(size_t)b * cap + slot] = ((unsigned long long)__float_as_uint(v) << 32) | (unsigned)(y * W + x);
+}
+
+// bitonic sort (descending) of the candidate keys of one image; one CTA per image, data stays in L2
+__global__ void __launch_bounds__(1024) sort_kernel(unsigned long long* __restrict__ keys, const int* __restrict__ n_cand,
+                                                    int cap) {
+    const int b = blockIdx.x;
+    unsigned long long* k = keys + (size_t)b * cap;
+    const int n = min(n_cand[b], cap);
+    int N = 1;
+    while (N < n) N <<= 1;
+    for (int i = n + threadIdx.x; i < N; i += blockDim.x) k[i] = 0ull;   // padding sorts last
+    __syncthreads();
+    for (int size = 2; size <= N; size <<= 1) {
+        for (int stride = size >> 1; stride > 0; stride >>= 1) {
+            for (int i = threadIdx.x; i < N; i += blockDim.x) {
+                const int j = i ^ stride;
+                if (j > i) {
+                    const unsigned long long a = k[i], c = k[j];
+                    const bool desc = (i & size) == 0;
+                    if (desc ? (a < c) : (a > c)) { k[i] = c; k[j] = a; }
+                }
+            }
+            __syncthreads();
+        }
+    }
+}
+
+// Greedy minimum-distance filter of goodFeaturesToTrack, in sorted order, one warp per image.
+// With cell = round(minDistance) and (cell-1)^2 * 2 < minDistance^2 a grid cell can hold one corner at most,
+// (slots = 1); otherwise up to four (corners of a cell of side ~minDistance).  The grid lives in shared memory:
+// one byte per slot = in-cell offset oy*cell+ox, 0xFF = empty (cell <= 15).
+__global__ void __launch_bounds__(256) suppress_kernel(const unsigned long long* __restrict__ keys,
+                                                       const int* __restrict__ n_cand, int cap, int H, int W, int cell,
+                                                       int slots,
+                                                       float min_dist, int max_corners, float2* __restrict__ corners,
+                                                       int* __restrict__ n_corners) {
+    extern __shared__ uint8_t grid[];
+    const int b = blockIdx.x;
+    const int gw = (W + cell - 1) / cell, gh = (H + cell - 1) / cell;
+    for (int i = threadIdx.x; i < gw * gh * slots; i += blockDim.x) grid[i] = 0xFFu;
+    __syncthreads();
+    if (threadIdx.x >= 32) return;
+    const int lane = threadIdx.x;
+    const unsigned long long* k = keys + (size_t)b * cap;
+    const int n = min(n_cand[b], cap);
+    const float md2 = min_dist * min_dist;
+    int kept = 0;
+    for (int base = 0; base < n && kept < max_corners; base += 32) {
+        // prefetch 32 keys, then process them in order
+        const unsigned long long mine = (base + lane < n) ? k[base + lane] : 0ull;
+        const int cnt = min(32, n - base);
+        for (int t = 0; t < cnt && kept < max_corners; ++t) {
+            const unsigned addr = (unsigned)__shfl_sync(0xffffffffu, mine, t);
+            const int y = (int)(addr / (unsigned)W), x = (int)(addr % (unsigned)W);
+            const int xc = x / cell, yc = y / cell;
+            bool bad = false;
+            if (lane < 9) {
+                const int cy = yc - 1 + lane / 3, cx = xc - 1 + lane % 3;
+                if (cy >= 0 && cy < gh && cx >= 0 && cx < gw) {
+                    for (int sl = 0; sl < slots; ++sl) {
+                        const int g = grid[(cy * gw + cx) * slots + sl];
+                        if (g == 0xFF) break;
+                        const float dx = (float)(x - (cx * cell + g % cell)), dy = (float)(y - (cy * cell + g / cell));
+                        bad = bad || (dx * dx + dy * dy < md2);
+                    }
+                }
+            }
+            if (!__any_sync(0xffffffffu, bad)) {
+                if (lane == 0) {
+                    uint8_t* cellp = grid + (yc * gw + xc) * slots;
+                    int sl = 0;
+                    while (sl < slots - 1 && cellp[sl] != 0xFF) ++sl;   // a cell never needs more than `slots`
+                    cellp[sl] = (uint8_t)((y - yc * cell) * cell + (x - xc * cell));
+                    corners[(size_t)b * max_corners + kept] = make_float2((float)x, (float)y);
+                }
+                ++kept;
+                __syncwarp();
+            }
+        }
+    }
+    if (lane == 0) n_corners[b] = kept;
+}
+
+// 7x7 Gaussian blur, sigma 2, fp32 separable, BORDER_REFLECT_101
+__global__ void blur_rows_kernel(const uint8_t* __restrict__ gray, float* __restrict__ tmp, int H, int W) {
+    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y, b = blockIdx.z;
+    if (x >= W) return;
+    const uint8_t* g = gray + (size_t)b * H * W + (size_t)y * W;
+    float s = __fmul_rn(c_gauss7[0], (float)g[reflect101(x - 3, W)]);
+#pragma unroll
+    for (int k = 1; k < 7; ++k) s = __fmaf_rn((float)g[reflect101(x - 3 + k, W)], c_gauss7[k], s);
+    tmp[(size_t)b * H * W + (size_t)y * W + x] = s;
+}
+__global__ void blur_cols_kernel(const float* __restrict__ tmp, uint8_t* __restrict__ blur, int H, int W) {
+    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y, b = blockIdx.z;
+    if (x >= W) return;
+    const float* t = tmp + (size_t)b * H * W + x;
+    float s = __fmul_rn(c_gauss7[3], t[(size_t)y * W]);
+#pragma unroll
+    for (int j = 1; j <= 3; ++j)
+        s = __fmaf_rn(__fadd_rn(t[(size_t)reflect101(y - j, H) * W], t[(size_t)reflect101(y + j, H) * W]), c_gauss7[3 - j], s);
+    const float r = rintf(s);   // saturate_cast<uchar>(float): round half to even, then clamp
+    blur[(size_t)b * H * W + (size_t)y * W + x] = (uint8_t)fminf(fmaxf(r, 0.0f), 255.0f);
+}
+
+// KeyPointsFilter::runByImageBorder(31) in order, then the 256 rBRIEF tests; one CTA per image
+__global__ void __launch_bounds__(256) orb_kernel(const uint8_t* __restrict__ blur, const float2* __restrict__ corners,
+                                                  const int* __restrict__ n_corners, int max_corners, int H, int W,
+                                                  int border, double* __restrict__ kps, uint8_t* __restrict__ des,
+                                                  int* __restrict__ n_kps) {
+    __shared__ int s_scan[256 / 32];
+    __shared__ int s_base;
+    const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int n = min(n_corners[b], max_corners);
+    const float2* c = corners + (size_t)b * max_corners;
+    const uint8_t* img = blur + (size_t)b * H * W;
+    if (tid == 0) s_base = 0;
+    __syncthreads();
+    for (int i0 = 0; i0 < n; i0 += 256) {
+        const int i = i0 + tid;
+        float2 p = make_float2(0.f, 0.f);
+        bool keep = false;
+        if (i < n) {
+            p = c[i];
+            keep = p.x >= (float)border && p.x < (float)(W - border) && p.y >= (float)border && p.y < (float)(H - border);
+        }
+        const unsigned bal = __ballot_sync(0xffffffffu, keep);
+        if (lane == 0) s_scan[warp] = __popc(bal);
+        __syncthreads();
+        int off = s_base;
+        for (int w = 0; w < warp; ++w) off += s_scan[w];
+        const int pos = off + __popc(bal & ((1u << lane) - 1u));
+        if (keep) {
+            kps[((size_t)b * max_corners + pos) * 2] = (double)p.x;
+            kps[((size_t)b * max_corners + pos) * 2 + 1] = (double)p.y;
+            const int cx = __float2int_rn(p.x), cy = __float2int_rn(p.y);
+            const uint8_t* ctr = img + (size_t)cy * W + cx;
+            uint8_t* d = des + ((size_t)b * max_corners + pos) * 32;
+            for (int byte = 0; byte < 32; ++byte) {
+                uint32_t v = 0;
+#pragma unroll
+                for (int bit = 0; bit < 8; ++bit) {
+                    const int q = (byte * 8 + bit) * 4;
+                    const int t0 = ctr[(int)c_orb_pattern[q + 1] * W + (int)c_orb_pattern[q]];
+                    const int t1 = ctr[(int)c_orb_pattern[q + 3] * W + (int)c_orb_pattern[q + 2]];
+                    v |= (uint32_t)(t0 < t1) << bit;
+                }
+                d[byte] = (uint8_t)v;
+            }
+        }
+        __syncthreads();
+        if (tid == 0) {
+            int tot = 0;
+            for (int w = 0; w < 256 / 32; ++w) tot += s_scan[w];
+            s_base += tot;
+        }
+        __syncthreads();
+    }
+    if (tid == 0) n_kps[b] = s_base;
+}
+
+cudaError_t frontend_set_tables(const int8_t* pattern_host, const float* gauss7_host, cudaStream_t stream) {
+    cudaError_t e = cudaMemcpyToSymbolAsync(c_orb_pattern, pattern_host, 1024, 0, cudaMemcpyHostToDevice, stream);
+    if (e != cudaSuccess) return e;
+    return cudaMemcpyToSymbolAsync(c_gauss7, gauss7_host, 7 * sizeof(float), 0, cudaMemcpyHostToDevice, stream);
+}
+
+cudaError_t launch_frontend(const FrontendParams& p, cudaStream_t stream) {
+    const int H = p.H, W = p.W, B = p.batch;
+    const size_t npix = (size_t)B * H * W;
+    gray_kernel<<<(unsigned)((npix + 255) / 256), 256, 0, stream>>>(p.images, p.gray, npix, p.channels);
+    dim3 g((W + 127) / 128, H, B);
+    cov_kernel<<<g, 128, 0, stream>>>(p.gray, p.cov, H, W);
+    cudaMemsetAsync(p.max_bits, 0, (size_t)B * sizeof(int), stream);
+    cudaMemsetAsync(p.n_cand, 0, (size_t)B * sizeof(int), stream);
+    eig_kernel<<<g, 128, 0, stream>>>(p.cov, p.eig, p.max_bits, H, W);
+    collect_kernel<<<g, 128, 0, stream>>>(p.eig, p.max_bits, p.quality, p.keys, p.n_cand, p.cap, H, W);
+    sort_kernel<<<B, 1024, 0, stream>>>(p.keys, p.n_cand, p.cap);
+    const int gw = (W + p.cell - 1) / p.cell, gh = (H + p.cell - 1) / p.cell;
+    const size_t smem = (size_t)gw * gh * p.slots;
+    cudaError_t e = cudaFuncSetAttribute(suppress_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    suppress_kernel<<<B, 256, smem, stream>>>(p.keys, p.n_cand, p.cap, H, W, p.cell, p.slots, p.min_distance, p.max_corners,
+                                              p.corners, p.n_corners);
+    blur_rows_kernel<<<g, 128, 0, stream>>>(p.gray, p.blur_tmp, H, W);
+    blur_cols_kernel<<<g, 128, 0, stream>>>(p.blur_tmp, p.blur, H, W);
+    orb_kernel<<<B, 256, 0, stream>>>(p.blur, p.corners, p.n_corners, p.max_corners, H, W, 31, p.kps, p.des, p.n_kps);
+    return cudaGetLastError();
+}
+
+}  // namespace tvg

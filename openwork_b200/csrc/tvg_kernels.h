@@ -147,6 +147,30 @@ struct MapParams {
 };
 cudaError_t launch_map_accumulate(const MapParams& p, int nseq, cudaStream_t stream);
 
+// ---------------------------------------------------------------- feature front-end (frontend.cu)
+struct FrontendParams {
+    const uint8_t* images;     // [batch][H][W][channels] (BGR when channels == 3)
+    int batch, H, W, channels;
+    int max_corners, cell, slots, cap;
+    double quality;
+    float min_distance;
+    uint8_t* gray;             // [batch][H][W]
+    float* cov;                // [batch][3][H][W]
+    float* eig;                // [batch][H][W]
+    int* max_bits;             // [batch]
+    unsigned long long* keys;  // [batch][cap]
+    int* n_cand;               // [batch]
+    float2* corners;           // [batch][max_corners]
+    int* n_corners;            // [batch]
+    float* blur_tmp;           // [batch][H][W]
+    uint8_t* blur;             // [batch][H][W]
+    double* kps;               // [batch][max_corners][2]
+    uint8_t* des;              // [batch][max_corners][32]
+    int* n_kps;                // [batch]
+};
+cudaError_t frontend_set_tables(const int8_t* pattern_host, const float* gauss7_host, cudaStream_t stream);
+cudaError_t launch_frontend(const FrontendParams& p, cudaStream_t stream);
+
 struct ExtractRtParams {
     const double* E;           // [batch][9]
     double* Rt;                // [batch][16]

@@ -357,6 +357,48 @@ def run_sequences(des, kps, K, words, seq_off=None, residual_threshold=RESIDUAL_
     return res
 
 
+_ORB_PATTERN = None
+
+
+def orb_pattern():
+    """int8[512,2] rBRIEF test points rotated by cv2.KeyPoint's default angle (-1 degree) and rounded, exactly as
+    cv2's computeOrbDescriptors does for keypoints without orientation (ORB.compute never computes one)."""
+    global _ORB_PATTERN
+    if _ORB_PATTERN is None:
+        import os
+        raw = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "orb_pattern.npy")).astype(np.float32)
+        ang = np.float32(-1.0) * np.float32(np.pi / 180.0)
+        a, b = np.float32(np.cos(ang)), np.float32(np.sin(ang))
+        x = raw[:, 0] * a - raw[:, 1] * b
+        y = raw[:, 0] * b + raw[:, 1] * a
+        _ORB_PATTERN = np.ascontiguousarray(np.stack([np.rint(x), np.rint(y)], axis=1).astype(np.int8))
+    return _ORB_PATTERN
+
+
+def extract_points(images, max_corners=3000, quality_level=0.01, min_distance=3, ctx=None):
+    """``extract_points(frame)`` (slam.py:112-122) for a batch of images on the device: BGR2GRAY,
+    goodFeaturesToTrack(max_corners, quality_level, min_distance), ORB.compute at the found corners.
+
+    images u8[B,H,W,3] (BGR) or u8[B,H,W] (gray); a single image may omit B.  Returns (kps f64[B,max,2],
+    des u8[B,max,32], n int32[B]) as CUDA tensors; rows beyond n[b] are unspecified."""
+    dev = _device_of(images)
+    img = _dev(images, torch.uint8, dev)
+    single = img.dim() == 2 or (img.dim() == 3 and img.shape[-1] == 3)
+    if single:
+        img = img.unsqueeze(0)
+    channels = 3 if (img.dim() == 4) else 1
+    B, H, W = img.shape[0], img.shape[1], img.shape[2]
+    ctx = ctx or context(dev.index)
+    kps = torch.empty((B, max_corners, 2), dtype=torch.float64, device=dev)
+    des = torch.empty((B, max_corners, 32), dtype=torch.uint8, device=dev)
+    n = torch.zeros(B, dtype=torch.int32, device=dev)
+    pat = orb_pattern()
+    check(ctx.lib.tvg_extract_points(ctx.handle, _p(img), B, H, W, channels, int(max_corners), float(quality_level),
+                                     float(min_distance), C.c_void_p(pat.ctypes.data), _p(kps), _p(des), _p(n), None,
+                                     _stream()), "tvg_extract_points")
+    return kps, des, n
+
+
 def check_points(points4d):
     """``check_points`` (slam.py:233-237): world z > 0 (elementwise on the device tensor)."""
     return points4d[:, 2] > 0

@@ -61,6 +61,13 @@ class Frame(object):
         cls.last_kps, cls.last_des, cls.last_pose = None, None, None
 
 
+def gpu_extract_points(frame):
+    """slam.py:112-122 on the GPU (GFTT corners + ORB descriptors): returns (kps f64[N,2], des u8[N,32])."""
+    kps, des, n = ops.extract_points(np.ascontiguousarray(frame.image))
+    n = int(n[0])
+    return kps[0, :n].cpu().numpy(), des[0, :n].cpu().numpy()
+
+
 def _np(x):
     return x.detach().cpu().numpy() if isinstance(x, torch.Tensor) else np.asarray(x)
 
@@ -135,6 +142,8 @@ def process_frame(frame_):
     frame = frame_
     if extract_points is not None:
         frame.curr_kps, frame.curr_des = extract_points(frame)
+    elif frame.kps is None and frame.image is not None:
+        frame.curr_kps, frame.curr_des = gpu_extract_points(frame)
     else:
         frame.curr_kps, frame.curr_des = np.asarray(frame.kps), np.asarray(frame.des)
     Frame.last_kps, Frame.last_des = frame.curr_kps, frame.curr_des
