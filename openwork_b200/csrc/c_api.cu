@@ -478,7 +478,7 @@ int tvg_extract_points(tvg_ctx* ctx, const uint8_t* images, int batch, int heigh
     memcpy(gauss, gauss_bits, sizeof(gauss));
     TVG_CUDA(tvg::frontend_set_tables(pattern_host, gauss, st));
     TVG_CUDA(tvg::launch_frontend(p, st));
-    ctx->launches += 10;
+    ctx->launches += 11;
     return 0;
 }
 

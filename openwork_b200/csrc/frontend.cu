@@ -51,10 +51,11 @@ __global__ void cov_kernel(const uint8_t* __restrict__ gray, float* __restrict__
     const uint8_t* g = gray + (size_t)b * H * W;
     const float s = (float)(1.0 / (255.0 * 4 * 3)), s2 = (float)(2.0 / (255.0 * 4 * 3));
     const int xm = reflect101(x - 1, W), xp = reflect101(x + 1, W);
+    const bool inner = y >= 1 && y < H - 1;
     float r[3], q[3];
 #pragma unroll
     for (int k = 0; k < 3; ++k) {
-        const int yy = reflect101(y - 1 + k, H);
+        const int yy = inner ? y - 1 + k : reflect101(y - 1 + k, H);
         const float pm = (float)g[(size_t)yy * W + xm], p0 = (float)g[(size_t)yy * W + x], pp = (float)g[(size_t)yy * W + xp];
         r[k] = __fsub_rn(pp, pm);
         q[k] = __fmaf_rn(s, pp, __fmaf_rn(s2, p0, __fmul_rn(s, pm)));
@@ -67,61 +68,96 @@ __global__ void cov_kernel(const uint8_t* __restrict__ gray, float* __restrict__
     c[(size_t)2 * H * W] = __fmul_rn(dy, dy);
 }
 
-__global__ void eig_kernel(const float* __restrict__ cov, float* __restrict__ eig, int* __restrict__ max_bits, int H,
-                           int W) {
-    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y, b = blockIdx.z;
-    float e = 0.0f;
+// Rolling three-row window: a thread walks EIG_ROWS rows of one pixel column, keeping the horizontal 3-sums
+// (double, 3 planes) of the last three rows in registers -> ~10 loads per pixel instead of 27.
+constexpr int EIG_ROWS = 16;
+
+__global__ void __launch_bounds__(128) eig_kernel(const float* __restrict__ cov, float* __restrict__ eig,
+                                                  int* __restrict__ max_bits, int H, int W) {
+    const int x = blockIdx.x * blockDim.x + threadIdx.x, y0 = blockIdx.y * EIG_ROWS, b = blockIdx.z;
+    float m = 0.0f;
     if (x < W) {
         const float* c = cov + (size_t)b * 3 * H * W;
-        double sum[3] = {0.0, 0.0, 0.0};
+        const int xm = reflect101(x - 1, W), xp = reflect101(x + 1, W);
+        double h[3][3];   // h[row slot][plane]
+        auto hsum = [&](int yy, double (&o)[3]) {
+            const int r = reflect101(yy, H);
 #pragma unroll
-        for (int dy = -1; dy <= 1; ++dy) {
-            const int yy = reflect101(y + dy, H);
-#pragma unroll
-            for (int dx = -1; dx <= 1; ++dx) {
-                const int xx = reflect101(x + dx, W);
-#pragma unroll
-                for (int k = 0; k < 3; ++k) sum[k] += (double)c[(size_t)k * H * W + (size_t)yy * W + xx];
+            for (int k = 0; k < 3; ++k) {
+                const float* row = c + (size_t)k * H * W + (size_t)r * W;
+                // same association as the direct 9-sum: left to right within a row
+                o[k] = ((double)row[xm] + (double)row[x]) + (double)row[xp];
             }
+        };
+        hsum(y0 - 1, h[0]);
+        hsum(y0, h[1]);
+        const int y1 = min(H, y0 + EIG_ROWS);
+        for (int y = y0; y < y1; ++y) {
+            hsum(y + 1, h[2]);
+            const float a = __fmul_rn((float)((h[0][0] + h[1][0]) + h[2][0]), 0.5f);
+            const float bb = (float)((h[0][1] + h[1][1]) + h[2][1]);
+            const float cc = __fmul_rn((float)((h[0][2] + h[1][2]) + h[2][2]), 0.5f);
+            const float d = __fsub_rn(a, cc);
+            const float e = __fsub_rn(__fadd_rn(a, cc), __fsqrt_rn(__fadd_rn(__fmul_rn(d, d), __fmul_rn(bb, bb))));
+            eig[(size_t)b * H * W + (size_t)y * W + x] = e;
+            m = fmaxf(m, e);
+#pragma unroll
+            for (int k = 0; k < 3; ++k) { h[0][k] = h[1][k]; h[1][k] = h[2][k]; }
         }
-        const float a = __fmul_rn((float)sum[0], 0.5f), bb = (float)sum[1], cc = __fmul_rn((float)sum[2], 0.5f);
-        const float d = __fsub_rn(a, cc);
-        e = __fsub_rn(__fadd_rn(a, cc), __fsqrt_rn(__fadd_rn(__fmul_rn(d, d), __fmul_rn(bb, bb))));
-        eig[(size_t)b * H * W + (size_t)y * W + x] = e;
     }
     // image maximum (cv::minMaxLoc): positive floats order like their bit patterns
-    float m = e > 0.0f ? e : 0.0f;
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
     if ((threadIdx.x & 31) == 0 && m > 0.0f) atomicMax(max_bits + b, __float_as_int(m));
 }
 
 // threshold + 3x3 non-maximum suppression; candidates are appended as sortable 64-bit keys
-__global__ void collect_kernel(const float* __restrict__ eig, const int* __restrict__ max_bits, double quality,
-                               unsigned long long* __restrict__ keys, int* __restrict__ n_cand, int cap, int H, int W) {
-    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y, b = blockIdx.z;
-    if (x < 1 || x >= W - 1 || y < 1 || y >= H - 1) return;
+__global__ void __launch_bounds__(128) collect_kernel(const float* __restrict__ eig, const int* __restrict__ max_bits,
+                                                      double quality, unsigned long long* __restrict__ keys,
+                                                      int* __restrict__ n_cand, int cap, int H, int W) {
+    const int x = blockIdx.x * blockDim.x + threadIdx.x, y0 = blockIdx.y * EIG_ROWS, b = blockIdx.z;
+    if (x < 1 || x >= W - 1) return;
     const float* e = eig + (size_t)b * H * W;
     const float thr = (float)((double)__int_as_float(max_bits[b]) * quality);
-    const float v = e[(size_t)y * W + x];
-    if (!(v > thr)) return;           // THRESH_TOZERO: values <= thr become 0 and are never candidates
-    float mx = v;
-#pragma unroll
-    for (int dy = -1; dy <= 1; ++dy)
-#pragma unroll
-        for (int dx = -1; dx <= 1; ++dx) {
-            const float w = e[(size_t)(y + dy) * W + (x + dx)];
-            mx = fmaxf(mx, w > thr ? w : 0.0f);
+    // rolling window over rows: horizontal maxima of the thresholded map (THRESH_TOZERO) and the centre values
+    auto hmax = [&](int yy, float& centre) -> float {
+        if (yy < 0 || yy >= H) { centre = 0.0f; return 0.0f; }
+        const float* row = e + (size_t)yy * W;
+        const float l = row[x - 1], c = row[x], r = row[x + 1];
+        centre = c > thr ? c : 0.0f;
+        return fmaxf(fmaxf(l > thr ? l : 0.0f, centre), r > thr ? r : 0.0f);
+    };
+    float c0, c1, c2;
+    float m0 = hmax(y0 - 1, c0), m1 = hmax(y0, c1);
+    const int y1 = min(H - 1, y0 + EIG_ROWS);
+    for (int y = y0; y < y1; ++y) {
+        const float m2 = hmax(y + 1, c2);
+        if (y >= 1 && c1 != 0.0f && c1 == fmaxf(fmaxf(m0, m1), m2)) {
+            const int slot = atomicAdd(n_cand + b, 1);
+            if (slot < cap)
+                keys[(size_t)b * cap + slot] = ((unsigned long long)__float_as_uint(c1) << 32) | (unsigned)(y * W + x);
         }
-    if (v != mx) return;
-    const int slot = atomicAdd(n_cand + b, 1);
-    if (slot < cap)
-        keys[(size_t)b * cap + slot] = ((unsigned long long)__float_as_uint(v) << 32) | (unsigned)(y * W + x);
+        m0 = m1; m1 = m2; c0 = c1; c1 = c2;
+    }
 }
 
-// bitonic sort (descending) of the candidate keys of one image; one CTA per image, data stays in L2
+// Bitonic sort (descending) of the candidate keys of one image, one CTA per image.  Compare-exchange steps whose
+// stride is below SORT_CHUNK stay inside aligned SORT_CHUNK-key blocks, so they run in shared memory (64 KB);
+// only the few steps with larger strides touch global memory (L2 resident).
+constexpr int SORT_CHUNK = 8192;
+
+__device__ __forceinline__ void cmpx(unsigned long long* k, int i, int stride, int size) {
+    const int j = i ^ stride;
+    if (j > i) {
+        const unsigned long long a = k[i], c = k[j];
+        const bool desc = (i & size) == 0;
+        if (desc ? (a < c) : (a > c)) { k[i] = c; k[j] = a; }
+    }
+}
+
 __global__ void __launch_bounds__(1024) sort_kernel(unsigned long long* __restrict__ keys, const int* __restrict__ n_cand,
                                                     int cap) {
+    extern __shared__ unsigned long long skeys[];
     const int b = blockIdx.x;
     unsigned long long* k = keys + (size_t)b * cap;
     const int n = min(n_cand[b], cap);
@@ -129,16 +165,47 @@ __global__ void __launch_bounds__(1024) sort_kernel(unsigned long long* __restri
     while (N < n) N <<= 1;
     for (int i = n + threadIdx.x; i < N; i += blockDim.x) k[i] = 0ull;   // padding sorts last
     __syncthreads();
-    for (int size = 2; size <= N; size <<= 1) {
-        for (int stride = size >> 1; stride > 0; stride >>= 1) {
-            for (int i = threadIdx.x; i < N; i += blockDim.x) {
-                const int j = i ^ stride;
-                if (j > i) {
-                    const unsigned long long a = k[i], c = k[j];
-                    const bool desc = (i & size) == 0;
-                    if (desc ? (a < c) : (a > c)) { k[i] = c; k[j] = a; }
+    const int chunk = min(N, SORT_CHUNK);
+    // phase 1: every chunk fully sorted in shared memory (all sizes <= chunk), directions as in the full network
+    for (int c0 = 0; c0 < N; c0 += chunk) {
+        for (int i = threadIdx.x; i < chunk; i += blockDim.x) skeys[i] = k[c0 + i];
+        __syncthreads();
+        for (int size = 2; size <= chunk; size <<= 1)
+            for (int stride = size >> 1; stride > 0; stride >>= 1) {
+                for (int i = threadIdx.x; i < chunk; i += blockDim.x) {
+                    const int j = i ^ stride;
+                    if (j > i) {
+                        const unsigned long long a = skeys[i], c = skeys[j];
+                        const bool desc = ((c0 + i) & size) == 0;
+                        if (desc ? (a < c) : (a > c)) { skeys[i] = c; skeys[j] = a; }
+                    }
                 }
+                __syncthreads();
             }
+        for (int i = threadIdx.x; i < chunk; i += blockDim.x) k[c0 + i] = skeys[i];
+        __syncthreads();
+    }
+    // phase 2: remaining merge stages; strides >= chunk in global memory, the rest per chunk in shared memory
+    for (int size = chunk << 1; size <= N; size <<= 1) {
+        for (int stride = size >> 1; stride >= chunk; stride >>= 1) {
+            for (int i = threadIdx.x; i < N; i += blockDim.x) cmpx(k, i, stride, size);
+            __syncthreads();
+        }
+        for (int c0 = 0; c0 < N; c0 += chunk) {
+            for (int i = threadIdx.x; i < chunk; i += blockDim.x) skeys[i] = k[c0 + i];
+            __syncthreads();
+            for (int stride = chunk >> 1; stride > 0; stride >>= 1) {
+                for (int i = threadIdx.x; i < chunk; i += blockDim.x) {
+                    const int j = i ^ stride;
+                    if (j > i) {
+                        const unsigned long long a = skeys[i], c = skeys[j];
+                        const bool desc = ((c0 + i) & size) == 0;
+                        if (desc ? (a < c) : (a > c)) { skeys[i] = c; skeys[j] = a; }
+                    }
+                }
+                __syncthreads();
+            }
+            for (int i = threadIdx.x; i < chunk; i += blockDim.x) k[c0 + i] = skeys[i];
             __syncthreads();
         }
     }
@@ -165,37 +232,40 @@ __global__ void __launch_bounds__(256) suppress_kernel(const unsigned long long*
     const float md2 = min_dist * min_dist;
     int kept = 0;
     for (int base = 0; base < n && kept < max_corners; base += 32) {
-        // prefetch 32 keys, then process them in order
-        const unsigned long long mine = (base + lane < n) ? k[base + lane] : 0ull;
-        const int cnt = min(32, n - base);
-        for (int t = 0; t < cnt && kept < max_corners; ++t) {
-            const unsigned addr = (unsigned)__shfl_sync(0xffffffffu, mine, t);
-            const int y = (int)(addr / (unsigned)W), x = (int)(addr % (unsigned)W);
-            const int xc = x / cell, yc = y / cell;
-            bool bad = false;
-            if (lane < 9) {
-                const int cy = yc - 1 + lane / 3, cx = xc - 1 + lane % 3;
-                if (cy >= 0 && cy < gh && cx >= 0 && cx < gw) {
+        // Each lane tests one candidate against the corners accepted so far (grid); the 32 candidates are then
+        // resolved against each other strictly in sorted order, which is what the sequential reference does.
+        const bool valid = base + lane < n;
+        const unsigned addr = valid ? (unsigned)k[base + lane] : 0u;
+        const int y = (int)(addr / (unsigned)W), x = (int)(addr % (unsigned)W);
+        const int xc = x / cell, yc = y / cell;
+        bool bad = !valid;
+        if (valid) {
+            for (int cy = max(0, yc - 1); cy <= min(gh - 1, yc + 1); ++cy)
+                for (int cx = max(0, xc - 1); cx <= min(gw - 1, xc + 1); ++cx)
                     for (int sl = 0; sl < slots; ++sl) {
                         const int g = grid[(cy * gw + cx) * slots + sl];
                         if (g == 0xFF) break;
                         const float dx = (float)(x - (cx * cell + g % cell)), dy = (float)(y - (cy * cell + g / cell));
                         bad = bad || (dx * dx + dy * dy < md2);
                     }
-                }
-            }
-            if (!__any_sync(0xffffffffu, bad)) {
-                if (lane == 0) {
-                    uint8_t* cellp = grid + (yc * gw + xc) * slots;
-                    int sl = 0;
-                    while (sl < slots - 1 && cellp[sl] != 0xFF) ++sl;   // a cell never needs more than `slots`
-                    cellp[sl] = (uint8_t)((y - yc * cell) * cell + (x - xc * cell));
-                    corners[(size_t)b * max_corners + kept] = make_float2((float)x, (float)y);
-                }
-                ++kept;
-                __syncwarp();
-            }
         }
+        unsigned open = __ballot_sync(0xffffffffu, !bad);
+        while (open && kept < max_corners) {
+            const int t = __ffs(open) - 1;                      // earliest candidate still alive: accepted
+            const int xt = __shfl_sync(0xffffffffu, x, t), yt = __shfl_sync(0xffffffffu, y, t);
+            if (lane == t) {
+                uint8_t* cellp = grid + (yc * gw + xc) * slots;
+                int sl = 0;
+                while (sl < slots - 1 && cellp[sl] != 0xFF) ++sl;   // a cell never needs more than `slots`
+                cellp[sl] = (uint8_t)((y - yc * cell) * cell + (x - xc * cell));
+                corners[(size_t)b * max_corners + kept] = make_float2((float)x, (float)y);
+            }
+            ++kept;
+            const float dx = (float)(x - xt), dy = (float)(y - yt);
+            const bool dead = lane <= t || (dx * dx + dy * dy < md2);
+            open &= ~__ballot_sync(0xffffffffu, dead);
+        }
+        __syncwarp();
     }
     if (lane == 0) n_corners[b] = kept;
 }
@@ -222,17 +292,16 @@ __global__ void blur_cols_kernel(const float* __restrict__ tmp, uint8_t* __restr
     blur[(size_t)b * H * W + (size_t)y * W + x] = (uint8_t)fminf(fmaxf(r, 0.0f), 255.0f);
 }
 
-// KeyPointsFilter::runByImageBorder(31) in order, then the 256 rBRIEF tests; one CTA per image
-__global__ void __launch_bounds__(256) orb_kernel(const uint8_t* __restrict__ blur, const float2* __restrict__ corners,
-                                                  const int* __restrict__ n_corners, int max_corners, int H, int W,
-                                                  int border, double* __restrict__ kps, uint8_t* __restrict__ des,
-                                                  int* __restrict__ n_kps) {
+// KeyPointsFilter::runByImageBorder(31), order preserving; one CTA per image
+__global__ void __launch_bounds__(256) border_filter_kernel(const float2* __restrict__ corners,
+                                                            const int* __restrict__ n_corners, int max_corners, int H,
+                                                            int W, int border, double* __restrict__ kps,
+                                                            int* __restrict__ n_kps) {
     __shared__ int s_scan[256 / 32];
     __shared__ int s_base;
     const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int n = min(n_corners[b], max_corners);
     const float2* c = corners + (size_t)b * max_corners;
-    const uint8_t* img = blur + (size_t)b * H * W;
     if (tid == 0) s_base = 0;
     __syncthreads();
     for (int i0 = 0; i0 < n; i0 += 256) {
@@ -252,20 +321,6 @@ __global__ void __launch_bounds__(256) orb_kernel(const uint8_t* __restrict__ bl
         if (keep) {
             kps[((size_t)b * max_corners + pos) * 2] = (double)p.x;
             kps[((size_t)b * max_corners + pos) * 2 + 1] = (double)p.y;
-            const int cx = __float2int_rn(p.x), cy = __float2int_rn(p.y);
-            const uint8_t* ctr = img + (size_t)cy * W + cx;
-            uint8_t* d = des + ((size_t)b * max_corners + pos) * 32;
-            for (int byte = 0; byte < 32; ++byte) {
-                uint32_t v = 0;
-#pragma unroll
-                for (int bit = 0; bit < 8; ++bit) {
-                    const int q = (byte * 8 + bit) * 4;
-                    const int t0 = ctr[(int)c_orb_pattern[q + 1] * W + (int)c_orb_pattern[q]];
-                    const int t1 = ctr[(int)c_orb_pattern[q + 3] * W + (int)c_orb_pattern[q + 2]];
-                    v |= (uint32_t)(t0 < t1) << bit;
-                }
-                d[byte] = (uint8_t)v;
-            }
         }
         __syncthreads();
         if (tid == 0) {
@@ -276,6 +331,35 @@ __global__ void __launch_bounds__(256) orb_kernel(const uint8_t* __restrict__ bl
         __syncthreads();
     }
     if (tid == 0) n_kps[b] = s_base;
+}
+
+// the 256 rBRIEF tests: one thread per keypoint, so that every lane reads the same pattern entry at the same
+// time (constant memory broadcasts uniform addresses and serialises divergent ones)
+__global__ void __launch_bounds__(128) orb_desc_kernel(const uint8_t* __restrict__ blur, const double* __restrict__ kps,
+                                                       const int* __restrict__ n_kps, int max_corners, int H, int W,
+                                                       uint8_t* __restrict__ des) {
+    const int b = blockIdx.y;
+    const int kp = blockIdx.x * 128 + threadIdx.x;
+    if (kp >= n_kps[b]) return;
+    const size_t o = (size_t)b * max_corners + kp;
+    const int cx = __double2int_rn(kps[o * 2]), cy = __double2int_rn(kps[o * 2 + 1]);
+    const uint8_t* ctr = blur + (size_t)b * H * W + (size_t)cy * W + cx;
+    uint32_t w[8];
+#pragma unroll
+    for (int word = 0; word < 8; ++word) {
+        uint32_t v = 0;
+#pragma unroll
+        for (int bit = 0; bit < 32; ++bit) {
+            const int q = (word * 32 + bit) * 4;
+            const int t0 = ctr[(int)c_orb_pattern[q + 1] * W + (int)c_orb_pattern[q]];
+            const int t1 = ctr[(int)c_orb_pattern[q + 3] * W + (int)c_orb_pattern[q + 2]];
+            v |= (uint32_t)(t0 < t1) << bit;
+        }
+        w[word] = v;
+    }
+    uint4* d = reinterpret_cast<uint4*>(des + o * 32);
+    d[0] = make_uint4(w[0], w[1], w[2], w[3]);
+    d[1] = make_uint4(w[4], w[5], w[6], w[7]);
 }
 
 cudaError_t frontend_set_tables(const int8_t* pattern_host, const float* gauss7_host, cudaStream_t stream) {
@@ -292,18 +376,24 @@ cudaError_t launch_frontend(const FrontendParams& p, cudaStream_t stream) {
     cov_kernel<<<g, 128, 0, stream>>>(p.gray, p.cov, H, W);
     cudaMemsetAsync(p.max_bits, 0, (size_t)B * sizeof(int), stream);
     cudaMemsetAsync(p.n_cand, 0, (size_t)B * sizeof(int), stream);
-    eig_kernel<<<g, 128, 0, stream>>>(p.cov, p.eig, p.max_bits, H, W);
-    collect_kernel<<<g, 128, 0, stream>>>(p.eig, p.max_bits, p.quality, p.keys, p.n_cand, p.cap, H, W);
-    sort_kernel<<<B, 1024, 0, stream>>>(p.keys, p.n_cand, p.cap);
+    dim3 gr((W + 127) / 128, (H + EIG_ROWS - 1) / EIG_ROWS, B);
+    eig_kernel<<<gr, 128, 0, stream>>>(p.cov, p.eig, p.max_bits, H, W);
+    collect_kernel<<<gr, 128, 0, stream>>>(p.eig, p.max_bits, p.quality, p.keys, p.n_cand, p.cap, H, W);
+    cudaError_t e = cudaFuncSetAttribute(sort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         SORT_CHUNK * (int)sizeof(unsigned long long));
+    if (e != cudaSuccess) return e;
+    sort_kernel<<<B, 1024, SORT_CHUNK * sizeof(unsigned long long), stream>>>(p.keys, p.n_cand, p.cap);
     const int gw = (W + p.cell - 1) / p.cell, gh = (H + p.cell - 1) / p.cell;
     const size_t smem = (size_t)gw * gh * p.slots;
-    cudaError_t e = cudaFuncSetAttribute(suppress_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    e = cudaFuncSetAttribute(suppress_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     suppress_kernel<<<B, 256, smem, stream>>>(p.keys, p.n_cand, p.cap, H, W, p.cell, p.slots, p.min_distance, p.max_corners,
                                               p.corners, p.n_corners);
     blur_rows_kernel<<<g, 128, 0, stream>>>(p.gray, p.blur_tmp, H, W);
     blur_cols_kernel<<<g, 128, 0, stream>>>(p.blur_tmp, p.blur, H, W);
-    orb_kernel<<<B, 256, 0, stream>>>(p.blur, p.corners, p.n_corners, p.max_corners, H, W, 31, p.kps, p.des, p.n_kps);
+    border_filter_kernel<<<B, 256, 0, stream>>>(p.corners, p.n_corners, p.max_corners, H, W, 31, p.kps, p.n_kps);
+    orb_desc_kernel<<<dim3((p.max_corners + 127) / 128, B), 128, 0, stream>>>(p.blur, p.kps, p.n_kps, p.max_corners, H, W,
+                                                                      p.des);
     return cudaGetLastError();
 }
 
