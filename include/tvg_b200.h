@@ -134,6 +134,9 @@ TVG_API int tvg_extract_rt(tvg_ctx* ctx, const double* E, int batch, double* Rt,
 TVG_API int tvg_pose_chain(tvg_ctx* ctx, const double* Rt, const int32_t* seq_off, int nseq,
                    const double* init_pose, double* poses, double* pair_pinv, void* stream);
 
+/* np.linalg.inv(pose) (slam.py:204-205) for n row-major 4x4 matrices (pivoted Gauss-Jordan, fp64). */
+TVG_API int tvg_invert_poses(tvg_ctx* ctx, const double* poses, int n, double* poses_inv, void* stream);
+
 /* triangulate(pts1, pts2, pose1, pose2) (slam.py:202-221) + check_points (slam.py:233-237).
  * pix1 / pix2 f64[batch][n_max][2] pixels; P1 / P2 = inv(pose1) / inv(pose2), one 4x4 per pair at
  * strides p1_stride / p2_stride doubles; n_pts int32[batch] (NULL -> n); kinv_host = inv(K).

@@ -61,6 +61,7 @@ SIGNATURES = {
     "tvg_ransac_essential": (C.c_int, [c_vp, C.POINTER(RansacIO), c_vp]),
     "tvg_extract_rt": (C.c_int, [c_vp, c_vp, C.c_int, c_vp, c_vp]),
     "tvg_pose_chain": (C.c_int, [c_vp, c_vp, c_vp, C.c_int, c_vp, c_vp, c_vp, c_vp]),
+    "tvg_invert_poses": (C.c_int, [c_vp, c_vp, C.c_int, c_vp, c_vp]),
     "tvg_triangulate": (C.c_int, [c_vp, c_vp, c_vp, C.c_int, C.c_int, C.c_int, c_vp, c_vp, C.c_longlong, c_vp,
                                   C.c_longlong, c_f64p, c_vp, c_vp, c_vp]),
     "tvg_point_quality": (C.c_int, [c_vp, c_vp, c_vp, C.c_int, C.c_int, C.c_int, c_vp, c_vp, C.c_longlong, c_vp,

@@ -377,6 +377,17 @@ int tvg_pose_chain(tvg_ctx* ctx, const double* Rt, const int32_t* seq_off, int n
     return 0;
 }
 
+int tvg_invert_poses(tvg_ctx* ctx, const double* poses, int n, double* poses_inv, void* stream) {
+    if (!ctx) return fail(-1, "ctx is NULL");
+    if (n < 0) return fail(-2, "tvg_invert_poses: bad n");
+    if (n == 0) return 0;
+    if (!poses || !poses_inv) return fail(-3, "tvg_invert_poses: NULL array");
+    DeviceGuard g(ctx->device);
+    TVG_CUDA(tvg::launch_invert4(poses, poses_inv, n, (cudaStream_t)stream));
+    ctx->launches += 1;
+    return 0;
+}
+
 int tvg_triangulate(tvg_ctx* ctx, const double* pix1, const double* pix2, int batch, int n_max, int n,
                     const int32_t* n_pts, const double* P1, long long p1_stride, const double* P2,
                     long long p2_stride, const double* kinv_host, double* points4d, uint8_t* good,

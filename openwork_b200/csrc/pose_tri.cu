@@ -60,6 +60,17 @@ cudaError_t launch_pose_chain(const PoseChainParams& p, int nseq, cudaStream_t s
     return cudaGetLastError();
 }
 
+// np.linalg.inv(pose) for a list of 4x4 matrices (slam.py:204-205), one thread each
+__global__ void invert4_kernel(const double* __restrict__ in, double* __restrict__ out, int n) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) inverse4(in + (size_t)i * 16, out + (size_t)i * 16);
+}
+
+cudaError_t launch_invert4(const double* in, double* out, int n, cudaStream_t stream) {
+    invert4_kernel<<<(n + 31) / 32, 32, 0, stream>>>(in, out, n);
+    return cudaGetLastError();
+}
+
 constexpr int TRI_THREADS = 128;
 
 __device__ __forceinline__ void dlt_point(const double* __restrict__ P1, const double* __restrict__ P2,

@@ -132,6 +132,7 @@ struct TriParams {
     double focal;              // pixels per normalised unit for `reproj` (K[0][0])
 };
 cudaError_t launch_triangulate(const TriParams& p, int batch, cudaStream_t stream);
+cudaError_t launch_invert4(const double* in, double* out, int n, cudaStream_t stream);
 
 struct MapParams {
     const double* points4d;    // [batch][n_max][4]

@@ -245,19 +245,26 @@ def pose_chain(Rt, seq_off=None, init_pose=None, ctx=None):
     return poses.view(-1, 4, 4), pinv.view(B, 2, 4, 4)
 
 
+def _invert_poses(poses, dev, ctx):
+    """np.linalg.inv of a stack of 4x4 poses, on the device (tvg_invert_poses)."""
+    P = _dev(np.ascontiguousarray(poses, dtype=np.float64), torch.float64, dev).reshape(-1, 16).contiguous()
+    out = torch.empty_like(P)
+    check(ctx.lib.tvg_invert_poses(ctx.handle, _p(P), P.shape[0], _p(out), _stream()), "tvg_invert_poses")
+    return out
+
+
 def triangulate(pts1, pts2, pose1, pose2, K, return_good=False, ctx=None):
     """``triangulate(pts1, pts2, pose1, pose2)`` (slam.py:202-221) with K explicit.
 
-    pts f64[M,2] pixels, pose f64[4,4] (camera -> world; inverted here like slam.py:204-205 -- on the
-    host with numpy for this single-pair form).  Returns points4d f64[M,4] (and z>0 flags)."""
+    pts f64[M,2] pixels, pose f64[4,4] (camera -> world; inverted on the device like slam.py:204-205).
+    Returns points4d f64[M,4] (and z>0 flags)."""
     dev = _device_of(pts1, pts2)
     p1 = _dev(pts1, torch.float64, dev)
     p2 = _dev(pts2, torch.float64, dev)
     M = p1.shape[0]
     ctx = ctx or context(dev.index)
-    P = np.stack([np.linalg.inv(np.asarray(_np(pose1), dtype=np.float64)),
-                  np.linalg.inv(np.asarray(_np(pose2), dtype=np.float64))])
-    Pd = _dev(P, torch.float64, dev)
+    Pd = _invert_poses(np.stack([np.asarray(_np(pose1), dtype=np.float64), np.asarray(_np(pose2), dtype=np.float64)]),
+                       dev, ctx)
     kinv, kinv_p = _kinv(K)
     X = torch.empty((max(M, 1), 4), dtype=torch.float64, device=dev)
     good = torch.zeros(max(M, 1), dtype=torch.uint8, device=dev)
@@ -296,9 +303,8 @@ def point_quality(pts1, pts2, pose1, pose2, K, ctx=None):
     p2 = _dev(pts2, torch.float64, dev)
     M = p1.shape[0]
     ctx = ctx or context(dev.index)
-    P = np.stack([np.linalg.inv(np.asarray(_np(pose1), dtype=np.float64)),
-                  np.linalg.inv(np.asarray(_np(pose2), dtype=np.float64))])
-    Pd = _dev(P, torch.float64, dev)
+    Pd = _invert_poses(np.stack([np.asarray(_np(pose1), dtype=np.float64), np.asarray(_np(pose2), dtype=np.float64)]),
+                       dev, ctx)
     kinv, kinv_p = _kinv(K)
     X = torch.empty((max(M, 1), 4), dtype=torch.float64, device=dev)
     rep = torch.empty(max(M, 1), dtype=torch.float64, device=dev)
@@ -397,6 +403,28 @@ def extract_points(images, max_corners=3000, quality_level=0.01, min_distance=3,
                                      float(min_distance), C.c_void_p(pat.ctypes.data), _p(kps), _p(des), _p(n), None,
                                      _stream()), "tvg_extract_points")
     return kps, des, n
+
+
+def run_sequences_from_images(images, K, words, seq_off=None, max_corners=3000, quality_level=0.01, min_distance=3,
+                              residual_threshold=RESIDUAL_THRESHOLD, ratio=RATIO, ctx=None):
+    """The reference's whole per-frame loop (slam.py:239-272 for every frame of every sequence) on the device,
+    from raw images: extract_points -> match -> RANSAC -> extract_Rt -> pose chain -> triangulate -> z>0 -> map.
+    images u8[F,H,W,3]; frames of sequence s consecutive.  Returns [(poses, points)] like :func:`run_sequences`,
+    plus the per-frame keypoint counts."""
+    kps, des, n = extract_points(images, max_corners, quality_level, min_distance, ctx=ctx)
+    F = kps.shape[0]
+    out = process_pairs_device(des, kps, K, words=words, frame_count=n, seq_off=seq_off, ratio=ratio,
+                               residual_threshold=residual_threshold,
+                               outputs=("n_inl", "poses", "points4d", "good", "status"), ctx=ctx)
+    B = out["n_inl"].shape[0]
+    so = np.array([0, B], dtype=np.int32) if seq_off is None else np.asarray(_np(seq_off), dtype=np.int32)
+    mp, cnt, _ = map_accumulate(out["points4d"], out["good"], out["n_inl"], so, ctx=ctx)
+    cnt = cnt.cpu().numpy()
+    res = []
+    for s in range(len(so) - 1):
+        p0 = so[s] + s
+        res.append((out["poses"][p0:p0 + (so[s + 1] - so[s]) + 1], mp[s, :cnt[s]]))
+    return res, n, out["status"]
 
 
 def check_points(points4d):

@@ -93,3 +93,36 @@ def test_process_frame_from_images():
     assert np.array_equal(slam.Frame.last_kps, k1) and np.array_equal(slam.Frame.last_des, d1)
     assert f1.curr_pose.shape == (4, 4) and np.isfinite(f1.curr_pose).all()
     assert len(f1.curr_kps) >= 8 and f1.points4d.shape[1] == 4
+
+
+@pytest.mark.gpu
+def test_run_sequences_from_images_matches_cv2_plus_oracle():
+    """Raw images -> poses + map points entirely on the device == cv2 front-end + CPU oracle pair pipeline."""
+    import cv2
+    import torch
+    from openwork_b200 import ops, synth
+    from oracle import two_view as tv
+    K = synth.K_640x480
+    img0 = fe.synthetic_image(31)
+    frames_img = [img0]
+    for i in range(1, 4):
+        M = np.float32([[1.0 + 0.008 * i, 0.002 * i, 2.5 * i], [-0.002 * i, 1.0 + 0.008 * i, -1.5 * i]])
+        frames_img.append(cv2.warpAffine(img0, M, (640, 480), flags=cv2.INTER_LINEAR, borderMode=cv2.BORDER_REFLECT_101))
+    imgs = np.stack(frames_img)
+    words = synth.sample_words(200, 12)
+    res, n, status = ops.run_sequences_from_images(torch.from_numpy(imgs).cuda(), K, words)
+    assert (status.cpu().numpy() == 0).all()
+    feats = [fe.extract_points_cv2(im) for im in frames_img]
+    assert n.cpu().numpy().tolist() == [len(f[0]) for f in feats]
+    pose = np.eye(4)
+    Xs, gs, poses_ref = [], [], [pose]
+    for i in range(3):
+        (lk, ld), (ck, cd) = feats[i], feats[i + 1]
+        r = tv.process_pair(lk, ld, ck, cd, pose, K, words=words)
+        Xs.append(r["points4d"]); gs.append(r["good"]); pose = r["curr_pose"]; poses_ref.append(pose)
+    poses, pts = res[0][0].cpu().numpy(), res[0][1].cpu().numpy()
+    np.testing.assert_allclose(poses, np.stack(poses_ref), atol=1e-5)
+    ref_pts = tv.map_points(Xs, gs)
+    assert pts.shape == ref_pts.shape
+    rel = np.linalg.norm(pts[1:, :3] - ref_pts[1:, :3], axis=1) / np.maximum(np.linalg.norm(ref_pts[1:, :3], axis=1), 1e-12)
+    assert np.median(rel) < 1e-4 and (rel < 1e-3).mean() > 0.98
