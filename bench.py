@@ -242,6 +242,29 @@ def single_pair_latency(ops, ctx, K, n, H, dev, reps=30):
             "matcher_gcmp_s": n * n / knn_us / 1e3}
 
 
+def frontend_rate(ops, ctx, dev, frames=256):
+    """Not part of the metric (the north star feeds synthetic keypoints): frames/s of the GPU feature front-end
+    (BGR2GRAY + goodFeaturesToTrack + ORB.compute, bit-exact vs cv2) on procedurally textured 640x480 images."""
+    import torch
+    g = torch.Generator(device="cpu").manual_seed(7)
+    low = torch.randint(0, 256, (8, 3, 60, 80), generator=g, dtype=torch.uint8).float()
+    img = torch.nn.functional.interpolate(low, size=(480, 640), mode="bicubic", align_corners=False)
+    img = (img + 12.0 * torch.randn(img.shape, generator=g)).clamp(0, 255).to(torch.uint8)
+    img = img.permute(0, 2, 3, 1).contiguous().repeat(frames // 8, 1, 1, 1).to(dev)
+    for _ in range(2):
+        kps, des, n = ops.extract_points(img, ctx=ctx)
+    torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(3):
+        kps, des, n = ops.extract_points(img, ctx=ctx)
+    b.record()
+    b.synchronize()
+    ms = a.elapsed_time(b) / 3
+    return {"frames_per_call": frames, "image": "640x480 BGR", "frames_per_s": frames / ms * 1e3,
+            "keypoints_per_frame": float(n.float().mean().item())}
+
+
 # ----------------------------------------------------------------------------------------- our arm
 def run_ours(args):
     import torch
@@ -387,6 +410,10 @@ def run_ours(args):
     if rank == 0 and not args.no_single_pair:
         single = {"C2": single_pair_latency(ops, ctx, K, 2048, 1024, dev), "C3": single_pair_latency(ops, ctx, K, 8192, 4096, dev)}
 
+    frontend = None
+    if rank == 0 and not args.no_frontend:
+        frontend = frontend_rate(ops, ctx, dev)
+
     t = torch.tensor([ms, knn_ms, e2e_s], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -463,6 +490,7 @@ def run_ours(args):
         "e2e": {"value": e2e_value, "unit": "pairs/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                 "steps": e2e_steps, "mode": "tvg_pairs_host_submit/_wait, 2 contexts alternating"},
         "roofline": roofline, "kernels": kernels, "cpu_baseline": cpu, "single_pair": single,
+        "frontend_outside_metric": frontend,
     }
     print(json.dumps(line))
     if world > 1:
@@ -484,6 +512,7 @@ def main():
                     help="pairs per chunk of the e2e host pipeline (streaming mode overlaps across batches, so large)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-single-pair", action="store_true")
+    ap.add_argument("--no-frontend", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
