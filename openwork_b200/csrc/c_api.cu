@@ -479,7 +479,6 @@ int tvg_extract_points(tvg_ctx* ctx, const uint8_t* images, int batch, int heigh
     TVG_OUT(ctx, n_candidates, S_FE_NCAND, B * sizeof(int), p.n_cand, int*);
     TVG_GET(ctx, S_FE_CORNERS, B * (size_t)max_corners * sizeof(float2), p.corners, float2*);
     TVG_GET(ctx, S_FE_NCORNERS, B * sizeof(int), p.n_corners, int*);
-    TVG_GET(ctx, S_FE_BLURTMP, B * HW * sizeof(float), p.blur_tmp, float*);
     TVG_GET(ctx, S_FE_BLUR, B * HW, p.blur, uint8_t*);
     p.kps = kps; p.des = des; p.n_kps = n_kps;
     // cv::getGaussianKernel(7, 2, CV_32F): exp(-x^2/8) normalised in double, rounded to float
@@ -489,7 +488,7 @@ int tvg_extract_points(tvg_ctx* ctx, const uint8_t* images, int batch, int heigh
     memcpy(gauss, gauss_bits, sizeof(gauss));
     TVG_CUDA(tvg::frontend_set_tables(pattern_host, gauss, st));
     TVG_CUDA(tvg::launch_frontend(p, st));
-    ctx->launches += 11;
+    ctx->launches += 10;
     return 0;
 }
 

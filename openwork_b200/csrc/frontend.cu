@@ -25,6 +25,7 @@
 namespace tvg {
 
 __constant__ int8_t c_orb_pattern[512 * 2];
+__device__ alignas(4) int8_t g_orb_pattern[512 * 2];   // same table in global memory: coalesced staging into shared memory
 __constant__ float c_gauss7[7];
 
 __device__ __forceinline__ int reflect101(int i, int n) {
@@ -116,14 +117,16 @@ __global__ void __launch_bounds__(128) collect_kernel(const float* __restrict__ 
                                                       double quality, unsigned long long* __restrict__ keys,
                                                       int* __restrict__ n_cand, int cap, int H, int W) {
     const int x = blockIdx.x * blockDim.x + threadIdx.x, y0 = blockIdx.y * EIG_ROWS, b = blockIdx.z;
-    if (x < 1 || x >= W - 1) return;
+    const bool live = x >= 1 && x < W - 1;
+    const int xs = live ? x : 1;            // out-of-range lanes shadow a valid column and never emit
     const float* e = eig + (size_t)b * H * W;
     const float thr = (float)((double)__int_as_float(max_bits[b]) * quality);
+    const int lane = threadIdx.x & 31;
     // rolling window over rows: horizontal maxima of the thresholded map (THRESH_TOZERO) and the centre values
     auto hmax = [&](int yy, float& centre) -> float {
         if (yy < 0 || yy >= H) { centre = 0.0f; return 0.0f; }
         const float* row = e + (size_t)yy * W;
-        const float l = row[x - 1], c = row[x], r = row[x + 1];
+        const float l = row[xs - 1], c = row[xs], r = row[xs + 1];
         centre = c > thr ? c : 0.0f;
         return fmaxf(fmaxf(l > thr ? l : 0.0f, centre), r > thr ? r : 0.0f);
     };
@@ -132,9 +135,15 @@ __global__ void __launch_bounds__(128) collect_kernel(const float* __restrict__ 
     const int y1 = min(H - 1, y0 + EIG_ROWS);
     for (int y = y0; y < y1; ++y) {
         const float m2 = hmax(y + 1, c2);
-        if (y >= 1 && c1 != 0.0f && c1 == fmaxf(fmaxf(m0, m1), m2)) {
-            const int slot = atomicAdd(n_cand + b, 1);
-            if (slot < cap)
+        const bool cand = live && y >= 1 && c1 != 0.0f && c1 == fmaxf(fmaxf(m0, m1), m2);
+        // one atomic per warp and row instead of one per candidate
+        const unsigned bal = __ballot_sync(0xffffffffu, cand);
+        if (bal) {
+            int base = 0;
+            if (lane == 0) base = atomicAdd(n_cand + b, __popc(bal));
+            base = __shfl_sync(0xffffffffu, base, 0);
+            const int slot = base + __popc(bal & ((1u << lane) - 1u));
+            if (cand && slot < cap)
                 keys[(size_t)b * cap + slot] = ((unsigned long long)__float_as_uint(c1) << 32) | (unsigned)(y * W + x);
         }
         m0 = m1; m1 = m2; c0 = c1; c1 = c2;
@@ -270,26 +279,37 @@ __global__ void __launch_bounds__(256) suppress_kernel(const unsigned long long*
     if (lane == 0) n_corners[b] = kept;
 }
 
-// 7x7 Gaussian blur, sigma 2, fp32 separable, BORDER_REFLECT_101
-__global__ void blur_rows_kernel(const uint8_t* __restrict__ gray, float* __restrict__ tmp, int H, int W) {
-    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y, b = blockIdx.z;
-    if (x >= W) return;
-    const uint8_t* g = gray + (size_t)b * H * W + (size_t)y * W;
-    float s = __fmul_rn(c_gauss7[0], (float)g[reflect101(x - 3, W)]);
+// 7x7 Gaussian blur, sigma 2, fp32 separable, BORDER_REFLECT_101.  A CTA filters the rows of a
+// (BLUR_TY + 6) x 128 tile into shared memory and then the columns out of it.
+constexpr int BLUR_TY = 16;
+
+__global__ void __launch_bounds__(128) blur_kernel(const uint8_t* __restrict__ gray, uint8_t* __restrict__ blur, int H,
+                                                   int W) {
+    __shared__ float s_rows[BLUR_TY + 6][128];
+    const int x = blockIdx.x * 128 + threadIdx.x, y0 = blockIdx.y * BLUR_TY, b = blockIdx.z;
+    const uint8_t* g = gray + (size_t)b * H * W;
+    if (x < W) {
+        int xi[7];
 #pragma unroll
-    for (int k = 1; k < 7; ++k) s = __fmaf_rn((float)g[reflect101(x - 3 + k, W)], c_gauss7[k], s);
-    tmp[(size_t)b * H * W + (size_t)y * W + x] = s;
-}
-__global__ void blur_cols_kernel(const float* __restrict__ tmp, uint8_t* __restrict__ blur, int H, int W) {
-    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y, b = blockIdx.z;
-    if (x >= W) return;
-    const float* t = tmp + (size_t)b * H * W + x;
-    float s = __fmul_rn(c_gauss7[3], t[(size_t)y * W]);
+        for (int k = 0; k < 7; ++k) xi[k] = reflect101(x - 3 + k, W);
+        for (int r = 0; r < BLUR_TY + 6; ++r) {
+            const uint8_t* row = g + (size_t)reflect101(y0 - 3 + r, H) * W;
+            float s = __fmul_rn(c_gauss7[0], (float)row[xi[0]]);
 #pragma unroll
-    for (int j = 1; j <= 3; ++j)
-        s = __fmaf_rn(__fadd_rn(t[(size_t)reflect101(y - j, H) * W], t[(size_t)reflect101(y + j, H) * W]), c_gauss7[3 - j], s);
-    const float r = rintf(s);   // saturate_cast<uchar>(float): round half to even, then clamp
-    blur[(size_t)b * H * W + (size_t)y * W + x] = (uint8_t)fminf(fmaxf(r, 0.0f), 255.0f);
+            for (int k = 1; k < 7; ++k) s = __fmaf_rn((float)row[xi[k]], c_gauss7[k], s);
+            s_rows[r][threadIdx.x] = s;
+        }
+        const int y1 = min(H, y0 + BLUR_TY);
+        for (int y = y0; y < y1; ++y) {
+            const int r = y - y0 + 3;
+            float s = __fmul_rn(c_gauss7[3], s_rows[r][threadIdx.x]);
+#pragma unroll
+            for (int j = 1; j <= 3; ++j)
+                s = __fmaf_rn(__fadd_rn(s_rows[r - j][threadIdx.x], s_rows[r + j][threadIdx.x]), c_gauss7[3 - j], s);
+            const float v = rintf(s);   // saturate_cast<uchar>(float): round half to even, then clamp
+            blur[(size_t)b * H * W + (size_t)y * W + x] = (uint8_t)fminf(fmaxf(v, 0.0f), 255.0f);
+        }
+    }
 }
 
 // KeyPointsFilter::runByImageBorder(31), order preserving; one CTA per image
@@ -333,37 +353,45 @@ __global__ void __launch_bounds__(256) border_filter_kernel(const float2* __rest
     if (tid == 0) n_kps[b] = s_base;
 }
 
-// the 256 rBRIEF tests: one thread per keypoint, so that every lane reads the same pattern entry at the same
-// time (constant memory broadcasts uniform addresses and serialises divergent ones)
-__global__ void __launch_bounds__(128) orb_desc_kernel(const uint8_t* __restrict__ blur, const double* __restrict__ kps,
-                                                       const int* __restrict__ n_kps, int max_corners, int H, int W,
-                                                       uint8_t* __restrict__ des) {
-    const int b = blockIdx.y;
-    const int kp = blockIdx.x * 128 + threadIdx.x;
+// The 256 rBRIEF tests.  One warp per keypoint: the 31x32 patch around it is fetched with coalesced row loads
+// into shared memory, the pattern sits in shared memory too (lanes index it divergently, which constant memory
+// would serialise), then lane = descriptor byte: 16 patch reads, 8 comparisons.
+constexpr int DESC_WARPS = 8;
+
+__global__ void __launch_bounds__(DESC_WARPS * 32) orb_desc_kernel(const uint8_t* __restrict__ blur,
+                                                                   const double* __restrict__ kps,
+                                                                   const int* __restrict__ n_kps, int max_corners, int H,
+                                                                   int W, uint8_t* __restrict__ des) {
+    __shared__ alignas(4) int8_t s_pat[1024];
+    __shared__ uint8_t s_patch[DESC_WARPS][31][32];
+    const int b = blockIdx.y, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (blockIdx.x * DESC_WARPS >= n_kps[b]) return;   // whole CTA beyond the last keypoint
+    reinterpret_cast<int*>(s_pat)[threadIdx.x] = reinterpret_cast<const int*>(g_orb_pattern)[threadIdx.x];
+    __syncthreads();
+    const int kp = blockIdx.x * DESC_WARPS + warp;
     if (kp >= n_kps[b]) return;
     const size_t o = (size_t)b * max_corners + kp;
     const int cx = __double2int_rn(kps[o * 2]), cy = __double2int_rn(kps[o * 2 + 1]);
-    const uint8_t* ctr = blur + (size_t)b * H * W + (size_t)cy * W + cx;
-    uint32_t w[8];
+    // rows cy-15 .. cy+15, columns cx-15 .. cx+16 (keypoints are >= 31 pixels from every border)
+    const uint8_t* src = blur + (size_t)b * H * W + (size_t)(cy - 15) * W + (cx - 15) + lane;
 #pragma unroll
-    for (int word = 0; word < 8; ++word) {
-        uint32_t v = 0;
+    for (int r = 0; r < 31; ++r) s_patch[warp][r][lane] = src[(size_t)r * W];
+    __syncwarp();
+    uint32_t v = 0;
 #pragma unroll
-        for (int bit = 0; bit < 32; ++bit) {
-            const int q = (word * 32 + bit) * 4;
-            const int t0 = ctr[(int)c_orb_pattern[q + 1] * W + (int)c_orb_pattern[q]];
-            const int t1 = ctr[(int)c_orb_pattern[q + 3] * W + (int)c_orb_pattern[q + 2]];
-            v |= (uint32_t)(t0 < t1) << bit;
-        }
-        w[word] = v;
+    for (int bit = 0; bit < 8; ++bit) {
+        const int q = (lane * 8 + bit) * 4;
+        const int t0 = s_patch[warp][15 + s_pat[q + 1]][15 + s_pat[q]];
+        const int t1 = s_patch[warp][15 + s_pat[q + 3]][15 + s_pat[q + 2]];
+        v |= (uint32_t)(t0 < t1) << bit;
     }
-    uint4* d = reinterpret_cast<uint4*>(des + o * 32);
-    d[0] = make_uint4(w[0], w[1], w[2], w[3]);
-    d[1] = make_uint4(w[4], w[5], w[6], w[7]);
+    des[o * 32 + lane] = (uint8_t)v;
 }
 
 cudaError_t frontend_set_tables(const int8_t* pattern_host, const float* gauss7_host, cudaStream_t stream) {
     cudaError_t e = cudaMemcpyToSymbolAsync(c_orb_pattern, pattern_host, 1024, 0, cudaMemcpyHostToDevice, stream);
+    if (e != cudaSuccess) return e;
+    e = cudaMemcpyToSymbolAsync(g_orb_pattern, pattern_host, 1024, 0, cudaMemcpyHostToDevice, stream);
     if (e != cudaSuccess) return e;
     return cudaMemcpyToSymbolAsync(c_gauss7, gauss7_host, 7 * sizeof(float), 0, cudaMemcpyHostToDevice, stream);
 }
@@ -389,11 +417,10 @@ cudaError_t launch_frontend(const FrontendParams& p, cudaStream_t stream) {
     if (e != cudaSuccess) return e;
     suppress_kernel<<<B, 256, smem, stream>>>(p.keys, p.n_cand, p.cap, H, W, p.cell, p.slots, p.min_distance, p.max_corners,
                                               p.corners, p.n_corners);
-    blur_rows_kernel<<<g, 128, 0, stream>>>(p.gray, p.blur_tmp, H, W);
-    blur_cols_kernel<<<g, 128, 0, stream>>>(p.blur_tmp, p.blur, H, W);
+    blur_kernel<<<dim3((W + 127) / 128, (H + BLUR_TY - 1) / BLUR_TY, B), 128, 0, stream>>>(p.gray, p.blur, H, W);
     border_filter_kernel<<<B, 256, 0, stream>>>(p.corners, p.n_corners, p.max_corners, H, W, 31, p.kps, p.n_kps);
-    orb_desc_kernel<<<dim3((p.max_corners + 127) / 128, B), 128, 0, stream>>>(p.blur, p.kps, p.n_kps, p.max_corners, H, W,
-                                                                      p.des);
+    orb_desc_kernel<<<dim3((p.max_corners + DESC_WARPS - 1) / DESC_WARPS, B), DESC_WARPS * 32, 0, stream>>>(
+        p.blur, p.kps, p.n_kps, p.max_corners, H, W, p.des);
     return cudaGetLastError();
 }
 

@@ -163,7 +163,6 @@ struct FrontendParams {
     int* n_cand;               // [batch]
     float2* corners;           // [batch][max_corners]
     int* n_corners;            // [batch]
-    float* blur_tmp;           // [batch][H][W]
     uint8_t* blur;             // [batch][H][W]
     double* kps;               // [batch][max_corners][2]
     uint8_t* des;              // [batch][max_corners][32]
