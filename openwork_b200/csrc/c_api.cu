@@ -456,6 +456,7 @@ int tvg_extract_points(tvg_ctx* ctx, const uint8_t* images, int batch, int heigh
         return fail(-2, "tvg_extract_points: bad sizes (64 <= H, W <= 32767; channels 1 or 3; max_corners >= 1)");
     if (batch == 0) return 0;
     if (!images || !pattern_host || !kps || !des || !n_kps) return fail(-3, "tvg_extract_points: NULL array");
+    if (reinterpret_cast<uintptr_t>(images) & 3u) return fail(-4, "tvg_extract_points: images must be 4-byte aligned");
     if (!(quality_level > 0.0) || !(min_distance >= 1.0)) return fail(-2, "tvg_extract_points: quality_level > 0, min_distance >= 1");
     const int cell = (int)__builtin_rint(min_distance);
     // one kept corner per grid cell when even the cell diagonal is shorter than min_distance; else at most 4
@@ -472,7 +473,6 @@ int tvg_extract_points(tvg_ctx* ctx, const uint8_t* images, int batch, int heigh
     p.max_corners = max_corners; p.cell = cell; p.slots = slots; p.cap = (int)(HW / 2); p.quality = quality_level;
     p.min_distance = (float)min_distance;
     TVG_GET(ctx, S_FE_GRAY, B * HW, p.gray, uint8_t*);
-    TVG_GET(ctx, S_FE_COV, B * 3 * HW * sizeof(float), p.cov, float*);
     TVG_GET(ctx, S_FE_EIG, B * HW * sizeof(float), p.eig, float*);
     TVG_GET(ctx, S_FE_MAX, B * sizeof(int), p.max_bits, int*);
     TVG_GET(ctx, S_FE_KEYS, B * (size_t)p.cap * sizeof(unsigned long long), p.keys, unsigned long long*);
@@ -488,7 +488,7 @@ int tvg_extract_points(tvg_ctx* ctx, const uint8_t* images, int batch, int heigh
     memcpy(gauss, gauss_bits, sizeof(gauss));
     TVG_CUDA(tvg::frontend_set_tables(pattern_host, gauss, st));
     TVG_CUDA(tvg::launch_frontend(p, st));
-    ctx->launches += 10;
+    ctx->launches += 9;
     return 0;
 }
 

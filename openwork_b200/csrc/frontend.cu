@@ -35,66 +35,85 @@ __device__ __forceinline__ int reflect101(int i, int n) {
 }
 
 __global__ void gray_kernel(const uint8_t* __restrict__ img, uint8_t* __restrict__ gray, size_t npix, int channels) {
-    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= npix) return;
-    if (channels == 1) {
-        gray[i] = img[i];
+    const size_t i4 = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) * 4;    // four pixels per thread
+    if (i4 >= npix) return;
+    if (i4 + 4 <= npix) {
+        if (channels == 1) {
+            *reinterpret_cast<uint32_t*>(gray + i4) = *reinterpret_cast<const uint32_t*>(img + i4);
+        } else {
+            const uint32_t* p = reinterpret_cast<const uint32_t*>(img + 3 * i4);   // 12 bytes = B G R x 4
+            const uint32_t w0 = p[0], w1 = p[1], w2 = p[2];
+            const uint32_t by[12] = {w0 & 255u, (w0 >> 8) & 255u, (w0 >> 16) & 255u, w0 >> 24,
+                                     w1 & 255u, (w1 >> 8) & 255u, (w1 >> 16) & 255u, w1 >> 24,
+                                     w2 & 255u, (w2 >> 8) & 255u, (w2 >> 16) & 255u, w2 >> 24};
+            uint32_t out = 0;
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+                out |= ((by[3 * k] * 3735u + by[3 * k + 1] * 19235u + by[3 * k + 2] * 9798u + (1u << 14)) >> 15) << (8 * k);
+            *reinterpret_cast<uint32_t*>(gray + i4) = out;
+        }
     } else {
-        const uint32_t b = img[3 * i], g = img[3 * i + 1], r = img[3 * i + 2];
-        gray[i] = (uint8_t)((b * 3735u + g * 19235u + r * 9798u + (1u << 14)) >> 15);
+        for (size_t i = i4; i < npix; ++i) {
+            if (channels == 1) gray[i] = img[i];
+            else gray[i] = (uint8_t)((img[3 * i] * 3735u + img[3 * i + 1] * 19235u + img[3 * i + 2] * 9798u + (1u << 14)) >> 15);
+        }
     }
 }
 
-// Sobel derivatives and their products: cov[b][3][H][W] = (Dx*Dx, Dx*Dy, Dy*Dy)
-__global__ void cov_kernel(const uint8_t* __restrict__ gray, float* __restrict__ cov, int H, int W) {
-    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y, b = blockIdx.z;
-    if (x >= W) return;
-    const uint8_t* g = gray + (size_t)b * H * W;
+// Sobel derivatives and their products at one pixel: (Dx*Dx, Dx*Dy, Dy*Dy)
+__device__ __forceinline__ void cov_at(const uint8_t* __restrict__ g, int y, int x, int H, int W, float (&c)[3]) {
     const float s = (float)(1.0 / (255.0 * 4 * 3)), s2 = (float)(2.0 / (255.0 * 4 * 3));
     const int xm = reflect101(x - 1, W), xp = reflect101(x + 1, W);
-    const bool inner = y >= 1 && y < H - 1;
     float r[3], q[3];
 #pragma unroll
     for (int k = 0; k < 3; ++k) {
-        const int yy = inner ? y - 1 + k : reflect101(y - 1 + k, H);
-        const float pm = (float)g[(size_t)yy * W + xm], p0 = (float)g[(size_t)yy * W + x], pp = (float)g[(size_t)yy * W + xp];
+        const uint8_t* row = g + (size_t)reflect101(y - 1 + k, H) * W;
+        const float pm = (float)row[xm], p0 = (float)row[x], pp = (float)row[xp];
         r[k] = __fsub_rn(pp, pm);
         q[k] = __fmaf_rn(s, pp, __fmaf_rn(s2, p0, __fmul_rn(s, pm)));
     }
     const float dx = __fmaf_rn(s, __fadd_rn(r[0], r[2]), __fmul_rn(s2, r[1]));
     const float dy = __fsub_rn(q[2], q[0]);
-    float* c = cov + (size_t)b * 3 * H * W + (size_t)y * W + x;
     c[0] = __fmul_rn(dx, dx);
-    c[(size_t)H * W] = __fmul_rn(dx, dy);
-    c[(size_t)2 * H * W] = __fmul_rn(dy, dy);
+    c[1] = __fmul_rn(dx, dy);
+    c[2] = __fmul_rn(dy, dy);
 }
 
-// Rolling three-row window: a thread walks EIG_ROWS rows of one pixel column, keeping the horizontal 3-sums
-// (double, 3 planes) of the last three rows in registers -> ~10 loads per pixel instead of 27.
+// cornerMinEigenVal fused: a CTA builds the three product planes of an (EIG_ROWS + 2) x 130 tile in shared memory
+// (BORDER_REFLECT_101 of the PRODUCT planes, like cv::boxFilter), then every thread walks its pixel column with a
+// rolling three-row window of horizontal 3-sums (double).  No product plane ever goes to global memory.
 constexpr int EIG_ROWS = 16;
 
-__global__ void __launch_bounds__(128) eig_kernel(const float* __restrict__ cov, float* __restrict__ eig,
+__global__ void __launch_bounds__(128) eig_kernel(const uint8_t* __restrict__ gray, float* __restrict__ eig,
                                                   int* __restrict__ max_bits, int H, int W) {
-    const int x = blockIdx.x * blockDim.x + threadIdx.x, y0 = blockIdx.y * EIG_ROWS, b = blockIdx.z;
+    __shared__ float s_cov[3][EIG_ROWS + 2][132];
+    const int x0 = blockIdx.x * 128, y0 = blockIdx.y * EIG_ROWS, b = blockIdx.z;
+    const uint8_t* g = gray + (size_t)b * H * W;
+    for (int i = threadIdx.x; i < (EIG_ROWS + 2) * 130; i += 128) {
+        const int ty = i / 130, tx = i % 130;
+        const int yy = reflect101(min(y0 - 1 + ty, H), H), xx = reflect101(min(x0 - 1 + tx, W), W);
+        float c[3];
+        cov_at(g, yy, xx, H, W, c);
+        s_cov[0][ty][tx] = c[0];
+        s_cov[1][ty][tx] = c[1];
+        s_cov[2][ty][tx] = c[2];
+    }
+    __syncthreads();
+    const int x = x0 + threadIdx.x;
     float m = 0.0f;
     if (x < W) {
-        const float* c = cov + (size_t)b * 3 * H * W;
-        const int xm = reflect101(x - 1, W), xp = reflect101(x + 1, W);
+        const int tx = threadIdx.x + 1;
         double h[3][3];   // h[row slot][plane]
-        auto hsum = [&](int yy, double (&o)[3]) {
-            const int r = reflect101(yy, H);
+        auto hsum = [&](int ty, double (&o)[3]) {
 #pragma unroll
-            for (int k = 0; k < 3; ++k) {
-                const float* row = c + (size_t)k * H * W + (size_t)r * W;
-                // same association as the direct 9-sum: left to right within a row
-                o[k] = ((double)row[xm] + (double)row[x]) + (double)row[xp];
-            }
+            for (int k = 0; k < 3; ++k)
+                o[k] = ((double)s_cov[k][ty][tx - 1] + (double)s_cov[k][ty][tx]) + (double)s_cov[k][ty][tx + 1];
         };
-        hsum(y0 - 1, h[0]);
-        hsum(y0, h[1]);
+        hsum(0, h[0]);
+        hsum(1, h[1]);
         const int y1 = min(H, y0 + EIG_ROWS);
         for (int y = y0; y < y1; ++y) {
-            hsum(y + 1, h[2]);
+            hsum(y - y0 + 2, h[2]);
             const float a = __fmul_rn((float)((h[0][0] + h[1][0]) + h[2][0]), 0.5f);
             const float bb = (float)((h[0][1] + h[1][1]) + h[2][1]);
             const float cc = __fmul_rn((float)((h[0][2] + h[1][2]) + h[2][2]), 0.5f);
@@ -121,7 +140,6 @@ __global__ void __launch_bounds__(128) collect_kernel(const float* __restrict__ 
     const int xs = live ? x : 1;            // out-of-range lanes shadow a valid column and never emit
     const float* e = eig + (size_t)b * H * W;
     const float thr = (float)((double)__int_as_float(max_bits[b]) * quality);
-    const int lane = threadIdx.x & 31;
     // rolling window over rows: horizontal maxima of the thresholded map (THRESH_TOZERO) and the centre values
     auto hmax = [&](int yy, float& centre) -> float {
         if (yy < 0 || yy >= H) { centre = 0.0f; return 0.0f; }
@@ -130,23 +148,30 @@ __global__ void __launch_bounds__(128) collect_kernel(const float* __restrict__ 
         centre = c > thr ? c : 0.0f;
         return fmaxf(fmaxf(l > thr ? l : 0.0f, centre), r > thr ? r : 0.0f);
     };
+    // Candidates are staged in shared memory (a pixel column holds at most EIG_ROWS/2 local maxima in EIG_ROWS
+    // rows); the CTA then reserves its output range with ONE global atomic, so no thread ever waits for an atomic's
+    // return value inside the row loop.
+    __shared__ unsigned long long s_keys[128 * (EIG_ROWS / 2)];
+    __shared__ int s_n, s_base;
+    if (threadIdx.x == 0) s_n = 0;
+    __syncthreads();
     float c0, c1, c2;
     float m0 = hmax(y0 - 1, c0), m1 = hmax(y0, c1);
     const int y1 = min(H - 1, y0 + EIG_ROWS);
     for (int y = y0; y < y1; ++y) {
         const float m2 = hmax(y + 1, c2);
-        const bool cand = live && y >= 1 && c1 != 0.0f && c1 == fmaxf(fmaxf(m0, m1), m2);
-        // one atomic per warp and row instead of one per candidate
-        const unsigned bal = __ballot_sync(0xffffffffu, cand);
-        if (bal) {
-            int base = 0;
-            if (lane == 0) base = atomicAdd(n_cand + b, __popc(bal));
-            base = __shfl_sync(0xffffffffu, base, 0);
-            const int slot = base + __popc(bal & ((1u << lane) - 1u));
-            if (cand && slot < cap)
-                keys[(size_t)b * cap + slot] = ((unsigned long long)__float_as_uint(c1) << 32) | (unsigned)(y * W + x);
-        }
+        if (live && y >= 1 && c1 != 0.0f && c1 == fmaxf(fmaxf(m0, m1), m2))
+            s_keys[atomicAdd(&s_n, 1)] = ((unsigned long long)__float_as_uint(c1) << 32) | (unsigned)(y * W + x);
         m0 = m1; m1 = m2; c0 = c1; c1 = c2;
+    }
+    __syncthreads();
+    const int n = s_n;
+    if (n == 0) return;
+    if (threadIdx.x == 0) s_base = atomicAdd(n_cand + b, n);
+    __syncthreads();
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        const int slot = s_base + i;
+        if (slot < cap) keys[(size_t)b * cap + slot] = s_keys[i];
     }
 }
 
@@ -399,13 +424,11 @@ cudaError_t frontend_set_tables(const int8_t* pattern_host, const float* gauss7_
 cudaError_t launch_frontend(const FrontendParams& p, cudaStream_t stream) {
     const int H = p.H, W = p.W, B = p.batch;
     const size_t npix = (size_t)B * H * W;
-    gray_kernel<<<(unsigned)((npix + 255) / 256), 256, 0, stream>>>(p.images, p.gray, npix, p.channels);
-    dim3 g((W + 127) / 128, H, B);
-    cov_kernel<<<g, 128, 0, stream>>>(p.gray, p.cov, H, W);
+    gray_kernel<<<(unsigned)((npix / 4 + 256) / 256), 256, 0, stream>>>(p.images, p.gray, npix, p.channels);
     cudaMemsetAsync(p.max_bits, 0, (size_t)B * sizeof(int), stream);
     cudaMemsetAsync(p.n_cand, 0, (size_t)B * sizeof(int), stream);
     dim3 gr((W + 127) / 128, (H + EIG_ROWS - 1) / EIG_ROWS, B);
-    eig_kernel<<<gr, 128, 0, stream>>>(p.cov, p.eig, p.max_bits, H, W);
+    eig_kernel<<<gr, 128, 0, stream>>>(p.gray, p.eig, p.max_bits, H, W);
     collect_kernel<<<gr, 128, 0, stream>>>(p.eig, p.max_bits, p.quality, p.keys, p.n_cand, p.cap, H, W);
     cudaError_t e = cudaFuncSetAttribute(sort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          SORT_CHUNK * (int)sizeof(unsigned long long));

@@ -156,7 +156,6 @@ struct FrontendParams {
     double quality;
     float min_distance;
     uint8_t* gray;             // [batch][H][W]
-    float* cov;                // [batch][3][H][W]
     float* eig;                // [batch][H][W]
     int* max_bits;             // [batch]
     unsigned long long* keys;  // [batch][cap]
