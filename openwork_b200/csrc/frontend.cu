@@ -60,6 +60,9 @@ __global__ void gray_kernel(const uint8_t* __restrict__ img, uint8_t* __restrict
     }
 }
 
+// exact u8 -> float without the conversion unit: 2^23 + b has b in its low mantissa bits
+__device__ __forceinline__ float u8f(unsigned b) { return __fsub_rn(__uint_as_float(0x4B000000u | b), 8388608.0f); }
+
 // Sobel derivatives and their products at one pixel: (Dx*Dx, Dx*Dy, Dy*Dy)
 __device__ __forceinline__ void cov_at(const uint8_t* __restrict__ g, int y, int x, int H, int W, float (&c)[3]) {
     const float s = (float)(1.0 / (255.0 * 4 * 3)), s2 = (float)(2.0 / (255.0 * 4 * 3));
@@ -68,7 +71,7 @@ __device__ __forceinline__ void cov_at(const uint8_t* __restrict__ g, int y, int
 #pragma unroll
     for (int k = 0; k < 3; ++k) {
         const uint8_t* row = g + (size_t)reflect101(y - 1 + k, H) * W;
-        const float pm = (float)row[xm], p0 = (float)row[x], pp = (float)row[xp];
+        const float pm = u8f(row[xm]), p0 = u8f(row[x]), pp = u8f(row[xp]);
         r[k] = __fsub_rn(pp, pm);
         q[k] = __fmaf_rn(s, pp, __fmaf_rn(s2, p0, __fmul_rn(s, pm)));
     }
@@ -81,22 +84,65 @@ __device__ __forceinline__ void cov_at(const uint8_t* __restrict__ g, int y, int
 
 // cornerMinEigenVal fused: a CTA builds the three product planes of an (EIG_ROWS + 2) x 130 tile in shared memory
 // (BORDER_REFLECT_101 of the PRODUCT planes, like cv::boxFilter), then every thread walks its pixel column with a
-// rolling three-row window of horizontal 3-sums (double).  No product plane ever goes to global memory.
+// rolling three-row window of horizontal 3-sums (double).  No product plane ever goes to global memory.  The tile
+// is stored as double: one float->double conversion per tile entry instead of one per use (the conversion unit,
+// 16 lanes/clk/SM, is what bounds this kernel).
 constexpr int EIG_ROWS = 16;
+constexpr int EIG_TW = 132;
+using eig_tile_t = float;   // double halves the conversions but the 57 KB tile costs more in occupancy (measured)
+constexpr int EIG_SMEM = 3 * (EIG_ROWS + 2) * EIG_TW * (int)sizeof(eig_tile_t);
 
 __global__ void __launch_bounds__(128) eig_kernel(const uint8_t* __restrict__ gray, float* __restrict__ eig,
                                                   int* __restrict__ max_bits, int H, int W) {
-    __shared__ float s_cov[3][EIG_ROWS + 2][132];
+    extern __shared__ eig_tile_t s_cov[];   // [3][EIG_ROWS + 2][EIG_TW]
+    constexpr int PLANE = (EIG_ROWS + 2) * EIG_TW;
     const int x0 = blockIdx.x * 128, y0 = blockIdx.y * EIG_ROWS, b = blockIdx.z;
     const uint8_t* g = gray + (size_t)b * H * W;
-    for (int i = threadIdx.x; i < (EIG_ROWS + 2) * 130; i += 128) {
-        const int ty = i / 130, tx = i % 130;
-        const int yy = reflect101(min(y0 - 1 + ty, H), H), xx = reflect101(min(x0 - 1 + tx, W), W);
-        float c[3];
-        cov_at(g, yy, xx, H, W, c);
-        s_cov[0][ty][tx] = c[0];
-        s_cov[1][ty][tx] = c[1];
-        s_cov[2][ty][tx] = c[2];
+    auto put = [&](int ty, int tx, const float (&c)[3]) {
+        s_cov[ty * EIG_TW + tx] = (eig_tile_t)c[0];
+        s_cov[PLANE + ty * EIG_TW + tx] = (eig_tile_t)c[1];
+        s_cov[2 * PLANE + ty * EIG_TW + tx] = (eig_tile_t)c[2];
+    };
+    if (y0 >= 2 && y0 + EIG_ROWS + 1 <= H - 1) {
+        // Rows away from the top/bottom border: a thread walks down tile column threadIdx.x keeping the horizontal
+        // Sobel parts (difference r, smoothing q) of three gray rows in registers: 3 loads per entry instead of 9.
+        const float s = (float)(1.0 / (255.0 * 4 * 3)), s2 = (float)(2.0 / (255.0 * 4 * 3));
+        const int xx = reflect101(min(x0 - 1 + (int)threadIdx.x, W), W);
+        const int xm = reflect101(xx - 1, W), xp = reflect101(xx + 1, W);
+        const uint8_t* row = g + (size_t)(y0 - 2) * W;
+        auto rq = [&](float& r, float& q) {
+            const float pm = u8f(row[xm]), p0 = u8f(row[xx]), pp = u8f(row[xp]);
+            r = __fsub_rn(pp, pm);
+            q = __fmaf_rn(s, pp, __fmaf_rn(s2, p0, __fmul_rn(s, pm)));
+            row += W;
+        };
+        float r0, q0, r1, q1;
+        rq(r0, q0);
+        rq(r1, q1);
+#pragma unroll
+        for (int ty = 0; ty < EIG_ROWS + 2; ++ty) {
+            float r2, q2;
+            rq(r2, q2);
+            const float dx = __fmaf_rn(s, __fadd_rn(r0, r2), __fmul_rn(s2, r1));
+            const float dy = __fsub_rn(q2, q0);
+            const float c[3] = {__fmul_rn(dx, dx), __fmul_rn(dx, dy), __fmul_rn(dy, dy)};
+            put(ty, threadIdx.x, c);
+            r0 = r1; r1 = r2; q0 = q1; q1 = q2;
+        }
+        if (threadIdx.x < 2 * (EIG_ROWS + 2)) {   // the two halo columns on the right
+            const int ty = threadIdx.x >> 1, tx = 128 + (threadIdx.x & 1);
+            float c[3];
+            cov_at(g, y0 - 1 + ty, reflect101(min(x0 - 1 + tx, W), W), H, W, c);
+            put(ty, tx, c);
+        }
+    } else {
+        for (int i = threadIdx.x; i < (EIG_ROWS + 2) * 130; i += 128) {
+            const int ty = i / 130, tx = i % 130;
+            const int yy = reflect101(min(y0 - 1 + ty, H), H), xx = reflect101(min(x0 - 1 + tx, W), W);
+            float c[3];
+            cov_at(g, yy, xx, H, W, c);
+            put(ty, tx, c);
+        }
     }
     __syncthreads();
     const int x = x0 + threadIdx.x;
@@ -106,8 +152,10 @@ __global__ void __launch_bounds__(128) eig_kernel(const uint8_t* __restrict__ gr
         double h[3][3];   // h[row slot][plane]
         auto hsum = [&](int ty, double (&o)[3]) {
 #pragma unroll
-            for (int k = 0; k < 3; ++k)
-                o[k] = ((double)s_cov[k][ty][tx - 1] + (double)s_cov[k][ty][tx]) + (double)s_cov[k][ty][tx + 1];
+            for (int k = 0; k < 3; ++k) {
+                const eig_tile_t* row = s_cov + k * PLANE + ty * EIG_TW + tx;
+                o[k] = ((double)row[-1] + (double)row[0]) + (double)row[1];
+            }
         };
         hsum(0, h[0]);
         hsum(1, h[1]);
@@ -339,9 +387,9 @@ __global__ void __launch_bounds__(128) blur_kernel(const uint8_t* __restrict__ g
         for (int k = 0; k < 7; ++k) xi[k] = reflect101(x - 3 + k, W);
         for (int r = 0; r < BLUR_TY + 6; ++r) {
             const uint8_t* row = g + (size_t)reflect101(y0 - 3 + r, H) * W;
-            float s = __fmul_rn(c_gauss7[0], (float)row[xi[0]]);
+            float s = __fmul_rn(c_gauss7[0], u8f(row[xi[0]]));
 #pragma unroll
-            for (int k = 1; k < 7; ++k) s = __fmaf_rn((float)row[xi[k]], c_gauss7[k], s);
+            for (int k = 1; k < 7; ++k) s = __fmaf_rn(u8f(row[xi[k]]), c_gauss7[k], s);
             s_rows[r][threadIdx.x] = s;
         }
         const int y1 = min(H, y0 + BLUR_TY);
@@ -351,8 +399,10 @@ __global__ void __launch_bounds__(128) blur_kernel(const uint8_t* __restrict__ g
 #pragma unroll
             for (int j = 1; j <= 3; ++j)
                 s = __fmaf_rn(__fadd_rn(s_rows[r - j][threadIdx.x], s_rows[r + j][threadIdx.x]), c_gauss7[3 - j], s);
-            const float v = rintf(s);   // saturate_cast<uchar>(float): round half to even, then clamp
-            blur[(size_t)b * H * W + (size_t)y * W + x] = (uint8_t)fminf(fmaxf(v, 0.0f), 255.0f);
+            // saturate_cast<uchar>(float): round half to even, then clamp.  0 <= s < 256 here, so adding 1.5 * 2^23
+            // leaves rint(s) in the low mantissa bits without touching the conversion unit.
+            const unsigned v = __float_as_uint(__fadd_rn(s, 12582912.0f)) & 0x1FFu;
+            blur[(size_t)b * H * W + (size_t)y * W + x] = (uint8_t)min(v, 255u);
         }
     }
 }
@@ -448,9 +498,11 @@ cudaError_t launch_frontend(const FrontendParams& p, cudaStream_t stream) {
     cudaMemsetAsync(p.max_bits, 0, (size_t)B * sizeof(int), stream);
     cudaMemsetAsync(p.n_cand, 0, (size_t)B * sizeof(int), stream);
     dim3 gr((W + 127) / 128, (H + EIG_ROWS - 1) / EIG_ROWS, B);
-    eig_kernel<<<gr, 128, 0, stream>>>(p.gray, p.eig, p.max_bits, H, W);
+    cudaError_t e = cudaFuncSetAttribute(eig_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, EIG_SMEM);
+    if (e != cudaSuccess) return e;
+    eig_kernel<<<gr, 128, EIG_SMEM, stream>>>(p.gray, p.eig, p.max_bits, H, W);
     collect_kernel<<<gr, 128, 0, stream>>>(p.eig, p.max_bits, p.quality, p.keys, p.n_cand, p.cap, H, W);
-    cudaError_t e = cudaFuncSetAttribute(sort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SORT_SMEM);
+    e = cudaFuncSetAttribute(sort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SORT_SMEM);
     if (e != cudaSuccess) return e;
     sort_kernel<<<B, 1024, SORT_SMEM, stream>>>(p.keys, p.n_cand, p.cap);
     const int gw = (W + p.cell - 1) / p.cell, gh = (H + p.cell - 1) / p.cell;
