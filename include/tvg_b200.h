@@ -42,10 +42,13 @@ TVG_API const char* tvg_last_error(void);
 TVG_API int tvg_abi_version(void);
 /* Number of CUDA kernels this library has launched through `ctx` since creation (bench.py: gpu_launches). */
 TVG_API long long tvg_launch_count(const tvg_ctx* ctx);
-/* Matcher tuning: queries per thread r in {2,4,8}; popcount variant 0 = 8xPOPC, 1 = Harley-Seal 4xPOPC,
- * 2 = 5xPOPC, 3 = Harley-Seal with query/train-shared XOR combos (14 LOP3 + 4 POPC); +4 (variants 5, 7) =
- * lazy top-2 insertion, +8 (variants 9, 11) = two queries' chunk-local 16-bit keys packed per register
- * (VIMNMX.U16x2 top-2 updates); ctas_per_sm sizes the split-Nt grid.  Results are bit-identical for every setting. */
+/* Matcher tuning.  variant -1 (the default state) = automatic: calls with >= 16 Mi descriptor comparisons run on
+ * the tensor cores (variant 16: e4m3 +-1 operands, tcgen05.mma, exact f16 dot products, top-2 in the TMEM
+ * epilogue), smaller calls on the integer pipe.  Integer-pipe variants: queries per thread r in {2,4,8}; popcount
+ * variant 0 = 8xPOPC, 1 = Harley-Seal 4xPOPC, 2 = 5xPOPC, 3 = Harley-Seal with query/train-shared XOR combos
+ * (14 LOP3 + 4 POPC); +4 (variants 5, 7) = lazy top-2 insertion, +8 (variants 9, 11) = two queries' chunk-local
+ * 16-bit keys packed per register (VIMNMX.U16x2 top-2 updates); ctas_per_sm sizes the split-Nt grid.
+ * Results are bit-identical for every setting. */
 TVG_API int tvg_set_matcher_config(tvg_ctx* ctx, int r, int variant, int ctas_per_sm);
 
 /* cv2.BFMatcher(cv2.NORM_HAMMING).knnMatch(q, t, k=2)  (slam.py:126-127) + the Lowe ratio flag

@@ -158,5 +158,6 @@ class Context:
     def set_host_chunk(self, pairs=256):
         check(self.lib.tvg_set_host_chunk(self.handle, int(pairs)), "tvg_set_host_chunk")
 
-    def set_matcher_config(self, r=4, variant=11, ctas_per_sm=6):
+    def set_matcher_config(self, r=4, variant=-1, ctas_per_sm=6):
+        """variant -1 = automatic (tensor cores for large calls), 16 = tensor cores, 0..11 = integer-pipe variants."""
         check(self.lib.tvg_set_matcher_config(self.handle, r, variant, ctas_per_sm), "tvg_set_matcher_config")

@@ -37,6 +37,7 @@ enum Slot {
     S_FE_CORNERS, S_FE_NCORNERS, S_FE_BLURTMP, S_FE_BLUR,
     // host-entry staging
     S_H_DES, S_H_KPS, S_H_FCOUNT, S_H_PAIRQ, S_H_PAIRT, S_H_SEQOFF, S_H_INIT, S_H_WORDS, S_H_SAMPLES,
+    S_KNN_TC,
     S_NUM
 };
 
@@ -45,6 +46,8 @@ enum Slot {
 // stage marks of the pair pipeline: before knn, compact, fit, score, reduce, rescore, refit+solve,
 // pose stage (cheirality + pose chain), triangulate, and after triangulate
 #define TVG_PROF_MARKS 10
+// tvg_knn2_hamming256 switches to the tensor-core matcher from this many descriptor comparisons per call
+#define TVG_TC_MIN_CMP (16ll << 20)
 
 struct tvg_ctx {
     int device = 0;
@@ -202,8 +205,16 @@ long long tvg_launch_count(const tvg_ctx* ctx) { return ctx ? ctx->launches : 0;
 
 int tvg_set_matcher_config(tvg_ctx* ctx, int r, int variant, int ctas_per_sm) {
     if (!ctx) return fail(-1, "ctx is NULL");
-    if (!(r == 2 || r == 4 || r == 8) || !((variant >= 0 && variant <= 3) || variant == 5 || variant == 7 || variant == 9 || variant == 11) || ctas_per_sm < 1 || ctas_per_sm > 16)
-        return fail(-2, "tvg_set_matcher_config: r in {2,4,8}, variant in {0,1,2,3,5,7,9,11}, ctas_per_sm in [1,16]");
+    if (variant == -1) {   // back to the automatic choice (integer pipe for small calls, tensor cores otherwise)
+        if (ctas_per_sm < 1 || ctas_per_sm > 16) return fail(-2, "tvg_set_matcher_config: ctas_per_sm in [1,16]");
+        ctx->knn_auto = true;
+        ctx->knn_r = 4;
+        ctx->knn_variant = 11;
+        ctx->knn_ctas_per_sm = ctas_per_sm;
+        return 0;
+    }
+    if (!(r == 2 || r == 4 || r == 8) || !((variant >= 0 && variant <= 3) || variant == 5 || variant == 7 || variant == 9 || variant == 11 || variant == 16) || ctas_per_sm < 1 || ctas_per_sm > 16)
+        return fail(-2, "tvg_set_matcher_config: r in {2,4,8}, variant in {0,1,2,3,5,7,9,11,16}, ctas_per_sm in [1,16]");
     ctx->knn_auto = false;
     ctx->knn_r = r;
     ctx->knn_variant = variant;
@@ -229,6 +240,18 @@ int tvg_knn2_hamming256(tvg_ctx* ctx, const uint8_t* q_des, const uint8_t* t_des
     p.n_max = n_max; p.nq = nq; p.nt = nt;
     p.idx = idx; p.dist = dist; p.keep = keep; p.ratio = ratio;
     p.key_mul = 1u << TVG_KEY_SHIFT; p.w2 = 2u; p.w128 = 128u; p.w65536 = 65536u;
+    const int q_rows_tc = q_count ? n_max : nq, t_rows_tc = t_count ? n_max : nt;
+    // Tensor-core path (variant 16): e4m3 +-1 operands, exact f16 dot products, same results.  Chosen automatically
+    // once the call holds enough comparisons to amortise the operand expansion (a single 2k x 2k pair stays on the
+    // split integer-pipe kernel, which has the lower latency).
+    const bool use_tc = ctx->knn_auto ? (double)batch * q_rows_tc * t_rows_tc >= (double)TVG_TC_MIN_CMP : ctx->knn_variant == 16;
+    if (use_tc) {
+        uint8_t* ws = nullptr;
+        TVG_GET(ctx, S_KNN_TC, tvg::knn2_tc_workspace_bytes(batch, n_max), ws, uint8_t*);
+        TVG_CUDA(tvg::launch_knn2_tc(p, batch, q_rows_tc, ws, ctx->sm_count, (cudaStream_t)stream));
+        ctx->launches += t_rows_tc > 0 ? 2 : 1;
+        return 0;
+    }
     // queries per thread: 4 for big batches; when the grid has to be filled by splitting the train rows
     // (one or few pairs) 2 queries per thread give twice the CTAs per query tile and measure ~6 % faster
     int knn_r = ctx->knn_r;

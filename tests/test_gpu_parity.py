@@ -35,7 +35,9 @@ def _fro_diff(A, B):
 # ------------------------------------------------------------------------------ matcher
 @pytest.mark.parametrize("nq,nt", [(1, 2), (5, 1), (7, 3), (33, 129), (500, 700), (2048, 2048), (1000, 4099),
                                    (4100, 257)])
-def test_knn2_bit_exact(ops, nq, nt):
+@pytest.mark.parametrize("variant", [-1, 11, 16])
+def test_knn2_bit_exact(ops, nq, nt, variant):
+    ops.context(0).set_matcher_config(4, variant, 6)
     rng = np.random.default_rng(nq * 10007 + nt)
     q = rng.integers(0, 256, (nq, 32), dtype=np.uint8)
     t = rng.integers(0, 256, (nt, 32), dtype=np.uint8)
@@ -48,16 +50,40 @@ def test_knn2_bit_exact(ops, nq, nt):
     ri, rd = tv.knn2_cv2(q, t)
     assert np.array_equal(dist.cpu().numpy(), rd)
     assert np.array_equal(idx.cpu().numpy(), ri)
+    ops.context(0).set_matcher_config()
     ni, nd = tv.knn2_numpy(q, t)
     assert np.array_equal(idx.cpu().numpy(), ni) and np.array_equal(dist.cpu().numpy(), nd)
 
 
-def test_knn2_all_equal_descriptors(ops):
+@pytest.mark.parametrize("variant", [11, 16])
+def test_knn2_all_equal_descriptors(ops, variant):
     q = np.full((300, 32), 0xA5, dtype=np.uint8)
     t = np.full((513, 32), 0xA5, dtype=np.uint8)
-    idx, dist, keep = ops.knn2_hamming256(q, t, return_keep=True)
+    ops.context(0).set_matcher_config(4, variant, 6)
+    try:
+        idx, dist, keep = ops.knn2_hamming256(q, t, return_keep=True)
+    finally:
+        ops.context(0).set_matcher_config()
     assert (idx.cpu().numpy() == np.array([0, 1])).all() and (dist.cpu().numpy() == 0).all()
     assert not keep.any()           # 0 < 0.75*0 is False
+
+
+@pytest.mark.parametrize("variant", [11, 16])
+def test_knn2_extreme_distances(ops, variant):
+    """Distances 0, 1, 255 and 256 (complemented descriptors) and 300 identical train rows: key packing limits."""
+    rng = np.random.default_rng(256)
+    r = rng.integers(0, 256, 32, dtype=np.uint8)
+    t = np.tile(r, (300, 1))
+    one = r.copy(); one[5] ^= 0x10
+    q = np.stack([~r, r, one, ~one] * 70).astype(np.uint8)
+    ops.context(0).set_matcher_config(4, variant, 6)
+    try:
+        idx, dist = ops.knn2_hamming256(q, t)
+    finally:
+        ops.context(0).set_matcher_config()
+    ri, rd = tv.knn2_numpy(q, t)
+    assert set(rd[:, 0].tolist()) == {0, 1, 255, 256}
+    assert np.array_equal(idx.cpu().numpy(), ri) and np.array_equal(dist.cpu().numpy(), rd)
 
 
 def test_knn2_empty(ops):
@@ -72,7 +98,8 @@ def test_knn2_empty(ops):
 @pytest.mark.parametrize("r,variant,ctas", [(2, 0, 6), (4, 0, 1), (4, 1, 6), (4, 2, 6), (8, 0, 4), (8, 1, 8),
                                             (2, 1, 16), (2, 2, 3), (8, 2, 2), (4, 3, 6), (2, 3, 2), (8, 3, 8),
                                             (4, 5, 6), (2, 5, 1), (8, 5, 8), (4, 7, 6), (2, 7, 16), (8, 7, 3),
-                                            (4, 9, 6), (2, 9, 3), (8, 9, 8), (4, 11, 6), (2, 11, 16), (8, 11, 1)])
+                                            (4, 9, 6), (2, 9, 3), (8, 9, 8), (4, 11, 6), (2, 11, 16), (8, 11, 1),
+                                            (4, 16, 6)])
 def test_knn2_every_config_is_bit_identical(ops, r, variant, ctas):
     q, t = synth.correlated_descriptors(3000, 2500, seed=r * 100 + variant * 10 + ctas)
     t[100:200] = t[300:400]
@@ -81,7 +108,7 @@ def test_knn2_every_config_is_bit_identical(ops, r, variant, ctas):
         ctx.set_matcher_config(r, variant, ctas)
         idx, dist, keep = ops.knn2_hamming256(q, t, return_keep=True)
     finally:
-        ctx.set_matcher_config(4, 11, 6)
+        ctx.set_matcher_config()
     ri, rd = tv.knn2_cv2(q, t)
     assert np.array_equal(idx.cpu().numpy(), ri) and np.array_equal(dist.cpu().numpy(), rd)
     qi, ti = tv.ratio_filter(ri, rd)
@@ -95,14 +122,19 @@ def test_knn2_8k_matches_cv2(ops):
     assert np.array_equal(idx.cpu().numpy(), ri) and np.array_equal(dist.cpu().numpy(), rd)
 
 
-def test_knn2_batched_ragged(ops):
+@pytest.mark.parametrize("variant", [11, 16])
+def test_knn2_batched_ragged(ops, variant):
     F, N = 5, 700
     rng = np.random.default_rng(5)
     des = rng.integers(0, 256, (F, N, 32), dtype=np.uint8)
     cnt = np.array([700, 650, 3, 512, 699], dtype=np.int32)
     pq = np.array([1, 2, 3, 4, 0, 2], dtype=np.int32)
     pt = np.array([0, 1, 2, 3, 4, 2], dtype=np.int32)
-    idx, dist, keep = ops.knn2_hamming256_batched(des, pq, pt, frame_count=cnt)
+    ops.context(0).set_matcher_config(4, variant, 6)
+    try:
+        idx, dist, keep = ops.knn2_hamming256_batched(des, pq, pt, frame_count=cnt)
+    finally:
+        ops.context(0).set_matcher_config()
     idx, dist = idx.cpu().numpy(), dist.cpu().numpy()
     for b in range(len(pq)):
         nq, nt = cnt[pq[b]], cnt[pt[b]]
@@ -444,7 +476,7 @@ def test_matcher_64k_properties(ops):
         ctx.set_matcher_config(8, 1, 2)
         i2, d2 = ops.knn2_hamming256(q, t)
     finally:
-        ctx.set_matcher_config(4, 11, 6)
+        ctx.set_matcher_config()
     assert np.array_equal(i2.cpu().numpy(), idx) and np.array_equal(d2.cpu().numpy(), dist)
 
 
@@ -596,7 +628,7 @@ def test_knn2_randomised_shapes_and_configs(ops):
     always equal to the stable-argsort oracle."""
     rng = np.random.default_rng(20261019)
     ctx = ops.context(0)
-    variants = [0, 1, 2, 3, 5, 7, 9, 11]
+    variants = [0, 1, 2, 3, 5, 7, 9, 11, 16, 16, 16]
     try:
         for trial in range(24):
             nq = int(rng.integers(1, 1400))
@@ -610,4 +642,4 @@ def test_knn2_randomised_shapes_and_configs(ops):
             assert np.array_equal(idx.cpu().numpy(), ri) and np.array_equal(dist.cpu().numpy(), rd), (trial, nq, nt)
             assert np.array_equal(np.flatnonzero(keep.cpu().numpy()), tv.ratio_filter(ri, rd)[0])
     finally:
-        ctx.set_matcher_config(4, 11, 6)
+        ctx.set_matcher_config()
