@@ -237,7 +237,12 @@ def single_pair_latency(ops, ctx, K, n, H, dev, reps=30):
                                               P(idx), P(dst), P(keep),
                                               C.c_void_p(torch.cuda.current_stream().cuda_stream)), "knn2")
     knn_us = timed(knn, reps)
-    return {"kpts": n, "hypotheses": H, "matches": int(out["m_count"][0]), "inliers": int(out["n_inl"][0]),
+    ctx.set_matcher_config(4, 11, 6)
+    knn_int_us = timed(knn, reps)
+    ctx.set_matcher_config(4, 16, 6)
+    knn_tc_us = timed(knn, reps)
+    ctx.set_matcher_config()
+    return {"matcher_us_int_pipe": knn_int_us, "matcher_us_tensor": knn_tc_us, "kpts": n, "hypotheses": H, "matches": int(out["m_count"][0]), "inliers": int(out["n_inl"][0]),
             "eager_us_per_pair": eager_us, "cuda_graph_us_per_pair": graph_us, "matcher_us": knn_us,
             "matcher_gcmp_s": n * n / knn_us / 1e3}
 
@@ -281,8 +286,8 @@ def run_ours(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     ctx = ops.context(local)
-    if args.knn_r is not None:
-        ctx.set_matcher_config(args.knn_r, args.knn_variant, args.knn_ctas)
+    if args.knn_variant is not None:
+        ctx.set_matcher_config(args.knn_r or 4, args.knn_variant, args.knn_ctas)
     ctx.set_host_chunk(args.host_chunk)
     K = synth.K_640x480
     P = args.pairs
@@ -367,6 +372,20 @@ def run_ours(args):
     k1.record()
     k1.synchronize()
     knn_ms = k0.elapsed_time(k1) / reps
+    # the integer-pipe kernel (the north star's LOP3+POPC design) over the same batch, for its INT32/POPC fraction
+    ctx.set_matcher_config(4, 11, args.knn_ctas)
+    for _ in range(2):
+        knn()
+    k0.record()
+    for _ in range(reps):
+        knn()
+    k1.record()
+    k1.synchronize()
+    knn_int_ms = k0.elapsed_time(k1) / reps
+    if args.knn_variant is not None:
+        ctx.set_matcher_config(args.knn_r or 4, args.knn_variant, args.knn_ctas)
+    else:
+        ctx.set_matcher_config()
     sampler.stop_evt.set()
     sampler.join()
 
@@ -377,8 +396,8 @@ def run_ours(args):
     e2e_outs = ("m_count", "E", "n_inl", "Rt", "poses", "status")
     ctxs = [ctx, _lib.Context(local)]
     for c in ctxs:
-        if args.knn_r is not None:
-            c.set_matcher_config(args.knn_r, args.knn_variant, args.knn_ctas)
+        if args.knn_variant is not None:
+            c.set_matcher_config(args.knn_r or 4, args.knn_variant, args.knn_ctas)
         c.set_host_chunk(args.host_chunk)
     host_out = [None, None]
     h2d = d2h = 0
@@ -434,19 +453,45 @@ def run_ours(args):
     popc_peak = 2.0 * n_sm * peaks.get("sm_max_mhz", 1965.0) * 1e6 / 1e9      # 8 POPC/cmp at 16 lanes/clk/SM
     alg_bytes = P * (2 * N_KPTS * 32 + N_KPTS * 17)                           # descriptors in, idx+dist+keep out
     hbm_gbs = alg_bytes / (knn_ms / 1e3) / 1e9
-    roofline = {
-        "kernel": "knn2_kernel (Hamming kNN-2, LOP3+POPC)", "bound": "int_pipe", "achieved": gcmp_s,
-        "peak": popc_peak, "unit": "Gcmp/s", "frac": gcmp_s / popc_peak,
+    tensor_path = args.knn_variant in (None, -1, 16)
+    gcmp_int = cmp_per_launch / (knn_int_ms / 1e3) / 1e9
+    matcher_int = {
+        "kernel": "knn2_kernel (LOP3+POPC, variant 11), timed alone on the same batch", "gcmp_s": gcmp_int,
+        "ms_per_launch": knn_int_ms, "popc_peak_gcmp_s": popc_peak, "frac_popc_peak": gcmp_int / popc_peak,
         "peak_note": "POPC-pipe bound of the plain 8xPOPC form: 2 cmp/clk/SM x %d SMs x sm_max_mhz (%s); the "
                      "Harley-Seal variant needs 4 POPC/cmp so it may exceed 1.0" % (n_sm, peak_kind),
-        "ms_per_launch": knn_ms, "cmp_per_launch": cmp_per_launch, "sm_mhz_during_run": f_mhz,
-        # dram__bytes_read.sum + dram__bytes_write.sum of this kernel at P=1024 from the committed ncu capture
-        # (profiles/r1_kernels_matcher_score.md: 135.37 MB + 19.37 MB), scaled to this run's P
+        # dram__bytes_read.sum + dram__bytes_write.sum at P=1024 from profiles/r1_kernels_matcher_score.md
         "traffic": 154.74e6 * P / 1024,
-        "hbm": {"achieved": hbm_gbs, "peak": peaks.get("hbm_gbs"), "unit": "GB/s",
-                "frac": hbm_gbs / peaks.get("hbm_gbs", 6650.0), "algorithmic_bytes_per_launch": alg_bytes,
-                "note": "matcher is integer-pipe bound, far below the HBM roofline"},
     }
+    if tensor_path:
+        # one comparison = a 256-term dot product of +-1 values = 512 flop on the e4m3 tensor path
+        tflops = gcmp_s * 512 / 1e3
+        bf16 = peaks.get("bf16_tflops", 2250.0)
+        roofline = {
+            "kernel": "knn2_tc_kernel (tcgen05.mma kind::f8f6f4, e4m3 +-1 operands, f16 accumulate, TMEM top-2 "
+                      "epilogue) + unpack_train_kernel, timed together",
+            "bound": "tensor", "achieved": tflops, "peak": 2.0 * bf16, "unit": "TFLOP/s", "frac": tflops / (2.0 * bf16),
+            "peak_note": "e4m3 runs at twice the bf16 rate: peak = 2 x the %s dense bf16 figure (%.1f TF/s, kernel "
+                         "timed alone -> burst); nominal e4m3 peak 4500 TF/s -> frac %.3f" %
+                         (peak_kind, bf16, tflops / 4500.0),
+            "ms_per_launch": knn_ms, "cmp_per_launch": cmp_per_launch, "gcmp_s": gcmp_s,
+            "x_int32_popc_peak": gcmp_s / popc_peak, "sm_mhz_during_run": f_mhz,
+            # dram bytes of knn2_tc_kernel + unpack_train_kernel at P=1024 (profiles/r1_kernels_tensor_matcher.md)
+            "traffic": TC_TRAFFIC_BYTES_P1024 * P / 1024 if TC_TRAFFIC_BYTES_P1024 else None,
+            "algorithmic_flop_per_launch": cmp_per_launch * 512,
+            "hbm": {"achieved": hbm_gbs, "peak": peaks.get("hbm_gbs"), "unit": "GB/s",
+                    "frac": hbm_gbs / peaks.get("hbm_gbs", 6650.0), "algorithmic_bytes_per_launch": alg_bytes},
+        }
+    else:
+        roofline = {
+            "kernel": "knn2_kernel (Hamming kNN-2, LOP3+POPC)", "bound": "int_pipe", "achieved": gcmp_s,
+            "peak": popc_peak, "unit": "Gcmp/s", "frac": gcmp_s / popc_peak, "peak_note": matcher_int["peak_note"],
+            "ms_per_launch": knn_ms, "cmp_per_launch": cmp_per_launch, "sm_mhz_during_run": f_mhz,
+            "traffic": 154.74e6 * P / 1024,
+            "hbm": {"achieved": hbm_gbs, "peak": peaks.get("hbm_gbs"), "unit": "GB/s",
+                    "frac": hbm_gbs / peaks.get("hbm_gbs", 6650.0), "algorithmic_bytes_per_launch": alg_bytes,
+                    "note": "matcher is integer-pipe bound, far below the HBM roofline"},
+        }
     fp32_peak = n_sm * 128 * 2 * peaks.get("sm_max_mhz", 1965.0) * 1e6 / 1e12
     evals = N_HYP * sum_m
     score_tflops = evals * 36 / (stage_ms["score"] / 1e3) / 1e12
@@ -455,7 +500,8 @@ def run_ours(args):
     kernels = {
         "stage_ms": stage_ms,
         "matcher_in_step": {"gcmp_s": cmp_per_launch / (stage_ms["knn2"] / 1e3) / 1e9,
-                            "frac_popc_peak": cmp_per_launch / (stage_ms["knn2"] / 1e3) / 1e9 / popc_peak},
+                            "x_int32_popc_peak": cmp_per_launch / (stage_ms["knn2"] / 1e3) / 1e9 / popc_peak},
+        "matcher_int_pipe": matcher_int,
         "ransac_score": {"bound": "fp32", "evaluations": evals, "flop_per_evaluation": 36,
                          "achieved_tflops": score_tflops, "peak_tflops": fp32_peak, "frac": score_tflops / fp32_peak,
                          "note": "19 FFMA per (hypothesis, correspondence) = 36 useful flop (two of the FFMA addends are the "
@@ -478,14 +524,15 @@ def run_ours(args):
     line = {
         "metric": "frame pairs/s (2k kpts, match+RANSAC+triangulate)", "value": value, "unit": "pairs/s",
         "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps,
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8 popcount + f32/f64",
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": ("e4m3 (+-1, exact) tensor-core Hamming" if tensor_path else "u8 popcount") + " + f32/f64",
         "data": "synthetic",
         "config": {"workload": "C2: frame pairs 2048x2048 256-bit descriptors, 1024 seeded RANSAC hypotheses, "
                                "triangulate inliers", "pairs_per_step_per_gpu": P, "kpts": N_KPTS, "hypotheses": N_HYP,
                    "l2_policy": "inputs larger than L2 (%.0f MB of descriptors+keypoints per step)" %
                                 ((des_h.nbytes + kps_h.nbytes) / 1e6),
-                   "matcher": {"r": args.knn_r or "auto (4 batched / 2 when train rows are split)",
-                               "variant": args.knn_variant, "ctas_per_sm": args.knn_ctas}},
+                   "matcher": {"variant": "auto -> 16 (tensor cores) for this batch" if args.knn_variant is None
+                               else args.knn_variant, "r": args.knn_r, "ctas_per_sm": args.knn_ctas}},
         "hamming_gcmp_s": gcmp_s * world, "clocks": clocks, "gpu_launches": int(launches),
         "e2e": {"value": e2e_value, "unit": "pairs/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                 "steps": e2e_steps, "mode": "tvg_pairs_host_submit/_wait, 2 contexts alternating"},
@@ -498,6 +545,10 @@ def run_ours(args):
     return 0
 
 
+# dram__bytes_read.sum + dram__bytes_write.sum of knn2_tc_kernel + unpack_train_kernel at P = 1024 (ncu --set full)
+TC_TRAFFIC_BYTES_P1024 = None
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -506,7 +557,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--pairs", type=int, default=1024, help="frame pairs per step per GPU")
     ap.add_argument("--knn-r", type=int, default=None, help="matcher queries/thread (default: library auto)")
-    ap.add_argument("--knn-variant", type=int, default=11)
+    ap.add_argument("--knn-variant", type=int, default=None,
+                    help="matcher variant (default: library auto; 16 = tensor cores, 0..11 = integer-pipe variants)")
     ap.add_argument("--knn-ctas", type=int, default=6)
     ap.add_argument("--host-chunk", type=int, default=4096,
                     help="pairs per chunk of the e2e host pipeline (streaming mode overlaps across batches, so large)")
