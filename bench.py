@@ -546,7 +546,7 @@ def run_ours(args):
 
 
 # dram__bytes_read.sum + dram__bytes_write.sum of knn2_tc_kernel + unpack_train_kernel at P = 1024 (ncu --set full)
-TC_TRAFFIC_BYTES_P1024 = None
+TC_TRAFFIC_BYTES_P1024 = 640.28e6 + 544.97e6   # profiles/r1_kernels_tensor_matcher.md
 
 
 def main():

@@ -145,6 +145,9 @@ constexpr int TN = 256;                       // MMA N = train rows per tile
 constexpr int A_BLK = QB * KBYTES;            // 32 KB
 constexpr int B_TILE = TN * KBYTES;           // 64 KB
 constexpr int NST = 2;
+#ifndef TMA_PARTS
+#define TMA_PARTS 4
+#endif
 constexpr int THREADS2 = 32 * (2 + 4 * NQB);  // warp 0 TMA, warp 1 MMA, 8 epilogue warps
 constexpr uint32_t IDESC2 = (0u << 4) | ((uint32_t)(TN >> 3) << 17) | ((uint32_t)(QB >> 4) << 24);   // f16 accumulate
 constexpr int SMEM2 = NQB * A_BLK + NST * B_TILE + 256;
@@ -201,7 +204,10 @@ __global__ void __launch_bounds__(THREADS2, 1) knn_tc_kernel(Params p) {
                 mbar_wait(empty + s, ph ^ 1, 2);
                 if (elect_one()) {
                     mbar_expect_tx(full + s, B_TILE);
-                    tma_load_1d(b_smem + s * B_TILE, p.ut + ((size_t)b * p.n_pad + (size_t)j * TN) * KBYTES, B_TILE, full + s);
+                    for (int part = 0; part < TMA_PARTS; ++part)
+                        tma_load_1d(b_smem + s * B_TILE + part * (B_TILE / TMA_PARTS),
+                                    p.ut + ((size_t)b * p.n_pad + (size_t)j * TN) * KBYTES + part * (B_TILE / TMA_PARTS),
+                                    B_TILE / TMA_PARTS, full + s);
                 }
                 __syncwarp();
             }
