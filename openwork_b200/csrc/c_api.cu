@@ -689,6 +689,10 @@ int tvg_pairs_host_submit(tvg_ctx* ctx, const tvg_pairs_io* hio, int frames, lon
         int rc0 = ctx->reserve_pinned(want);
         if (rc0) return rc0;
     }
+    // every host->device copy of this call goes through s_in (in order: small arrays, then the frame chunks), so a
+    // copy never queues behind the previous batch's kernels on the caller's stream
+    if (!ctx->s_in) TVG_CUDA(cudaStreamCreateWithFlags(&ctx->s_in, cudaStreamNonBlocking));
+    if (!ctx->s_out) TVG_CUDA(cudaStreamCreateWithFlags(&ctx->s_out, cudaStreamNonBlocking));
 #define TVG_UP(slot, hptr, bytes, field, type)                                              \
     do {                                                                                    \
         if (hptr) {                                                                         \
@@ -699,7 +703,7 @@ int tvg_pairs_host_submit(tvg_ctx* ctx, const tvg_pairs_io* hio, int frames, lon
                 void* st__ = ctx->stage(src__, (bytes));                                    \
                 if (st__) src__ = st__;                                                     \
             }                                                                               \
-            TVG_CUDA(cudaMemcpyAsync((void*)dp__, src__, (bytes), cudaMemcpyHostToDevice, st)); \
+            TVG_CUDA(cudaMemcpyAsync((void*)dp__, src__, (bytes), cudaMemcpyHostToDevice, ctx->s_in)); \
             h2d += (long long)(bytes);                                                      \
             field = dp__;                                                                   \
         }                                                                                   \
@@ -744,8 +748,6 @@ int tvg_pairs_host_submit(tvg_ctx* ctx, const tvg_pairs_io* hio, int frames, lon
     TVG_GET(ctx, S_MASK, B * N, mask, uint8_t*);
     TVG_GET(ctx, S_GOOD, B * N, good, uint8_t*);
     // ---- chunked schedule: frame copies (stream s_in), kernels (caller's stream), result copies (s_out)
-    if (!ctx->s_in) TVG_CUDA(cudaStreamCreateWithFlags(&ctx->s_in, cudaStreamNonBlocking));
-    if (!ctx->s_out) TVG_CUDA(cudaStreamCreateWithFlags(&ctx->s_out, cudaStreamNonBlocking));
     // chunk boundaries: ramp up (C/4, C/2, C, C, ...) so the first kernels start after a short first copy
     const int C = ctx->host_chunk_pairs;
     std::vector<int> cb(1, 0);
@@ -783,7 +785,7 @@ int tvg_pairs_host_submit(tvg_ctx* ctx, const tvg_pairs_io* hio, int frames, lon
     TVG_GET(ctx, S_H_SEQOFF, so_all.size() * sizeof(int32_t), so_d, int32_t*);
     {
         const void* src = ctx->stage(so_all.data(), so_all.size() * sizeof(int32_t));
-        TVG_CUDA(cudaMemcpyAsync(so_d, src ? src : so_all.data(), so_all.size() * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+        TVG_CUDA(cudaMemcpyAsync(so_d, src ? src : so_all.data(), so_all.size() * sizeof(int32_t), cudaMemcpyHostToDevice, ctx->s_in));
     }
     h2d += (long long)((size_t)(nseq + 1) * sizeof(int32_t));
     // The frame copies read HOST buffers and write this context's private staging pool, which nothing else
