@@ -180,6 +180,19 @@ TVG_API int tvg_extract_points(tvg_ctx* ctx, const uint8_t* images, int batch, i
                        int max_corners, double quality_level, double min_distance, const int8_t* pattern_host,
                        double* kps, uint8_t* des, int32_t* n_kps, int32_t* n_candidates, void* stream);
 
+/* Two-view bundle adjustment per pair -- the back-end step slam.py:267 leaves as a TODO ("g2o bundle adjustment");
+ * no reference behaviour, specification = oracle/bundle.py.  Levenberg-Marquardt (Marquardt scaling, lambda0, a step is
+ * accepted iff the cost decreases: lambda /= 10, else *= 10; exactly `iters` iterations) on the squared reprojection
+ * error in normalised image coordinates over the SECOND view's pose (6-DoF left twist; the first view is fixed) and
+ * the points (eliminated by the Schur complement).  pose1 / pose2: camera-to-world 4x4 per pair (the reference's
+ * `pose`, slam.py:261) at strides pose*_stride doubles; pose2 and points4d f64[batch][n_max][4] are refined in place.
+ * pix1 / pix2 f64[batch][n_max][2] pixels; n_pts int32[batch] (NULL -> n); use u8[batch][n_max] (NULL -> all points).
+ * cost f64[batch][2] = initial / final cost; accepted int32[batch] (may be NULL) = accepted steps. */
+TVG_API int tvg_bundle_adjust_pairs(tvg_ctx* ctx, const double* pix1, const double* pix2, int batch, int n_max, int n,
+                            const int32_t* n_pts, const uint8_t* use, const double* kinv_host, const double* pose1,
+                            long long pose1_stride, double* pose2, long long pose2_stride, double* points4d,
+                            int iters, double lambda0, double* cost, int32_t* accepted, void* stream);
+
 /* Cheirality vote over the four (R, +-t) decompositions of E (north-star extra; the reference uses the
  * trace / t_z heuristics of slam.py:174-181 instead).  votes int32[batch][4], Rts f64[batch][4][16],
  * choice int32[batch].  mask may be NULL. */

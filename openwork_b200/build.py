@@ -15,7 +15,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT_DIR = os.path.join(HERE, "_lib")
 LIB = os.path.join(OUT_DIR, "libtvg_b200.so")
-SOURCES = ["hamming_knn2.cu", "hamming_tc.cu", "compact.cu", "ransac.cu", "pose_tri.cu", "frontend.cu", "c_api.cu"]
+SOURCES = ["hamming_knn2.cu", "hamming_tc.cu", "compact.cu", "ransac.cu", "pose_tri.cu", "bundle.cu", "frontend.cu", "c_api.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden"]
 

@@ -37,7 +37,7 @@ enum Slot {
     S_FE_CORNERS, S_FE_NCORNERS, S_FE_BLURTMP, S_FE_BLUR,
     // host-entry staging
     S_H_DES, S_H_KPS, S_H_FCOUNT, S_H_PAIRQ, S_H_PAIRT, S_H_SEQOFF, S_H_INIT, S_H_WORDS, S_H_SAMPLES,
-    S_KNN_TC,
+    S_KNN_TC, S_BA_TRIAL,
     S_NUM
 };
 
@@ -449,6 +449,30 @@ int tvg_point_quality(tvg_ctx* ctx, const double* pix1, const double* pix2, int 
     memcpy(p.kinv, kinv_host, sizeof(p.kinv));
     p.points4d = points4d; p.good = good; p.reproj = reproj; p.parallax_cos = parallax_cos; p.focal = focal;
     TVG_CUDA(tvg::launch_triangulate(p, batch, (cudaStream_t)stream));
+    ctx->launches += 1;
+    return 0;
+}
+
+int tvg_bundle_adjust_pairs(tvg_ctx* ctx, const double* pix1, const double* pix2, int batch, int n_max, int n,
+                            const int32_t* n_pts, const uint8_t* use, const double* kinv_host, const double* pose1,
+                            long long pose1_stride, double* pose2, long long pose2_stride, double* points4d,
+                            int iters, double lambda0, double* cost, int32_t* accepted, void* stream) {
+    if (!ctx) return fail(-1, "ctx is NULL");
+    if (batch < 0 || n_max < 0 || n < 0 || n > n_max || iters < 0 || !(lambda0 > 0.0))
+        return fail(-2, "tvg_bundle_adjust_pairs: bad sizes / iters / lambda0");
+    if (batch == 0) return 0;
+    if (!pix1 || !pix2 || !kinv_host || !pose1 || !pose2 || !points4d || !cost)
+        return fail(-3, "tvg_bundle_adjust_pairs: NULL array");
+    if (!aligned16(pix1) || !aligned16(pix2)) return fail(-4, "tvg_bundle_adjust_pairs: pix arrays must be 16-byte aligned");
+    DeviceGuard g(ctx->device);
+    tvg::BundleParams p{};
+    p.pix1 = pix1; p.pix2 = pix2; p.n_pts = n_pts; p.use = use; p.n_max = n_max; p.n = n; p.iters = iters;
+    p.lambda0 = lambda0;
+    memcpy(p.kinv, kinv_host, sizeof(p.kinv));
+    p.pose1 = pose1; p.pose2 = pose2; p.pose1_stride = pose1_stride; p.pose2_stride = pose2_stride;
+    p.points4d = points4d; p.cost = cost; p.accepted = accepted;
+    TVG_GET(ctx, S_BA_TRIAL, (size_t)batch * (n_max > 0 ? n_max : 1) * 3 * sizeof(double), p.trial, double*);
+    TVG_CUDA(tvg::launch_bundle_pairs(p, batch, (cudaStream_t)stream));
     ctx->launches += 1;
     return 0;
 }

@@ -137,6 +137,25 @@ struct TriParams {
 cudaError_t launch_triangulate(const TriParams& p, int batch, cudaStream_t stream);
 cudaError_t launch_invert4(const double* in, double* out, int n, cudaStream_t stream);
 
+// ---------------------------------------------------------------- two-view bundle adjustment (bundle.cu)
+struct BundleParams {
+    const double* pix1;        // [batch][n_max][2] pixel coords in the first / second view
+    const double* pix2;
+    const int32_t* n_pts;      // [batch] (NULL -> n)
+    const uint8_t* use;        // [batch][n_max] points that take part (NULL -> all)
+    int n_max, n, iters;
+    double lambda0;
+    double kinv[9];
+    const double* pose1;       // 4x4 camera-to-world pose of the first view per pair (fixed)
+    double* pose2;             // second view, refined in place
+    long long pose1_stride, pose2_stride;
+    double* points4d;          // [batch][n_max][4], refined in place (w stays 1)
+    double* trial;             // [batch][n_max][3] scratch
+    double* cost;              // [batch][2] initial / final sum of squared reprojection errors (normalised coords)
+    int32_t* accepted;         // [batch] accepted steps (may be NULL)
+};
+cudaError_t launch_bundle_pairs(const BundleParams& p, int batch, cudaStream_t stream);
+
 struct MapParams {
     const double* points4d;    // [batch][n_max][4]
     const uint8_t* good;       // [batch][n_max]

@@ -450,6 +450,32 @@ def cheirality(E, src, dst, mask=None, ctx=None):
     return votes, Rts.view(4, 4, 4), int(choice.item())
 
 
+def bundle_adjust_pairs(pix1, pix2, pose1, pose2, points4d, K, n_pts=None, use=None, iters=10, lambda0=1e-3, ctx=None):
+    """Two-view bundle adjustment per pair (the `g2o bundle adjustment` TODO at slam.py:267; spec: oracle/bundle.py).
+
+    pix1 / pix2 f64[B,N,2] pixels of the same points in the first / second view, pose1 / pose2 f64[B,4,4]
+    camera-to-world (the reference's `pose`), points4d f64[B,N,4].  Returns (pose2_refined, points4d_refined,
+    cost f64[B,2] = initial / final, accepted int32[B]); inputs are not modified."""
+    dev = _device_of(pix1, pix2, points4d)
+    pix1 = _dev(pix1, torch.float64, dev).contiguous()
+    pix2 = _dev(pix2, torch.float64, dev).contiguous()
+    B, N = pix1.shape[0], pix1.shape[1]
+    pose1 = _dev(pose1, torch.float64, dev).reshape(B, 16).contiguous()
+    pose2 = _dev(pose2, torch.float64, dev).reshape(B, 16).clone()
+    pts = _dev(points4d, torch.float64, dev).reshape(B, N, 4).clone()
+    cnt = None if n_pts is None else _dev(n_pts, torch.int32, dev).contiguous()
+    u8 = None if use is None else _dev(use, None, dev).to(torch.uint8).contiguous()
+    kinv = np.ascontiguousarray(np.linalg.inv(np.asarray(K, dtype=np.float64)))
+    ctx = ctx or context(dev.index)
+    cost = torch.zeros((B, 2), dtype=torch.float64, device=dev)
+    acc = torch.zeros(B, dtype=torch.int32, device=dev)
+    check(ctx.lib.tvg_bundle_adjust_pairs(ctx.handle, _p(pix1), _p(pix2), B, N, N, _p(cnt), _p(u8),
+                                          kinv.ctypes.data_as(C.c_void_p), _p(pose1), 16, _p(pose2), 16, _p(pts),
+                                          int(iters), float(lambda0), _p(cost), _p(acc), _stream()),
+          "tvg_bundle_adjust_pairs")
+    return pose2.view(B, 4, 4), pts, cost, acc
+
+
 def _np(x):
     return x.detach().cpu().numpy() if isinstance(x, torch.Tensor) else np.asarray(x)
 

@@ -86,6 +86,32 @@ def test_knn2_extreme_distances(ops, variant):
     assert np.array_equal(idx.cpu().numpy(), ri) and np.array_equal(dist.cpu().numpy(), rd)
 
 
+@pytest.mark.parametrize("variant", [11, 16])
+def test_knn2_batched_with_empty_frames(ops, variant):
+    """Frames with zero rows on either side of a pair (the persistent tensor-core kernel skips such items)."""
+    F, N = 6, 600
+    rng = np.random.default_rng(77)
+    des = rng.integers(0, 256, (F, N, 32), dtype=np.uint8)
+    cnt = np.array([600, 0, 1, 300, 0, 599], dtype=np.int32)
+    pq = np.array([0, 1, 2, 3, 5, 4, 0, 3], dtype=np.int32)
+    pt = np.array([1, 0, 0, 2, 4, 5, 5, 0], dtype=np.int32)
+    ops.context(0).set_matcher_config(4, variant, 6)
+    try:
+        idx, dist, keep = ops.knn2_hamming256_batched(des, pq, pt, frame_count=cnt)
+    finally:
+        ops.context(0).set_matcher_config()
+    idx, dist, keep = idx.cpu().numpy(), dist.cpu().numpy(), keep.cpu().numpy()
+    for b in range(len(pq)):
+        nq, nt = cnt[pq[b]], cnt[pt[b]]
+        if nq == 0:
+            continue
+        if nt == 0:
+            assert (idx[b, :nq] == -1).all() and (dist[b, :nq] == -1).all() and not keep[b, :nq].any()
+            continue
+        ri, rd = tv.knn2_numpy(des[pq[b], :nq], des[pt[b], :nt])
+        assert np.array_equal(idx[b, :nq], ri) and np.array_equal(dist[b, :nq], rd), b
+
+
 def test_knn2_empty(ops):
     q = np.zeros((0, 32), dtype=np.uint8)
     t = np.zeros((10, 32), dtype=np.uint8)
