@@ -248,8 +248,11 @@ int tvg_knn2_hamming256(tvg_ctx* ctx, const uint8_t* q_des, const uint8_t* t_des
     if (use_tc) {
         uint8_t* ws = nullptr;
         TVG_GET(ctx, S_KNN_TC, tvg::knn2_tc_workspace_bytes(batch, n_max), ws, uint8_t*);
-        TVG_CUDA(tvg::launch_knn2_tc(p, batch, q_rows_tc, ws, ctx->sm_count, (cudaStream_t)stream));
-        ctx->launches += t_rows_tc > 0 ? 2 : 1;
+        const int tc_splits = tvg::knn2_tc_splits(batch, q_rows_tc, n_max, ctx->sm_count);
+        if (tc_splits > 1) TVG_GET(ctx, S_PARTIAL, (size_t)batch * n_max * tc_splits * sizeof(uint2), p.partial, uint2*);
+        int nl = 0;
+        TVG_CUDA(tvg::launch_knn2_tc(p, batch, q_rows_tc, ws, ctx->sm_count, &nl, (cudaStream_t)stream));
+        ctx->launches += nl;
         return 0;
     }
     // queries per thread: 4 for big batches; when the grid has to be filled by splitting the train rows

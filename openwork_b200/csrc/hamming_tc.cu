@@ -103,6 +103,9 @@ struct TcArgs {
     KnnParams k;
     uint8_t* unpacked;     // [batch][n_pad][256] e4m3 train rows in core-matrix order
     int n_pad, batch, qis, items;
+    int splits, tiles_per_split;   // train tiles of a pair are cut into `splits` ranges (one item each) when the
+                                   // (pair, query block) items alone cannot fill the SMs; partial top-2s are merged
+                                   // by knn2_tc_merge_kernel
 };
 
 __device__ __forceinline__ void tc_counts(const TcArgs& a, int b, int& fq, int& ft, int& nq, int& nt) {
@@ -172,21 +175,25 @@ __global__ void __launch_bounds__(TC_THREADS, 1) knn2_tc_kernel(TcArgs a) {
     const uint32_t tmem_base = *tmem_slot;
 
     // An item is live when it has query rows and the pair has train rows; every role walks the same item sequence.
-    auto item_info = [&](int item, int& b, int& qi, int& fq, int& nq, int& nt) -> bool {
-        b = item / a.qis;
-        qi = item % a.qis;
+    auto item_info = [&](int item, int& b, int& qi, int& fq, int& nq, int& nt, int& j0, int& j1) -> bool {
+        const int sp = item % a.splits;
+        const int rest = item / a.splits;
+        b = rest / a.qis;
+        qi = rest % a.qis;
         int ft;
         tc_counts(a, b, fq, ft, nq, nt);
-        return qi * TC_QI < nq && nt > 0;
+        const int ttiles = (nt + TC_TN - 1) / TC_TN;
+        j0 = sp * a.tiles_per_split;
+        j1 = min(ttiles, j0 + a.tiles_per_split);
+        return qi * TC_QI < nq && j0 < j1;
     };
 
     if (warp == 0) {
         uint32_t step = 0;
         for (int item = blockIdx.x; item < a.items; item += gridDim.x) {
-            int b, qi, fq, nq, nt;
-            if (!item_info(item, b, qi, fq, nq, nt)) continue;
-            const int ttiles = (nt + TC_TN - 1) / TC_TN;
-            for (int j = 0; j < ttiles; ++j, ++step) {
+            int b, qi, fq, nq, nt, j0, j1;
+            if (!item_info(item, b, qi, fq, nq, nt, j0, j1)) continue;
+            for (int j = j0; j < j1; ++j, ++step) {
                 const uint32_t s = step % TC_NST, ph = (step / TC_NST) & 1;
                 tc_mbar_wait(empty + s, ph ^ 1);
                 if (tc_elect_one()) {
@@ -200,17 +207,16 @@ __global__ void __launch_bounds__(TC_THREADS, 1) knn2_tc_kernel(TcArgs a) {
     } else if (warp == 1) {
         uint32_t step = 0, it = 0;
         for (int item = blockIdx.x; item < a.items; item += gridDim.x) {
-            int b, qi, fq, nq, nt;
-            if (!item_info(item, b, qi, fq, nq, nt)) continue;
-            const int ttiles = (nt + TC_TN - 1) / TC_TN;
-            for (int j = 0; j < ttiles; ++j, ++step) {
+            int b, qi, fq, nq, nt, j0, j1;
+            if (!item_info(item, b, qi, fq, nq, nt, j0, j1)) continue;
+            for (int j = j0; j < j1; ++j, ++step) {
                 const uint32_t s = step % TC_NST, ph = (step / TC_NST) & 1;
                 tc_mbar_wait(full + s, ph);
                 tc_fence_after();
                 const uint64_t b_desc = tc_smem_desc(smem_u32(b_smem + s * TC_B_TILE));
 #pragma unroll
                 for (int h = 0; h < TC_NQB; ++h) {
-                    if (j == 0) tc_mbar_wait(a_full + h, it & 1);
+                    if (j == j0) tc_mbar_wait(a_full + h, it & 1);
                     tc_mbar_wait(acc_empty + h, (step & 1) ^ 1);
                     tc_fence_after();
                     const uint64_t a_desc = tc_smem_desc(smem_u32(a_smem + h * TC_A_BLK));
@@ -255,8 +261,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) knn2_tc_kernel(TcArgs a) {
         };
         auto next_live = [&](int item, int& fq, int& nq, int& qi) -> bool {
             for (item += gridDim.x; item < a.items; item += gridDim.x) {
-                int b, nt;
-                if (item_info(item, b, qi, fq, nq, nt)) return true;
+                int b, nt, j0, j1;
+                if (item_info(item, b, qi, fq, nq, nt, j0, j1)) return true;
             }
             return false;
         };
@@ -266,11 +272,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) knn2_tc_kernel(TcArgs a) {
             if (next_live((int)blockIdx.x - (int)gridDim.x, fq, nq, qi)) write_a(fq, nq, qi);
         }
         for (int item = blockIdx.x; item < a.items; item += gridDim.x) {
-            int b, qi, fq, nq, nt;
-            const bool live = item_info(item, b, qi, fq, nq, nt);
+            int b, qi, fq, nq, nt, j0, j1;
+            const bool live = item_info(item, b, qi, fq, nq, nt, j0, j1);
             uint32_t g1 = TVG_SENTINEL_KEY, g2 = TVG_SENTINEL_KEY;       // dist << 23 | train idx
-            const int ttiles = live ? (nt + TC_TN - 1) / TC_TN : 0;
-            for (int j = 0; j < ttiles; ++j, ++use) {
+            if (!live) j1 = j0;
+            for (int j = j0; j < j1; ++j, ++use) {
                 tc_mbar_wait(acc_full + h, use & 1);
                 tc_fence_after();
                 uint32_t v[4][32];
@@ -282,7 +288,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) knn2_tc_kernel(TcArgs a) {
                 __syncwarp();
                 if (lane == 0) tc_mbar_arrive(acc_empty + h);
                 // last tile of the item: every MMA that read this A block is complete -> stage the next item's rows
-                if (j == ttiles - 1) {
+                if (j == j1 - 1) {
                     int fq2, nq2, qi2;
                     if (next_live(item, fq2, nq2, qi2)) write_a(fq2, nq2, qi2);
                 }
@@ -332,7 +338,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) knn2_tc_kernel(TcArgs a) {
                 }
             }
             const int q = qi * TC_QI + h * TC_QB + row_in_blk;
-            if (q < nq) tc_emit(p, (size_t)b * p.n_max + q, g1, g2);
+            if (q < nq) {
+                if (a.splits == 1) tc_emit(p, (size_t)b * p.n_max + q, g1, g2);
+                else p.partial[((size_t)b * p.n_max + q) * a.splits + item % a.splits] = make_uint2(g1, g2);
+            }
         }
     }
     tc_fence_before();
@@ -343,6 +352,23 @@ __global__ void __launch_bounds__(TC_THREADS, 1) knn2_tc_kernel(TcArgs a) {
     }
 }
 
+// split-Nt: fold the per-split partial top-2s of one query (thread = query) and emit
+__global__ void __launch_bounds__(256) knn2_tc_merge_kernel(TcArgs a) {
+    const int b = blockIdx.y, q = blockIdx.x * blockDim.x + threadIdx.x;
+    int fq, ft, nq, nt;
+    tc_counts(a, b, fq, ft, nq, nt);
+    if (q >= nq) return;
+    const int ttiles = (nt + TC_TN - 1) / TC_TN;
+    const int used = (ttiles + a.tiles_per_split - 1) / a.tiles_per_split;   // splits that held tiles for this pair
+    uint32_t g1 = TVG_SENTINEL_KEY, g2 = TVG_SENTINEL_KEY;
+    const uint2* part = a.k.partial + ((size_t)b * a.k.n_max + q) * a.splits;
+    for (int sp = 0; sp < used; ++sp) {
+        const uint2 v = part[sp];
+        top2_merge(g1, g2, v.x, v.y);
+    }
+    tc_emit(a.k, (size_t)b * a.k.n_max + q, g1, g2);
+}
+
 }  // namespace
 
 size_t knn2_tc_workspace_bytes(int batch, int n_max) {
@@ -350,7 +376,20 @@ size_t knn2_tc_workspace_bytes(int batch, int n_max) {
     return (size_t)batch * n_pad * TC_KB;
 }
 
-cudaError_t launch_knn2_tc(const KnnParams& p, int batch, int q_rows, uint8_t* workspace, int sm_count, cudaStream_t stream) {
+int knn2_tc_splits(int batch, int q_rows, int n_max, int sm_count) {
+    const int qis = (q_rows + TC_QI - 1) / TC_QI > 0 ? (q_rows + TC_QI - 1) / TC_QI : 1;
+    const long long base = (long long)batch * qis;
+    const int ttiles = (n_max + TC_TN - 1) / TC_TN;
+    long long splits = base >= sm_count ? 1 : sm_count / base;
+    if (splits > ttiles) splits = ttiles;
+    if (splits < 1) splits = 1;
+    const int tps = (ttiles + (int)splits - 1) / (int)splits;
+    return tps > 0 ? (ttiles + tps - 1) / tps : 1;
+}
+
+// p.partial must hold batch * n_max * splits uint2 when splits = knn2_tc_splits(...) > 1
+cudaError_t launch_knn2_tc(const KnnParams& p, int batch, int q_rows, uint8_t* workspace, int sm_count, int* launches,
+                           cudaStream_t stream) {
     TcArgs a{};
     a.k = p;
     a.unpacked = workspace;
@@ -358,16 +397,28 @@ cudaError_t launch_knn2_tc(const KnnParams& p, int batch, int q_rows, uint8_t* w
     a.batch = batch;
     a.qis = (q_rows + TC_QI - 1) / TC_QI;
     if (a.qis < 1) a.qis = 1;
-    a.items = batch * a.qis;
+    a.splits = knn2_tc_splits(batch, q_rows, p.n_max, sm_count);
+    const int ttiles = (p.n_max + TC_TN - 1) / TC_TN;
+    a.tiles_per_split = (ttiles + a.splits - 1) / a.splits;
+    if (a.tiles_per_split < 1) a.tiles_per_split = 1;
+    a.items = batch * a.qis * a.splits;
+    *launches = 0;
     const int t_rows = p.t_count ? p.n_max : p.nt;
     if (t_rows > 0) {
         dim3 ug((unsigned)(((size_t)a.n_pad * 16 + 255) / 256), (unsigned)batch);
         unpack_train_kernel<<<ug, 256, 0, stream>>>(a);
+        ++*launches;
     }
     cudaError_t e = cudaFuncSetAttribute(knn2_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM);
     if (e != cudaSuccess) return e;
     const int grid = a.items < sm_count ? a.items : sm_count;
     knn2_tc_kernel<<<grid, TC_THREADS, TC_SMEM, stream>>>(a);
+    ++*launches;
+    if (a.splits > 1) {
+        dim3 mg((unsigned)((q_rows + 255) / 256 > 0 ? (q_rows + 255) / 256 : 1), (unsigned)batch);
+        knn2_tc_merge_kernel<<<mg, 256, 0, stream>>>(a);
+        ++*launches;
+    }
     return cudaGetLastError();
 }
 
