@@ -372,6 +372,19 @@ def run_ours(args):
     k1.record()
     k1.synchronize()
     knn_ms = k0.elapsed_time(k1) / reps
+    # the tensor-core matcher's L2-resident mode (sub-batches whose e4m3 expansion never leaves L2)
+    knn_l2_ms = None
+    if args.knn_variant in (None, -1, 16):
+        ctx.set_matcher_l2_budget(40 << 20)
+        for _ in range(2):
+            knn()
+        k0.record()
+        for _ in range(reps):
+            knn()
+        k1.record()
+        k1.synchronize()
+        knn_l2_ms = k0.elapsed_time(k1) / reps
+        ctx.set_matcher_l2_budget(0)
     # the integer-pipe kernel (the north star's LOP3+POPC design) over the same batch, for its INT32/POPC fraction
     ctx.set_matcher_config(4, 11, args.knn_ctas)
     for _ in range(2):
@@ -476,8 +489,14 @@ def run_ours(args):
                          (peak_kind, bf16, tflops / 4500.0),
             "ms_per_launch": knn_ms, "cmp_per_launch": cmp_per_launch, "gcmp_s": gcmp_s,
             "x_int32_popc_peak": gcmp_s / popc_peak, "sm_mhz_during_run": f_mhz,
-            # dram bytes of knn2_tc_kernel + unpack_train_kernel at P=1024 (profiles/r1_kernels_tensor_matcher.md)
+            # dram bytes of knn2_tc_kernel + unpack_train_kernel at P=1024 (profiles/r1_tensor_matcher_dram_traffic.md)
             "traffic": TC_TRAFFIC_BYTES_P1024 * P / 1024 if TC_TRAFFIC_BYTES_P1024 else None,
+            "traffic_note": "7x the algorithmic bytes: the e4m3 expansion of the train side (512 KB per pair) is written "
+                            "and read back once; 20 % of HBM peak, the kernel is tensor-pipe bound",
+            "l2_resident_mode": {"ms_per_launch": knn_l2_ms, "gcmp_s": cmp_per_launch / (knn_l2_ms / 1e3) / 1e9,
+                                 "traffic": TC_TRAFFIC_L2MODE_BYTES_P1024 * P / 1024,
+                                 "note": "tvg_set_matcher_l2_budget(40 MiB): sub-batches whose expansion stays in L2; DRAM "
+                                         "traffic = the algorithmic bytes, more launches"} if knn_l2_ms else None,
             "algorithmic_flop_per_launch": cmp_per_launch * 512,
             "hbm": {"achieved": hbm_gbs, "peak": peaks.get("hbm_gbs"), "unit": "GB/s",
                     "frac": hbm_gbs / peaks.get("hbm_gbs", 6650.0), "algorithmic_bytes_per_launch": alg_bytes},
@@ -546,7 +565,8 @@ def run_ours(args):
 
 
 # dram__bytes_read.sum + dram__bytes_write.sum of knn2_tc_kernel + unpack_train_kernel at P = 1024 (ncu --set full)
-TC_TRAFFIC_BYTES_P1024 = 640.28e6 + 544.97e6   # profiles/r1_kernels_tensor_matcher.md
+TC_TRAFFIC_BYTES_P1024 = 671.3e6 + 571.7e6        # default mode, ncu --cache-control none (profiles/r1_tensor_matcher_dram_traffic.md)
+TC_TRAFFIC_L2MODE_BYTES_P1024 = 133.9e6 + 39.4e6   # L2-resident mode, 40 MiB budget
 
 
 def main():

@@ -50,6 +50,10 @@ TVG_API long long tvg_launch_count(const tvg_ctx* ctx);
  * 16-bit keys packed per register (VIMNMX.U16x2 top-2 updates); ctas_per_sm sizes the split-Nt grid.
  * Results are bit-identical for every setting. */
 TVG_API int tvg_set_matcher_config(tvg_ctx* ctx, int r, int variant, int ctas_per_sm);
+/* Tensor-core matcher only.  bytes = 0 (default): the e4m3 expansion of all train frames of a call is written once and
+ * read back (fastest; 7x the algorithmic DRAM traffic, 20 % of HBM peak).  bytes > 0: the call is processed in
+ * sub-batches whose expansion fits in `bytes` of L2 (40 MiB measured: DRAM traffic = the algorithmic bytes, +8 % time). */
+TVG_API int tvg_set_matcher_l2_budget(tvg_ctx* ctx, long long bytes);
 
 /* cv2.BFMatcher(cv2.NORM_HAMMING).knnMatch(q, t, k=2)  (slam.py:126-127) + the Lowe ratio flag
  * m.distance < ratio * n.distance (slam.py:131).

@@ -76,6 +76,7 @@ SIGNATURES = {
                                           C.c_longlong, c_vp, C.c_longlong, c_vp, C.c_int, C.c_double, c_vp, c_vp, c_vp]),
     "tvg_pairs_device": (C.c_int, [c_vp, C.POINTER(PairsIO), c_vp]),
     "tvg_set_host_chunk": (C.c_int, [c_vp, C.c_int]),
+    "tvg_set_matcher_l2_budget": (C.c_int, [c_vp, C.c_longlong]),
     "tvg_set_profile": (C.c_int, [c_vp, C.c_int]),
     "tvg_get_stage_ms": (C.c_int, [c_vp, c_f32p, C.c_int]),
     "tvg_pairs_host": (C.c_int, [c_vp, C.POINTER(PairsIO), C.c_int, C.POINTER(C.c_longlong),
@@ -156,6 +157,9 @@ class Context:
         buf = (C.c_float * 9)()
         check(self.lib.tvg_get_stage_ms(self.handle, buf, 9), "tvg_get_stage_ms")
         return dict(zip(self.STAGES, [float(v) for v in buf]))
+
+    def set_matcher_l2_budget(self, nbytes=0):
+        check(self.lib.tvg_set_matcher_l2_budget(self.handle, int(nbytes)), "tvg_set_matcher_l2_budget")
 
     def set_host_chunk(self, pairs=256):
         check(self.lib.tvg_set_host_chunk(self.handle, int(pairs)), "tvg_set_host_chunk")

@@ -53,6 +53,7 @@ struct tvg_ctx {
     int device = 0;
     int sm_count = 148;
     int knn_r = 4, knn_variant = 11, knn_ctas_per_sm = 6;
+    size_t knn_tc_l2_budget = 0;   // 0 = one unpack + one match launch per call; > 0 = L2-resident sub-batches
     bool knn_auto = true;      // until tvg_set_matcher_config is called: r = 2 when the train rows get split
     long long launches = 0;
     int host_chunk_pairs = 256;
@@ -222,6 +223,13 @@ int tvg_set_matcher_config(tvg_ctx* ctx, int r, int variant, int ctas_per_sm) {
     return 0;
 }
 
+int tvg_set_matcher_l2_budget(tvg_ctx* ctx, long long bytes) {
+    if (!ctx) return fail(-1, "ctx is NULL");
+    if (bytes < 0) return fail(-2, "tvg_set_matcher_l2_budget: bytes must be >= 0");
+    ctx->knn_tc_l2_budget = (size_t)bytes;
+    return 0;
+}
+
 int tvg_knn2_hamming256(tvg_ctx* ctx, const uint8_t* q_des, const uint8_t* t_des, int batch, int n_max,
                         int nq, int nt, const int32_t* pair_q, const int32_t* pair_t,
                         const int32_t* q_count, const int32_t* t_count, double ratio, int32_t* idx,
@@ -247,11 +255,11 @@ int tvg_knn2_hamming256(tvg_ctx* ctx, const uint8_t* q_des, const uint8_t* t_des
     const bool use_tc = ctx->knn_auto ? (double)batch * q_rows_tc * t_rows_tc >= (double)TVG_TC_MIN_CMP : ctx->knn_variant == 16;
     if (use_tc) {
         uint8_t* ws = nullptr;
-        TVG_GET(ctx, S_KNN_TC, tvg::knn2_tc_workspace_bytes(batch, n_max), ws, uint8_t*);
+        TVG_GET(ctx, S_KNN_TC, tvg::knn2_tc_workspace_bytes(batch, n_max, ctx->knn_tc_l2_budget), ws, uint8_t*);
         const int tc_splits = tvg::knn2_tc_splits(batch, q_rows_tc, n_max, ctx->sm_count);
         if (tc_splits > 1) TVG_GET(ctx, S_PARTIAL, (size_t)batch * n_max * tc_splits * sizeof(uint2), p.partial, uint2*);
         int nl = 0;
-        TVG_CUDA(tvg::launch_knn2_tc(p, batch, q_rows_tc, ws, ctx->sm_count, &nl, (cudaStream_t)stream));
+        TVG_CUDA(tvg::launch_knn2_tc(p, batch, q_rows_tc, ws, ctx->sm_count, ctx->knn_tc_l2_budget, &nl, (cudaStream_t)stream));
         ctx->launches += nl;
         return 0;
     }

@@ -28,10 +28,10 @@ struct KnnParams {
 cudaError_t launch_knn2(const KnnParams& p, int batch, int qtiles, int r, int variant, cudaStream_t stream);
 int knn2_block_queries(int r);
 // tensor-core matcher (hamming_tc.cu): workspace = e4m3 train rows, 256 B per row, rows padded to 256 per pair
-size_t knn2_tc_workspace_bytes(int batch, int n_max);
+size_t knn2_tc_workspace_bytes(int batch, int n_max, size_t l2_budget);
 int knn2_tc_splits(int batch, int q_rows, int n_max, int sm_count);
-cudaError_t launch_knn2_tc(const KnnParams& p, int batch, int q_rows, uint8_t* workspace, int sm_count, int* launches,
-                           cudaStream_t stream);
+cudaError_t launch_knn2_tc(const KnnParams& p, int batch, int q_rows, uint8_t* workspace, int sm_count, size_t l2_budget,
+                           int* launches, cudaStream_t stream);
 
 // ---------------------------------------------------------------- ratio compaction (compact.cu)
 struct CompactParams {

@@ -148,6 +148,48 @@ def test_knn2_8k_matches_cv2(ops):
     assert np.array_equal(idx.cpu().numpy(), ri) and np.array_equal(dist.cpu().numpy(), rd)
 
 
+def test_knn2_tensor_l2_resident_sub_batches(ops):
+    """L2-resident mode of the tensor-core matcher: several sub-batch launches, default and explicit pairing."""
+    F, N = 9, 520
+    rng = np.random.default_rng(40)
+    des = rng.integers(0, 256, (F, N, 32), dtype=np.uint8)
+    cnt = np.array([520, 400, 7, 519, 300, 520, 64, 257, 511], dtype=np.int32)
+    pq = np.array([1, 2, 3, 4, 5, 6, 7, 8, 0, 4], dtype=np.int32)
+    pt = np.array([0, 1, 2, 3, 4, 5, 6, 7, 8, 4], dtype=np.int32)
+    ctx = ops.context(0)
+    ctx.set_matcher_config(4, 16, 6)
+    ctx.set_matcher_l2_budget(3 * 768 * 256)       # room for 3 pairs (768 padded rows x 256 B each) -> 4 launches
+    import ctypes as C
+    import torch
+    qd = torch.from_numpy(des).cuda()
+    td = torch.from_numpy(np.roll(des, 1, axis=0).copy()).cuda()
+    qc = torch.from_numpy(cnt).cuda()
+    tc = torch.from_numpy(np.roll(cnt, 1).copy()).cuda()
+    i2 = torch.full((F, N, 2), -7, dtype=torch.int32, device="cuda")
+    d2 = torch.full((F, N, 2), -7, dtype=torch.int32, device="cuda")
+    P = lambda t: C.c_void_p(t.data_ptr())
+    try:
+        idx, dist, keep = ops.knn2_hamming256_batched(des, pq, pt, frame_count=cnt)
+        # default pairing (pair b = frame b of either pool), per-frame counts, straight through the C ABI
+        ops.check(ctx.lib.tvg_knn2_hamming256(ctx.handle, P(qd), P(td), F, N, N, N, None, None, P(qc), P(tc), 0.75,
+                                              P(i2), P(d2), None, C.c_void_p(torch.cuda.current_stream().cuda_stream)),
+                  "tvg_knn2_hamming256")
+    finally:
+        ctx.set_matcher_l2_budget(0)
+        ctx.set_matcher_config()
+    idx, dist = idx.cpu().numpy(), dist.cpu().numpy()
+    for b in range(len(pq)):
+        nq, nt = cnt[pq[b]], cnt[pt[b]]
+        ri, rd = tv.knn2_numpy(des[pq[b], :nq], des[pt[b], :nt])
+        assert np.array_equal(idx[b, :nq], ri) and np.array_equal(dist[b, :nq], rd), b
+    i2, d2 = i2.cpu().numpy(), d2.cpu().numpy()
+    for b in range(F):
+        nq, nt = cnt[b], cnt[(b - 1) % F]
+        ri, rd = tv.knn2_numpy(des[b, :nq], des[(b - 1) % F, :nt])
+        assert np.array_equal(i2[b, :nq], ri) and np.array_equal(d2[b, :nq], rd), b
+        assert (i2[b, nq:] == -7).all()
+
+
 @pytest.mark.parametrize("variant", [11, 16])
 def test_knn2_batched_ragged(ops, variant):
     F, N = 5, 700
