@@ -37,7 +37,7 @@ enum Slot {
     S_FE_CORNERS, S_FE_NCORNERS, S_FE_BLURTMP, S_FE_BLUR,
     // host-entry staging
     S_H_DES, S_H_KPS, S_H_FCOUNT, S_H_PAIRQ, S_H_PAIRT, S_H_SEQOFF, S_H_INIT, S_H_WORDS, S_H_SAMPLES,
-    S_KNN_TC, S_BA_TRIAL,
+    S_KNN_TC, S_BA_TRIAL, S_REFITBIG,
     S_NUM
 };
 
@@ -369,6 +369,9 @@ int tvg_ransac_essential(tvg_ctx* ctx, const tvg_ransac_io* io, void* stream) {
     TVG_OUT(ctx, io->Rt, S_RT, B * 16 * sizeof(double), p.Rt, double*);
     TVG_OUT(ctx, io->status, S_STATUS, B * sizeof(int32_t), p.status, int32_t*);
     TVG_GET(ctx, S_REFITWS, B * tvg::ransac_refit_ws_doubles() * sizeof(double), p.refit_ws, double*);
+    if (tvg::ransac_refit_big_blocks(io->n_max) > 0)
+        TVG_GET(ctx, S_REFITBIG, B * tvg::ransac_refit_big_blocks(io->n_max) * tvg::ransac_refit_big_stride() * sizeof(double),
+                p.refit_big, double*);
     cudaStream_t st = (cudaStream_t)stream;
     int mrc = ctx->mark(2, st);
     if (mrc) return mrc;
@@ -382,7 +385,7 @@ int tvg_ransac_essential(tvg_ctx* ctx, const tvg_ransac_io* io, void* stream) {
     if ((mrc = ctx->mark(6, st))) return mrc;
     TVG_CUDA(tvg::launch_ransac_refit(p, io->batch, st));
     if ((mrc = ctx->mark(7, st))) return mrc;
-    ctx->launches += 6;
+    ctx->launches += 6 + (p.refit_big ? 4 : 0);
     return 0;
 }
 

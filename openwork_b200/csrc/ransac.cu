@@ -619,6 +619,256 @@ __global__ void __launch_bounds__(REFIT_THREADS, 2) ransac_refit_kernel(const Ra
     }
 }
 
+// ---- large-M form of the refit accumulation (n_max > REFIT_BIG_N): the same steps as ransac_refit_kernel cut into
+// grid-wide phases so that a single huge pair (C3: M ~ 6.5 k, C5: M ~ 52 k) is not walked by one CTA.  A block owns
+// REFIT_BIG_ROWS consecutive correspondences; every cross-block quantity is a fixed-order sum of per-block partials,
+// so the result does not depend on the launch (and not on the number of ranks in dist.huge_pair).
+//   select  (1 CTA / pair)      best hypothesis, "no model" outputs
+//   mask    (blocks x pairs)    pre-refit inlier mask, per-block inlier count and coordinate sums
+//   scatter (blocks x pairs)    ordered inlier list + pixel gather, per-block squared distances to the centroid
+//   ata     (blocks x pairs)    per-block A^T A (45 sums)
+//   combine (1 CTA / pair)      fixed-order sums -> refit_ws, the hand-off ransac_solve_kernel reads
+constexpr int REFIT_BIG_N = 4096;
+constexpr int REFIT_BIG_ROWS = 2048;
+constexpr int REFIT_BIG_STRIDE = 64;    // doubles per (pair, block): [0] count, [1..4] sums, [5..6] q sums, [8..52] A^T A
+int ransac_refit_big_blocks(int n_max) { return n_max > REFIT_BIG_N ? (n_max + REFIT_BIG_ROWS - 1) / REFIT_BIG_ROWS : 0; }
+int ransac_refit_big_stride() { return REFIT_BIG_STRIDE; }
+
+__global__ void __launch_bounds__(REFIT_THREADS) ransac_refit_big_select_kernel(const RansacParams p) {
+    __shared__ int s_bc[REFIT_THREADS / 32], s_bh[REFIT_THREADS / 32];
+    __shared__ double s_bs[REFIT_THREADS / 32];
+    const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int M = p.m_count ? min(p.m_count[b], p.n_max) : p.m;
+    const size_t oh = (size_t)b * p.H;
+    const int ncand = p.n_cand[b];
+    const double qnan = __longlong_as_double(0x7ff8000000000000LL);
+    int bc = -1, bh = 0x7fffffff;
+    double bs = 0.0;
+    for (int ci = tid; ci < ncand; ci += REFIT_THREADS) {
+        const int h = p.cand[oh + ci];
+        const int c = p.cand_cnt[oh + h];
+        const double s = p.cand_sse[oh + h];
+        const bool better = (c > bc) || (c == bc && (s < bs || (s == bs && h < bh)));
+        if (better) { bc = c; bs = s; bh = h; }
+    }
+#pragma unroll
+    for (int m = 16; m > 0; m >>= 1) {
+        const int oc = __shfl_xor_sync(0xffffffffu, bc, m);
+        const int ohh = __shfl_xor_sync(0xffffffffu, bh, m);
+        const double os = shfl_xor_f64(bs, m);
+        if ((oc > bc) || (oc == bc && (os < bs || (os == bs && ohh < bh)))) { bc = oc; bs = os; bh = ohh; }
+    }
+    if (lane == 0) { s_bc[warp] = bc; s_bs[warp] = bs; s_bh[warp] = bh; }
+    __syncthreads();
+    if (tid == 0) {
+        for (int w = 1; w < REFIT_THREADS / 32; ++w) {
+            const int oc = s_bc[w], ohh = s_bh[w];
+            const double os = s_bs[w];
+            if ((oc > bc) || (oc == bc && (os < bs || (os == bs && ohh < bh)))) { bc = oc; bs = os; bh = ohh; }
+        }
+        const int best = (bc >= 0) ? bh : -1;
+        p.best[b] = best;
+        p.best_sse[b] = (bc >= 0) ? bs : qnan;
+        if (best < 0) {
+            p.n_inl[b] = 0;
+            p.status[b] = (M <= 8) ? 1 : 2;
+            for (int i = 0; i < 9; ++i) { p.E[b * 9 + i] = qnan; p.E_best[b * 9 + i] = qnan; }
+            for (int i = 0; i < 16; ++i) p.Rt[b * 16 + i] = qnan;
+            p.refit_ws[(size_t)b * REFIT_WS + 51] = 0.0;
+        }
+    }
+}
+
+__global__ void __launch_bounds__(REFIT_THREADS) ransac_refit_big_mask_kernel(const RansacParams p, int nblk) {
+    __shared__ double s_buf[REFIT_THREADS / 32];
+    const int blk = blockIdx.x, b = blockIdx.y, tid = threadIdx.x;
+    const int M = p.m_count ? min(p.m_count[b], p.n_max) : p.m;
+    const size_t ob = (size_t)b * p.n_max;
+    const int best = p.best[b];
+    const int lo = blk * REFIT_BIG_ROWS, hi = min(M, lo + REFIT_BIG_ROWS);
+    double* out = p.refit_big + ((size_t)b * nblk + blk) * REFIT_BIG_STRIDE;
+    if (best < 0) {
+        for (int m = lo + tid; m < hi; m += REFIT_THREADS) p.mask[ob + m] = 0;
+        return;
+    }
+    double Eb[9];
+#pragma unroll
+    for (int i = 0; i < 9; ++i) Eb[i] = p.E64[((size_t)b * p.H + best) * 9 + i];
+    const double2* src = reinterpret_cast<const double2*>(p.src) + ob;
+    const double2* dst = reinterpret_cast<const double2*>(p.dst) + ob;
+    double cnt = 0.0, sum[4] = {0.0, 0.0, 0.0, 0.0};
+    for (int m = lo + tid; m < hi; m += REFIT_THREADS) {
+        const double2 s = src[m], d = dst[m];
+        const bool in = sampson_residual(Eb, s.x, s.y, d.x, d.y) < p.thr;
+        p.mask[ob + m] = in ? 1 : 0;
+        if (in) { cnt += 1.0; sum[0] += s.x; sum[1] += s.y; sum[2] += d.x; sum[3] += d.y; }
+    }
+    cnt = block_sum_f64<REFIT_THREADS>(cnt, s_buf);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) sum[k] = block_sum_f64<REFIT_THREADS>(sum[k], s_buf);
+    if (tid == 0) {
+        out[0] = cnt;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) out[1 + k] = sum[k];
+    }
+}
+
+// inlier total and centroid of a pair from the per-block partials (same order in every kernel)
+__device__ __forceinline__ void refit_big_stats(const double* part, int nblk, int blk, int& base, int& total, double (&c)[4]) {
+    base = 0; total = 0;
+    double s[4] = {0.0, 0.0, 0.0, 0.0};
+    for (int k = 0; k < nblk; ++k) {
+        const double* q = part + (size_t)k * REFIT_BIG_STRIDE;
+        const int n = (int)q[0];
+        if (k < blk) base += n;
+        total += n;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) s[i] += q[1 + i];
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) c[i] = s[i] / (double)total;
+}
+
+__global__ void __launch_bounds__(REFIT_THREADS) ransac_refit_big_scatter_kernel(const RansacParams p, int nblk) {
+    __shared__ double s_buf[REFIT_THREADS / 32];
+    __shared__ int s_wcnt[REFIT_THREADS / 32];
+    const int blk = blockIdx.x, b = blockIdx.y, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int M = p.m_count ? min(p.m_count[b], p.n_max) : p.m;
+    const size_t ob = (size_t)b * p.n_max;
+    const int best = p.best[b];
+    if (best < 0) return;
+    double* part = p.refit_big + (size_t)b * nblk * REFIT_BIG_STRIDE;
+    int base, total;
+    double c[4];
+    refit_big_stats(part, nblk, blk, base, total, c);
+    if (blk == 0 && tid == 0) {
+        p.n_inl[b] = total;
+        p.status[b] = 0;
+#pragma unroll
+        for (int i = 0; i < 9; ++i) p.E_best[b * 9 + i] = p.E64[((size_t)b * p.H + best) * 9 + i];
+    }
+    const double2* src = reinterpret_cast<const double2*>(p.src) + ob;
+    const double2* dst = reinterpret_cast<const double2*>(p.dst) + ob;
+    const int fq = p.pair_q ? p.pair_q[b] : b;
+    const int ft = p.pair_t ? p.pair_t[b] : b;
+    const double2* kq = p.kps_q ? reinterpret_cast<const double2*>(p.kps_q) + (size_t)fq * p.n_max : nullptr;
+    const double2* kt = p.kps_t ? reinterpret_cast<const double2*>(p.kps_t) + (size_t)ft * p.n_max : nullptr;
+    const int lo = blk * REFIT_BIG_ROWS, hi = min(M, lo + REFIT_BIG_ROWS);
+    double qs = 0.0, qd = 0.0;
+    int run = base;
+    for (int m0 = lo; m0 < hi; m0 += REFIT_THREADS) {   // ordered compaction, 256 consecutive rows per round
+        const int m = m0 + tid;
+        const bool in = m < hi && p.mask[ob + m];
+        const unsigned bal = __ballot_sync(0xffffffffu, in);
+        if (lane == 0) s_wcnt[warp] = __popc(bal);
+        __syncthreads();
+        int off = 0, tot = 0;
+#pragma unroll
+        for (int w = 0; w < REFIT_THREADS / 32; ++w) {
+            if (w < warp) off += s_wcnt[w];
+            tot += s_wcnt[w];
+        }
+        if (in) {
+            const int pos = run + off + __popc(bal & ((1u << lane) - 1u));
+            p.inl_idx[ob + pos] = m;
+            if (kq) {
+                reinterpret_cast<double2*>(p.pix_curr)[ob + pos] = kq[p.qidx[ob + m]];
+                reinterpret_cast<double2*>(p.pix_last)[ob + pos] = kt[p.tidx[ob + m]];
+            }
+            const double2 s = src[m], d = dst[m];
+            qs = fma(s.x - c[0], s.x - c[0], qs); qs = fma(s.y - c[1], s.y - c[1], qs);
+            qd = fma(d.x - c[2], d.x - c[2], qd); qd = fma(d.y - c[3], d.y - c[3], qd);
+        }
+        run += tot;
+        __syncthreads();
+    }
+    qs = block_sum_f64<REFIT_THREADS>(qs, s_buf);
+    qd = block_sum_f64<REFIT_THREADS>(qd, s_buf);
+    if (tid == 0) {
+        double* out = part + (size_t)blk * REFIT_BIG_STRIDE;
+        out[5] = qs;
+        out[6] = qd;
+    }
+}
+
+__global__ void __launch_bounds__(REFIT_THREADS) ransac_refit_big_ata_kernel(const RansacParams p, int nblk) {
+    __shared__ double s_acc[45][REFIT_THREADS / 32];
+    const int blk = blockIdx.x, b = blockIdx.y, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int M = p.m_count ? min(p.m_count[b], p.n_max) : p.m;
+    const size_t ob = (size_t)b * p.n_max;
+    if (p.best[b] < 0) return;
+    double* part = p.refit_big + (size_t)b * nblk * REFIT_BIG_STRIDE;
+    int base, total;
+    double c[4];
+    refit_big_stats(part, nblk, blk, base, total, c);
+    if (total < 8) return;
+    double qs = 0.0, qd = 0.0;
+    for (int k = 0; k < nblk; ++k) { qs += part[(size_t)k * REFIT_BIG_STRIDE + 5]; qd += part[(size_t)k * REFIT_BIG_STRIDE + 6]; }
+    const double ss = 1.4142135623730951 / sqrt(qs / (double)total);
+    const double sd = 1.4142135623730951 / sqrt(qd / (double)total);
+    const double2* src = reinterpret_cast<const double2*>(p.src) + ob;
+    const double2* dst = reinterpret_cast<const double2*>(p.dst) + ob;
+    const int lo = blk * REFIT_BIG_ROWS, hi = min(M, lo + REFIT_BIG_ROWS);
+    double acc[45];
+#pragma unroll
+    for (int i = 0; i < 45; ++i) acc[i] = 0.0;
+    for (int m = lo + tid; m < hi; m += REFIT_THREADS) {
+        if (!p.mask[ob + m]) continue;
+        const double2 s = src[m], d = dst[m];
+        const double xs = ss * s.x - ss * c[0], ys = ss * s.y - ss * c[1];
+        const double xd = sd * d.x - sd * c[2], yd = sd * d.y - sd * c[3];
+        const double a[9] = {xd * xs, xd * ys, xd, yd * xs, yd * ys, yd, xs, ys, 1.0};
+        int t = 0;
+#pragma unroll
+        for (int i = 0; i < 9; ++i)
+#pragma unroll
+            for (int j = i; j < 9; ++j) { acc[t] = fma(a[i], a[j], acc[t]); ++t; }
+    }
+#pragma unroll
+    for (int i = 0; i < 45; ++i) {
+        const double v = warp_sum_f64(acc[i]);
+        if (lane == 0) s_acc[i][warp] = v;
+    }
+    __syncthreads();
+    if (tid < 45) {
+        double v = 0.0;
+#pragma unroll
+        for (int w = 0; w < REFIT_THREADS / 32; ++w) v += s_acc[tid][w];
+        part[(size_t)blk * REFIT_BIG_STRIDE + 8 + tid] = v;
+    }
+}
+
+__global__ void __launch_bounds__(64) ransac_refit_big_combine_kernel(const RansacParams p, int nblk) {
+    const int b = blockIdx.x, tid = threadIdx.x;
+    const int best = p.best[b];
+    if (best < 0) return;
+    const double* part = p.refit_big + (size_t)b * nblk * REFIT_BIG_STRIDE;
+    double* ws = p.refit_ws + (size_t)b * REFIT_WS;
+    int base, total;
+    double c[4];
+    refit_big_stats(part, nblk, 0, base, total, c);
+    if (total < 8) {
+        if (tid == 0) {
+            ws[51] = 1.0;
+            for (int i = 0; i < 9; ++i) ws[52 + i] = p.E64[((size_t)b * p.H + best) * 9 + i];
+        }
+        return;
+    }
+    if (tid < 45) {
+        double v = 0.0;
+        for (int k = 0; k < nblk; ++k) v += part[(size_t)k * REFIT_BIG_STRIDE + 8 + tid];
+        ws[tid] = v;
+    }
+    if (tid == 0) {
+        double qs = 0.0, qd = 0.0;
+        for (int k = 0; k < nblk; ++k) { qs += part[(size_t)k * REFIT_BIG_STRIDE + 5]; qd += part[(size_t)k * REFIT_BIG_STRIDE + 6]; }
+        ws[45] = 1.4142135623730951 / sqrt(qs / (double)total); ws[46] = c[0]; ws[47] = c[1];
+        ws[48] = 1.4142135623730951 / sqrt(qd / (double)total); ws[49] = c[2]; ws[50] = c[3];
+        ws[51] = 2.0;
+        for (int i = 0; i < 9; ++i) ws[52 + i] = p.E64[((size_t)b * p.H + best) * 9 + i];
+    }
+}
+
 // One warp per pair: smallest eigenvector of A^T A, (s,s,0) projection, de-normalisation, extract_Rt.
 // Split from the accumulation kernel so that all pairs' (latency-bound) solves run concurrently.
 constexpr int SOLVE_WARPS = 4;
@@ -671,7 +921,17 @@ __global__ void __launch_bounds__(SOLVE_WARPS * 32) ransac_solve_kernel(const Ra
 }
 
 cudaError_t launch_ransac_refit(const RansacParams& p, int batch, cudaStream_t stream) {
-    ransac_refit_kernel<<<batch, REFIT_THREADS, 0, stream>>>(p);
+    const int nblk = p.refit_big ? ransac_refit_big_blocks(p.n_max) : 0;
+    if (nblk > 0) {
+        dim3 grid(nblk, batch);
+        ransac_refit_big_select_kernel<<<batch, REFIT_THREADS, 0, stream>>>(p);
+        ransac_refit_big_mask_kernel<<<grid, REFIT_THREADS, 0, stream>>>(p, nblk);
+        ransac_refit_big_scatter_kernel<<<grid, REFIT_THREADS, 0, stream>>>(p, nblk);
+        ransac_refit_big_ata_kernel<<<grid, REFIT_THREADS, 0, stream>>>(p, nblk);
+        ransac_refit_big_combine_kernel<<<batch, 64, 0, stream>>>(p, nblk);
+    } else {
+        ransac_refit_kernel<<<batch, REFIT_THREADS, 0, stream>>>(p);
+    }
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return e;
     ransac_solve_kernel<<<(batch + SOLVE_WARPS - 1) / SOLVE_WARPS, SOLVE_WARPS * 32, 0, stream>>>(p, batch);

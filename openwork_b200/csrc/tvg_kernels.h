@@ -101,6 +101,7 @@ struct RansacParams {
     double* Rt;                // [batch][16]
     int32_t* status;           // [batch] 0 ok, 1 = fewer than 9 correspondences
     double* refit_ws;          // [batch][ransac_refit_ws_doubles()] accumulate -> solve hand-off
+    double* refit_big;         // [batch][ransac_refit_big_blocks(n_max)][ransac_refit_big_stride()] (NULL -> single-CTA refit)
 };
 cudaError_t launch_ransac_fit(const RansacParams& p, int batch, cudaStream_t stream);
 cudaError_t launch_ransac_score(const RansacParams& p, int batch, int mode, cudaStream_t stream);
@@ -109,6 +110,8 @@ cudaError_t launch_ransac_reduce(const RansacParams& p, int batch, cudaStream_t 
 cudaError_t launch_ransac_rescore(const RansacParams& p, int batch, cudaStream_t stream);
 cudaError_t launch_ransac_refit(const RansacParams& p, int batch, cudaStream_t stream);
 int ransac_refit_ws_doubles();
+int ransac_refit_big_blocks(int n_max);   // 0 when the single-CTA refit is used
+int ransac_refit_big_stride();
 
 // ---------------------------------------------------------------- pose + triangulation (pose_tri.cu)
 struct PoseChainParams {
