@@ -37,7 +37,7 @@ enum Slot {
     S_FE_CORNERS, S_FE_NCORNERS, S_FE_BLURTMP, S_FE_BLUR,
     // host-entry staging
     S_H_DES, S_H_KPS, S_H_FCOUNT, S_H_PAIRQ, S_H_PAIRT, S_H_SEQOFF, S_H_INIT, S_H_WORDS, S_H_SAMPLES,
-    S_KNN_TC, S_BA_TRIAL, S_REFITBIG,
+    S_KNN_TC, S_BA_TRIAL, S_REFITBIG, S_COMPACTBIG,
     S_NUM
 };
 
@@ -314,8 +314,10 @@ int tvg_ratio_compact(tvg_ctx* ctx, const uint8_t* keep, const int32_t* idx, int
     if (gather) memcpy(p.kinv, kinv_host, sizeof(p.kinv));
     p.qidx = qidx; p.tidx = tidx; p.m_count = m_count; p.src = src; p.dst = dst;
     p.corr32 = reinterpret_cast<float4*>(corr32);
+    if (tvg::compact_big_blocks(n_max) > 0)
+        TVG_GET(ctx, S_COMPACTBIG, (size_t)batch * tvg::compact_big_blocks(n_max) * sizeof(int32_t), p.blk_cnt, int32_t*);
     TVG_CUDA(tvg::launch_compact(p, batch, (cudaStream_t)stream));
-    ctx->launches += 1;
+    ctx->launches += p.blk_cnt ? 2 : 1;
     return 0;
 }
 

@@ -50,7 +50,9 @@ struct CompactParams {
     double* src;               // [batch][n_max][2]  K-normalised LAST (train) points
     double* dst;               // [batch][n_max][2]  K-normalised CURR (query) points
     float4* corr32;            // [batch][n_max]     (src.x, src.y, dst.x, dst.y)
+    int32_t* blk_cnt;          // [batch][compact_big_blocks(n_max)] scratch (NULL -> single-CTA form)
 };
+int compact_big_blocks(int n_max);   // 0 when the single-CTA form is used
 cudaError_t launch_compact(const CompactParams& p, int batch, cudaStream_t stream);
 
 // ---------------------------------------------------------------- RANSAC (ransac.cu)
