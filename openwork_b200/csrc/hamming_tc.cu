@@ -115,23 +115,34 @@ __device__ __forceinline__ void tc_counts(const TcArgs& a, int b, int& fq, int& 
     nt = a.k.t_count ? min(a.k.t_count[ft], a.k.n_max) : a.k.nt;
 }
 
-// one thread = one 16-byte piece (consecutive threads, consecutive pieces of a pair's buffer)
+// one thread = four 16-byte pieces, 256 pieces apart (consecutive threads write consecutive pieces; four independent
+// load -> expand -> store chains per thread keep more bytes in flight)
+constexpr int UNPACK_PER_THREAD = 4;
+
 __global__ void __launch_bounds__(256) unpack_train_kernel(TcArgs a) {
     const int b = blockIdx.y;
     int fq, ft, nq, nt;
     tc_counts(a, b, fq, ft, nq, nt);
     const int rows = (nt + TC_TN - 1) / TC_TN * TC_TN;       // only the tiles the matcher will load
-    const int piece = blockIdx.x * blockDim.x + threadIdx.x;
-    if (piece >= rows * 16) return;
-    const int r = piece & 7, c = (piece >> 3) & 15, g = piece >> 7;
-    const int row = g * 8 + r;
-    uint4 o = make_uint4(0, 0, 0, 0);
-    if (row < nt) {
-        const uint8_t* d = a.k.t_base + ((size_t)ft * a.k.n_max + row) * 32 + 2 * c;
-        const uint32_t bits = (uint32_t)__ldg(reinterpret_cast<const unsigned short*>(d));
-        o = make_uint4(tc_expand4(bits), tc_expand4(bits >> 4), tc_expand4(bits >> 8), tc_expand4(bits >> 12));
+    const int piece0 = blockIdx.x * (256 * UNPACK_PER_THREAD) + threadIdx.x;
+    uint32_t bits[UNPACK_PER_THREAD];
+#pragma unroll
+    for (int u = 0; u < UNPACK_PER_THREAD; ++u) {
+        const int piece = piece0 + u * 256;
+        const int r = piece & 7, c = (piece >> 3) & 15, row = (piece >> 7) * 8 + r;
+        bits[u] = 0x10000u;   // marker: zero row
+        if (piece < rows * 16 && row < nt)
+            bits[u] = (uint32_t)__ldg(reinterpret_cast<const unsigned short*>(a.k.t_base + ((size_t)ft * a.k.n_max + row) * 32 + 2 * c));
     }
-    reinterpret_cast<uint4*>(a.unpacked + (size_t)b * a.n_pad * TC_KB)[piece] = o;
+    uint4* out = reinterpret_cast<uint4*>(a.unpacked + (size_t)b * a.n_pad * TC_KB);
+#pragma unroll
+    for (int u = 0; u < UNPACK_PER_THREAD; ++u) {
+        const int piece = piece0 + u * 256;
+        if (piece >= rows * 16) continue;
+        const uint32_t v = bits[u];
+        out[piece] = (v & 0x10000u) ? make_uint4(0, 0, 0, 0)
+                                    : make_uint4(tc_expand4(v), tc_expand4(v >> 4), tc_expand4(v >> 8), tc_expand4(v >> 12));
+    }
 }
 
 __device__ __forceinline__ void tc_emit(const KnnParams& p, size_t o, uint32_t k1, uint32_t k2) {
@@ -453,7 +464,7 @@ cudaError_t launch_knn2_tc(const KnnParams& p, int batch, int q_rows, uint8_t* w
         a.batch = nb;
         a.items = nb * a.qis * a.splits;
         if (t_rows > 0) {
-            dim3 ug((unsigned)(((size_t)a.n_pad * 16 + 255) / 256), (unsigned)nb);
+            dim3 ug((unsigned)(((size_t)a.n_pad * 16 + 256 * UNPACK_PER_THREAD - 1) / (256 * UNPACK_PER_THREAD)), (unsigned)nb);
             unpack_train_kernel<<<ug, 256, 0, stream>>>(a);
             ++*launches;
         }
