@@ -488,7 +488,7 @@ def run_ours(args):
                          "timed alone -> burst); nominal e4m3 peak 4500 TF/s -> frac %.3f" %
                          (peak_kind, bf16, tflops / 4500.0),
             "ms_per_launch": knn_ms, "cmp_per_launch": cmp_per_launch, "gcmp_s": gcmp_s,
-            "x_int32_popc_peak": gcmp_s / popc_peak, "sm_mhz_during_run": f_mhz,
+            "x_int32_popc_peak": gcmp_s / popc_peak, "x_measured_bf16_peak": tflops / bf16, "sm_mhz_during_run": f_mhz,
             # dram bytes of knn2_tc_kernel + unpack_train_kernel at P=1024 (profiles/r1_tensor_matcher_dram_traffic.md)
             "traffic": TC_TRAFFIC_BYTES_P1024 * P / 1024 if TC_TRAFFIC_BYTES_P1024 else None,
             "traffic_note": "7x the algorithmic bytes: the e4m3 expansion of the train side (512 KB per pair) is written "
