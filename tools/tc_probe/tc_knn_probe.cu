@@ -1,6 +1,10 @@
 // Probe: 256-bit Hamming kNN(k=2) on the 5th-gen tensor cores.  bits -> e4m3 (+1/-1), D = Q.T^T via tcgen05.mma
 // kind::f8f6f4 (fp32 accumulate, exact), hamming = (256 - dot) / 2, top-2 in the TMEM epilogue.
 // Standalone (own main) so the layout/descriptor assumptions can be checked before the kernel goes into the library.
+// This file is the experiment bench, not product code: it holds the configuration that was promoted to
+// openwork_b200/csrc/hamming_tc.cu (2 query blocks x N=256, f16 accumulate, packed 16-bit epilogue) plus the ablation
+// switches (MODE 1 = TMEM loads only, MODE 2 = no epilogue work) behind DESIGN.md's table; earlier tilings are in the
+// git history of this file.  Build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -o tc_knn_probe tc_knn_probe.cu
 #include <cuda_runtime.h>
 #include <cuda_fp16.h>
 #include <stdint.h>
