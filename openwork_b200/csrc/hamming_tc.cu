@@ -40,6 +40,9 @@ constexpr int TC_KB = 256;                    // bytes per e4m3 row
 constexpr int TC_A_BLK = TC_QB * TC_KB;       // 32 KB
 constexpr int TC_B_TILE = TC_TN * TC_KB;      // 64 KB
 constexpr int TC_NST = 2;
+#ifndef TC_LISTS
+#define TC_LISTS 4   // independent top-2 lists per thread in the epilogue (instruction-level parallelism)
+#endif
 constexpr int TC_THREADS = 32 * (2 + 4 * TC_NQB);
 constexpr int TC_SMEM = TC_NQB * TC_A_BLK + TC_NST * TC_B_TILE + 256;
 // instruction descriptor: D = f16 (bits 4-5 = 0), A = B = e4m3 (0), both K-major, N >> 3 at bit 17, M >> 4 at bit 24
@@ -303,9 +306,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) knn2_tc_kernel(TcArgs a) {
                     int fq2, nq2, qi2;
                     if (next_live(item, fq2, nq2, qi2)) write_a(fq2, nq2, qi2);
                 }
-                uint32_t m1[4], m2[4];
+                uint32_t m1[TC_LISTS], m2[TC_LISTS];
 #pragma unroll
-                for (int l = 0; l < 4; ++l) m1[l] = m2[l] = 0xFFFFFFFFu;
+                for (int l = 0; l < TC_LISTS; ++l) m1[l] = m2[l] = 0xFFFFFFFFu;
                 const int cols = min(TC_TN, nt - j * TC_TN);
                 auto chunk = [&](auto masked) {
 #pragma unroll
@@ -325,7 +328,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) knn2_tc_kernel(TcArgs a) {
                                 }
                             }
                             // two keys per update: 5 min/max (one 3-input) instead of 6
-                            const int l = (i >> 1) & 3;
+                            const int l = (i >> 1) & (TC_LISTS - 1);
                             const uint32_t lo = __vminu2(key[0], key[1]), hi = __vmaxu2(key[0], key[1]);
                             m2[l] = __vimin3_u16x2(m2[l], hi, __vmaxu2(m1[l], lo));
                             m1[l] = __vminu2(m1[l], lo);
@@ -334,7 +337,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) knn2_tc_kernel(TcArgs a) {
                 if (cols >= TC_TN) chunk(std::false_type{}); else chunk(std::true_type{});
                 // fold the four lists, then the four 16-bit candidates into the 32-bit global keys
 #pragma unroll
-                for (int l = 1; l < 4; ++l) {
+                for (int l = 1; l < TC_LISTS; ++l) {
                     const uint32_t hi = __vmaxu2(m1[0], m1[l]);
                     m1[0] = __vminu2(m1[0], m1[l]);
                     m2[0] = __vminu2(hi, __vminu2(m2[0], m2[l]));
