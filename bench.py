@@ -247,6 +247,33 @@ def single_pair_latency(ops, ctx, K, n, H, dev, reps=30):
             "matcher_gcmp_s": n * n / knn_us / 1e3}
 
 
+def process_frame_latency(K, n=2048, H=1024, reps=7):
+    """Wall-clock microseconds of openwork_b200.slam.process_frame for one new frame (numpy in, numpy out, the call a
+    user of the reference's slam.py makes per video frame): the default single-pipeline-call path and the
+    function-by-function path."""
+    import torch
+    from openwork_b200 import slam, synth
+    slam.K, slam.mapp = K, None
+    slam.ransac_config.update(max_trials=H, residual_threshold=THR, seed=0)
+    lk, ld, ck, cd = synth.make_pair_large(n, SEED + n)
+    res = {"kpts": n, "hypotheses": H}
+    for fused in (True, False):
+        slam.FUSED_PROCESS_FRAME = fused
+        times = []
+        for _ in range(reps):
+            slam.Frame.reset()
+            slam.process_frame(slam.Frame(kps=lk, des=ld))
+            torch.cuda.synchronize()
+            t = time.perf_counter()
+            slam.process_frame(slam.Frame(kps=ck, des=cd))
+            torch.cuda.synchronize()
+            times.append(time.perf_counter() - t)
+        res["fused_us" if fused else "stepwise_us"] = sorted(times[2:])[len(times[2:]) // 2] * 1e6
+    slam.FUSED_PROCESS_FRAME = True
+    slam.Frame.reset()
+    return res
+
+
 def frontend_rate(ops, ctx, dev, frames=256):
     """Not part of the metric (the north star feeds synthetic keypoints): frames/s of the GPU feature front-end
     (BGR2GRAY + goodFeaturesToTrack + ORB.compute, bit-exact vs cv2) on procedurally textured 640x480 images."""
@@ -440,7 +467,8 @@ def run_ours(args):
 
     single = None
     if rank == 0 and not args.no_single_pair:
-        single = {"C2": single_pair_latency(ops, ctx, K, 2048, 1024, dev), "C3": single_pair_latency(ops, ctx, K, 8192, 4096, dev)}
+        single = {"C2": single_pair_latency(ops, ctx, K, 2048, 1024, dev), "C3": single_pair_latency(ops, ctx, K, 8192, 4096, dev),
+                  "process_frame_C2": process_frame_latency(K)}
 
     frontend = None
     if rank == 0 and not args.no_frontend:

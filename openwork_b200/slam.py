@@ -39,6 +39,9 @@ mapp = None
 extract_points = None
 ransac_config = dict(max_trials=200, residual_threshold=0.005, seed=0)
 RATIO = 0.75
+# process_frame runs the frame pair through ONE pipeline call (tvg_pairs_host: one upload, ten kernels, one download)
+# instead of the function-by-function sequence with a host round trip per step; same results, same exceptions.
+FUSED_PROCESS_FRAME = True
 
 
 class Frame(object):
@@ -136,6 +139,54 @@ def check_points(points4d):
     return np.asarray(points4d)[:, 2] > 0
 
 
+_fused_buffers = {}     # (n, H) -> pinned output buffers + staging arrays of the fused path, reused frame after frame
+
+
+def _process_pair_fused(frame):
+    """The else-branch of process_frame (slam.py:249-266) as one call of the batched pipeline on a batch of one pair.
+    Leaves the frame exactly as the function-by-function sequence does."""
+    curr_kps, last_kps = np.asarray(frame.curr_kps, dtype=np.float64), np.asarray(frame.last_kps, dtype=np.float64)
+    curr_des, last_des = np.asarray(frame.curr_des), np.asarray(frame.last_des)
+    nq, nt = len(curr_des), len(last_des)
+    if nt < 2:
+        raise ValueError("not enough values to unpack (expected 2, got %d)" % nt)      # slam.py:130
+    n = max(nq, nt)
+    H = int(ransac_config["max_trials"])
+    buf = _fused_buffers.get((n, H))
+    if buf is None:
+        if len(_fused_buffers) > 8:
+            _fused_buffers.clear()
+        buf = _fused_buffers[(n, H)] = dict(des=torch.zeros((2, n, 32), dtype=torch.uint8).pin_memory(),
+                                            kps=torch.zeros((2, n, 2), dtype=torch.float64).pin_memory(), out=None)
+    des, kps = buf["des"].numpy(), buf["kps"].numpy()      # rows beyond the counts are never read
+    des[0, :nt], des[1, :nq] = last_des, curr_des
+    kps[0, :nt], kps[1, :nq] = last_kps, curr_kps
+    words = synth.sample_words(H, int(ransac_config["seed"]) * 1000003 + int(frame.idx))
+    out, _, _ = ops.process_pairs_host(
+        buf["des"], buf["kps"], K, words=words, frame_count=np.array([nt, nq], dtype=np.int32), pair_q=np.array([1], dtype=np.int32),
+        pair_t=np.array([0], dtype=np.int32), seq_off=np.array([0, 1], dtype=np.int32),
+        init_pose=np.ascontiguousarray(frame.last_pose, dtype=np.float64)[None], ratio=RATIO,
+        residual_threshold=float(ransac_config["residual_threshold"]),
+        outputs=("qidx", "tidx", "m_count", "mask", "E", "best", "Rt", "poses", "points4d", "good", "n_inl", "status"),
+        out=buf["out"])
+    buf["out"] = out
+    M = int(out["m_count"][0])
+    assert M >= 8                                                                       # slam.py:138
+    if M <= 8:
+        raise ValueError("`min_samples` must be in range (0, <number-of-samples>)")     # skimage.measure.ransac
+    idx1, idx2 = out["qidx"][0, :M].numpy(), out["tidx"][0, :M].numpy()
+    inliers = out["mask"][0, :M].numpy().astype(bool)
+    frame.curr_kps = curr_kps[idx1][inliers]
+    frame.last_kps = last_kps[idx2][inliers]
+    frame.ransac = dict(E=out["E"][0].clone(), mask=out["mask"][0, :M].clone(), best=int(out["best"][0]),
+                        status=int(out["status"][0]))
+    frame.essential_matrix = out["E"][0].numpy().copy()
+    frame.curr_pose = out["poses"][1].numpy().copy()
+    n_inl = int(out["n_inl"][0])
+    points4d = out["points4d"][0, :n_inl].numpy()
+    return points4d[out["good"][0, :n_inl].numpy().astype(bool)]                        # check_points filter
+
+
 def process_frame(frame_):
     """slam.py:239-272, same order of operations."""
     global frame
@@ -151,6 +202,8 @@ def process_frame(frame_):
     if frame.idx == 1:
         frame.curr_pose = np.eye(4)
         points4d = [[0, 0, 0, 1]]
+    elif FUSED_PROCESS_FRAME:
+        points4d = _process_pair_fused(frame)
     else:
         match_kps = match_points(frame)
         essential_matrix = fit_essential_matrix(match_kps)

@@ -9,10 +9,12 @@ from oracle import two_view as tv
 pytestmark = pytest.mark.gpu
 
 
-def test_process_frame_sequence_matches_oracle():
+@pytest.mark.parametrize("fused", [True, False])
+def test_process_frame_sequence_matches_oracle(fused):
     from openwork_b200 import slam
     K = synth.K_640x480
     slam.K = K
+    slam.FUSED_PROCESS_FRAME = fused
     slam.ransac_config.update(max_trials=200, residual_threshold=0.005, seed=3)   # reference defaults slam.py:157-159
     slam.Frame.reset()
     observations = []
@@ -46,6 +48,41 @@ def test_process_frame_sequence_matches_oracle():
         pose = ref["curr_pose"]
     assert len(observations) == 4
     slam.mapp = None
+    slam.FUSED_PROCESS_FRAME = True
+
+
+def test_process_frame_fused_equals_stepwise():
+    """One pipeline call per frame (default) leaves every frame attribute as the function-by-function sequence does,
+    including ragged keypoint counts and the exceptions."""
+    from openwork_b200 import slam
+    slam.K = synth.K_640x480
+    slam.mapp = None
+    slam.ransac_config.update(max_trials=128, residual_threshold=0.005, seed=11)
+    frames, _ = synth.make_sequence(5, 800, seed=77)
+    frames = [(k[: 800 - 37 * i], d[: 800 - 37 * i]) for i, (k, d) in enumerate(frames)]     # different N per frame
+    res = {}
+    for fused in (True, False):
+        slam.FUSED_PROCESS_FRAME = fused
+        slam.Frame.reset()
+        res[fused] = [slam.process_frame(slam.Frame(kps=k, des=d)) for k, d in frames]
+    slam.FUSED_PROCESS_FRAME = True
+    for a, b in zip(res[True][1:], res[False][1:]):
+        assert np.array_equal(a.curr_kps, b.curr_kps) and np.array_equal(a.last_kps, b.last_kps)
+        assert np.array_equal(a.essential_matrix, b.essential_matrix)          # the same kernels ran
+        np.testing.assert_allclose(a.curr_pose, b.curr_pose, rtol=0, atol=1e-12)
+        assert a.points4d.shape == b.points4d.shape
+        np.testing.assert_allclose(a.points4d, b.points4d, rtol=1e-8, atol=1e-10)
+    # exceptions of the fused path: too few train rows, too few matches
+    slam.Frame.reset()
+    lk, ld, ck, cd = synth.make_pair(64, 1)
+    slam.process_frame(slam.Frame(kps=lk[:1], des=ld[:1]))
+    with pytest.raises(ValueError):
+        slam.process_frame(slam.Frame(kps=ck, des=cd))
+    slam.Frame.reset()
+    slam.process_frame(slam.Frame(kps=lk, des=synth.random_descriptors(64, 4)))
+    with pytest.raises(AssertionError):
+        slam.process_frame(slam.Frame(kps=ck, des=synth.random_descriptors(64, 3)))
+    slam.Frame.reset()
 
 
 def test_reference_error_conventions():
