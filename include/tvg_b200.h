@@ -55,6 +55,10 @@ TVG_API int tvg_set_matcher_config(tvg_ctx* ctx, int r, int variant, int ctas_pe
  * sub-batches whose expansion fits in `bytes` of L2 (40 MiB measured: DRAM traffic = the algorithmic bytes, +8 % time). */
 TVG_API int tvg_set_matcher_l2_budget(tvg_ctx* ctx, long long bytes);
 
+/* RANSAC scoring kernel tuning (results do not depend on it): hypotheses per thread (2 or 4; 0 = default) and resident
+ * CTAs per SM of the persistent grid (0 = automatic: the count whose rounds the work items fill best). */
+TVG_API int tvg_set_score_config(tvg_ctx* ctx, int hyp_per_thread, int ctas_per_sm);
+
 /* cv2.BFMatcher(cv2.NORM_HAMMING).knnMatch(q, t, k=2)  (slam.py:126-127) + the Lowe ratio flag
  * m.distance < ratio * n.distance (slam.py:131).
  * Pair b matches query frame (pair_q ? pair_q[b] : b) of the pool q_des[frames][n_max][32] against train

@@ -77,6 +77,7 @@ SIGNATURES = {
     "tvg_pairs_device": (C.c_int, [c_vp, C.POINTER(PairsIO), c_vp]),
     "tvg_set_host_chunk": (C.c_int, [c_vp, C.c_int]),
     "tvg_set_matcher_l2_budget": (C.c_int, [c_vp, C.c_longlong]),
+    "tvg_set_score_config": (C.c_int, [c_vp, C.c_int, C.c_int]),
     "tvg_set_profile": (C.c_int, [c_vp, C.c_int]),
     "tvg_get_stage_ms": (C.c_int, [c_vp, c_f32p, C.c_int]),
     "tvg_pairs_host": (C.c_int, [c_vp, C.POINTER(PairsIO), C.c_int, C.POINTER(C.c_longlong),
@@ -160,6 +161,10 @@ class Context:
 
     def set_matcher_l2_budget(self, nbytes=0):
         check(self.lib.tvg_set_matcher_l2_budget(self.handle, int(nbytes)), "tvg_set_matcher_l2_budget")
+
+    def set_score_config(self, hyp_per_thread=0, ctas_per_sm=0):
+        """Scoring kernel tuning: hypotheses per thread (0 = default, 2, 4), resident CTAs per SM (0 = automatic)."""
+        check(self.lib.tvg_set_score_config(self.handle, int(hyp_per_thread), int(ctas_per_sm)), "tvg_set_score_config")
 
     def set_host_chunk(self, pairs=256):
         check(self.lib.tvg_set_host_chunk(self.handle, int(pairs)), "tvg_set_host_chunk")

@@ -37,7 +37,7 @@ enum Slot {
     S_FE_CORNERS, S_FE_NCORNERS, S_FE_BLURTMP, S_FE_BLUR,
     // host-entry staging
     S_H_DES, S_H_KPS, S_H_FCOUNT, S_H_PAIRQ, S_H_PAIRT, S_H_SEQOFF, S_H_INIT, S_H_WORDS, S_H_SAMPLES,
-    S_KNN_TC, S_BA_TRIAL, S_REFITBIG, S_COMPACTBIG,
+    S_KNN_TC, S_BA_TRIAL, S_REFITBIG, S_COMPACTBIG, S_SCOREQ,
     S_NUM
 };
 
@@ -53,6 +53,7 @@ struct tvg_ctx {
     int device = 0;
     int sm_count = 148;
     int knn_r = 4, knn_variant = 11, knn_ctas_per_sm = 6;
+    int score_hpt = 0, score_ctas = 0;   // scoring kernel tuning (0 = automatic), tvg_set_score_config
     size_t knn_tc_l2_budget = 0;   // 0 = one unpack + one match launch per call; > 0 = L2-resident sub-batches
     bool knn_auto = true;      // until tvg_set_matcher_config is called: r = 2 when the train rows get split
     long long launches = 0;
@@ -98,11 +99,20 @@ struct tvg_ctx {
     }
     void* slot[S_NUM] = {};
     size_t slot_bytes[S_NUM] = {};
+    cudaStream_t cur_stream = nullptr;   // stream of the entry point being served (set by every stream-taking call)
+    bool in_flight = false;              // tvg_pairs_host_submit without its tvg_pairs_host_wait yet
 
-    // grow-only scratch; zero_on_grow for buffers the kernels expect zeroed (tile counters)
+    // grow-only scratch; zero_on_grow for buffers the kernels expect zeroed (tile counters): the memset is ordered
+    // on the caller's stream, like the kernels that read the buffer.  Growing synchronises the device and
+    // (re)allocates, which is illegal while `cur_stream` is being captured into a CUDA graph: warm the context up
+    // at the same sizes before capturing.
     int get(Slot s, size_t bytes, void** out, bool zero_on_grow = false) {
         if (bytes == 0) bytes = 16;
         if (slot_bytes[s] < bytes) {
+            cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+            if (cudaStreamIsCapturing(cur_stream, &cap) == cudaSuccess && cap != cudaStreamCaptureStatusNone)
+                return fail(-6, "scratch must grow while the stream is being captured: run the call once eagerly at "
+                                "the same sizes before capturing it into a CUDA graph");
             if (slot[s]) {
                 cudaError_t e = cudaDeviceSynchronize();
                 if (e != cudaSuccess) return cuda_fail(e, "cudaDeviceSynchronize");
@@ -114,8 +124,8 @@ struct tvg_ctx {
             cudaError_t e = cudaMalloc(&slot[s], want);
             if (e != cudaSuccess) return cuda_fail(e, "cudaMalloc(scratch)");
             if (zero_on_grow) {
-                e = cudaMemset(slot[s], 0, want);
-                if (e != cudaSuccess) return cuda_fail(e, "cudaMemset(scratch)");
+                e = cudaMemsetAsync(slot[s], 0, want, cur_stream);
+                if (e != cudaSuccess) return cuda_fail(e, "cudaMemsetAsync(scratch)");
             }
             slot_bytes[s] = want;
         }
@@ -158,7 +168,8 @@ __global__ void make_pairs_kernel(const int32_t* seq_off, int nseq, int batch, i
     const int b = blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= batch) return;
     int s = 0;
-    while (s + 1 < nseq && b >= seq_off[s + 1]) ++s;
+    if (seq_off)   // NULL = one sequence holding every pair
+        while (s + 1 < nseq && b >= seq_off[s + 1]) ++s;
     pair_t[b] = b + s;      // last frame of the pair
     pair_q[b] = b + s + 1;  // current frame
 }
@@ -223,6 +234,15 @@ int tvg_set_matcher_config(tvg_ctx* ctx, int r, int variant, int ctas_per_sm) {
     return 0;
 }
 
+int tvg_set_score_config(tvg_ctx* ctx, int hyp_per_thread, int ctas_per_sm) {
+    if (!ctx) return fail(-1, "ctx is NULL");
+    if (!(hyp_per_thread == 0 || hyp_per_thread == 2 || hyp_per_thread == 4) || ctas_per_sm < 0 || ctas_per_sm > 16)
+        return fail(-2, "tvg_set_score_config: hyp_per_thread in {0, 2, 4}, ctas_per_sm in [0, 16]");
+    ctx->score_hpt = hyp_per_thread;
+    ctx->score_ctas = ctas_per_sm;
+    return 0;
+}
+
 int tvg_set_matcher_l2_budget(tvg_ctx* ctx, long long bytes) {
     if (!ctx) return fail(-1, "ctx is NULL");
     if (bytes < 0) return fail(-2, "tvg_set_matcher_l2_budget: bytes must be >= 0");
@@ -242,6 +262,7 @@ int tvg_knn2_hamming256(tvg_ctx* ctx, const uint8_t* q_des, const uint8_t* t_des
     if (!q_des || !t_des || !idx || !dist) return fail(-3, "tvg_knn2_hamming256: NULL array");
     if (!aligned16(q_des) || !aligned16(t_des)) return fail(-4, "tvg_knn2_hamming256: descriptors must be 16-byte aligned");
     DeviceGuard g(ctx->device);
+    ctx->cur_stream = (cudaStream_t)stream;
     tvg::KnnParams p{};
     p.q_base = q_des; p.t_base = t_des; p.pair_q = pair_q; p.pair_t = pair_t;
     p.q_count = q_count; p.t_count = t_count;
@@ -307,6 +328,7 @@ int tvg_ratio_compact(tvg_ctx* ctx, const uint8_t* keep, const int32_t* idx, int
     if (gather && (!kps_q || !kps_t || !kinv_host || !src || !dst || !corr32))
         return fail(-3, "tvg_ratio_compact: gather needs kps_q, kps_t, kinv, src, dst, corr32");
     DeviceGuard g(ctx->device);
+    ctx->cur_stream = (cudaStream_t)stream;
     tvg::CompactParams p{};
     p.keep = keep; p.idx = idx; p.pair_q = pair_q; p.pair_t = pair_t; p.q_count = q_count;
     p.n_max = n_max; p.nq = nq;
@@ -332,6 +354,7 @@ int tvg_ransac_essential(tvg_ctx* ctx, const tvg_ransac_io* io, void* stream) {
     if (!aligned16(io->src) || !aligned16(io->dst) || !aligned16(io->corr32))
         return fail(-4, "tvg_ransac_essential: correspondences must be 16-byte aligned");
     DeviceGuard g(ctx->device);
+    ctx->cur_stream = (cudaStream_t)stream;
     const size_t B = (size_t)io->batch, N = (size_t)io->n_max, H = (size_t)io->H;
     tvg::RansacParams p{};
     p.src = io->src; p.dst = io->dst; p.corr32 = reinterpret_cast<const float4*>(io->corr32);
@@ -342,8 +365,15 @@ int tvg_ransac_essential(tvg_ctx* ctx, const tvg_ransac_io* io, void* stream) {
     p.band_rel = 2e-3f;     // |num^2 - thr^2 den| <= band_rel * thr^2 den  <=>  |r - thr| <~ 1e-3 thr = 5e-6
     p.want_sse = io->sse32 ? 1 : 0;
     p.band_floor = 9e-11f;  // delta^2 / (band_rel / 2), delta = 3e-7: fp32 cancellation error of num
-    int score_mode = 0;
-    tvg::ransac_score_plan(io->batch, io->n_max, io->H, ctx->sm_count, &p.chunks, &p.chunk, &score_mode);
+    tvg::ScorePlan plan{};
+    tvg::ransac_score_plan(io->batch, io->n_max, io->H, ctx->sm_count, ctx->score_hpt, ctx->score_ctas, &plan);
+    p.chunks = plan.slots; p.chunk = plan.rows_per_slot;
+    {
+        void* v = nullptr;
+        int rcq = ctx->get(S_SCOREQ, sizeof(unsigned int), &v, true);
+        if (rcq) return rcq;
+        p.score_queue = reinterpret_cast<unsigned int*>(v);
+    }
     TVG_OUT(ctx, io->models, S_E64, B * H * 9 * sizeof(double), p.E64, double*);
     TVG_GET(ctx, S_E32, B * H * 9 * sizeof(float), p.E32, float*);
     TVG_GET(ctx, S_VALID, B * H * sizeof(int32_t), p.valid, int32_t*);
@@ -379,7 +409,7 @@ int tvg_ransac_essential(tvg_ctx* ctx, const tvg_ransac_io* io, void* stream) {
     if (mrc) return mrc;
     TVG_CUDA(tvg::launch_ransac_fit(p, io->batch, st));
     if ((mrc = ctx->mark(3, st))) return mrc;
-    TVG_CUDA(tvg::launch_ransac_score(p, io->batch, score_mode, st));
+    TVG_CUDA(tvg::launch_ransac_score(p, io->batch, plan, st));
     if ((mrc = ctx->mark(4, st))) return mrc;
     TVG_CUDA(tvg::launch_ransac_reduce(p, io->batch, st));
     if ((mrc = ctx->mark(5, st))) return mrc;
@@ -397,6 +427,7 @@ int tvg_extract_rt(tvg_ctx* ctx, const double* E, int batch, double* Rt, void* s
     if (batch == 0) return 0;
     if (!E || !Rt) return fail(-3, "tvg_extract_rt: NULL array");
     DeviceGuard g(ctx->device);
+    ctx->cur_stream = (cudaStream_t)stream;
     tvg::ExtractRtParams p{E, Rt};
     TVG_CUDA(tvg::launch_extract_rt(p, batch, (cudaStream_t)stream));
     ctx->launches += 1;
@@ -410,7 +441,8 @@ int tvg_pose_chain(tvg_ctx* ctx, const double* Rt, const int32_t* seq_off, int n
     if (nseq == 0) return 0;
     if (!Rt || !seq_off || !poses) return fail(-3, "tvg_pose_chain: NULL array");
     DeviceGuard g(ctx->device);
-    tvg::PoseChainParams p{Rt, seq_off, init_pose, poses, pair_pinv, nullptr};
+    ctx->cur_stream = (cudaStream_t)stream;
+    tvg::PoseChainParams p{Rt, seq_off, init_pose, poses, pair_pinv, nullptr, 0};
     TVG_CUDA(tvg::launch_pose_chain(p, nseq, (cudaStream_t)stream));
     ctx->launches += 1;
     return 0;
@@ -422,6 +454,7 @@ int tvg_invert_poses(tvg_ctx* ctx, const double* poses, int n, double* poses_inv
     if (n == 0) return 0;
     if (!poses || !poses_inv) return fail(-3, "tvg_invert_poses: NULL array");
     DeviceGuard g(ctx->device);
+    ctx->cur_stream = (cudaStream_t)stream;
     TVG_CUDA(tvg::launch_invert4(poses, poses_inv, n, (cudaStream_t)stream));
     ctx->launches += 1;
     return 0;
@@ -438,6 +471,7 @@ int tvg_triangulate(tvg_ctx* ctx, const double* pix1, const double* pix2, int ba
     if (!aligned16(pix1) || !aligned16(pix2) || (reinterpret_cast<uintptr_t>(points4d) & 31u))
         return fail(-4, "tvg_triangulate: pix arrays must be 16-byte, points4d 32-byte aligned");
     DeviceGuard g(ctx->device);
+    ctx->cur_stream = (cudaStream_t)stream;
     tvg::TriParams p{};
     p.pix1 = pix1; p.pix2 = pix2; p.n_pts = n_pts; p.n_max = n_max; p.n = n;
     p.P1 = P1; p.P2 = P2; p.p1_stride = p1_stride; p.p2_stride = p2_stride;
@@ -459,6 +493,7 @@ int tvg_point_quality(tvg_ctx* ctx, const double* pix1, const double* pix2, int 
     if (!aligned16(pix1) || !aligned16(pix2) || (reinterpret_cast<uintptr_t>(points4d) & 31u))
         return fail(-4, "tvg_point_quality: pix arrays must be 16-byte, points4d 32-byte aligned");
     DeviceGuard g(ctx->device);
+    ctx->cur_stream = (cudaStream_t)stream;
     tvg::TriParams p{};
     p.pix1 = pix1; p.pix2 = pix2; p.n_pts = n_pts; p.n_max = n_max; p.n = n;
     p.P1 = P1; p.P2 = P2; p.p1_stride = p1_stride; p.p2_stride = p2_stride;
@@ -481,6 +516,7 @@ int tvg_bundle_adjust_pairs(tvg_ctx* ctx, const double* pix1, const double* pix2
         return fail(-3, "tvg_bundle_adjust_pairs: NULL array");
     if (!aligned16(pix1) || !aligned16(pix2)) return fail(-4, "tvg_bundle_adjust_pairs: pix arrays must be 16-byte aligned");
     DeviceGuard g(ctx->device);
+    ctx->cur_stream = (cudaStream_t)stream;
     tvg::BundleParams p{};
     p.pix1 = pix1; p.pix2 = pix2; p.n_pts = n_pts; p.use = use; p.n_max = n_max; p.n = n; p.iters = iters;
     p.lambda0 = lambda0;
@@ -504,6 +540,7 @@ int tvg_map_accumulate(tvg_ctx* ctx, const double* points4d, const uint8_t* good
     if ((reinterpret_cast<uintptr_t>(points4d) & 31u) || (reinterpret_cast<uintptr_t>(map_points) & 31u))
         return fail(-4, "tvg_map_accumulate: point arrays must be 32-byte aligned");
     DeviceGuard g(ctx->device);
+    ctx->cur_stream = (cudaStream_t)stream;
     tvg::MapParams p{points4d, good, n_pts, seq_off, n_max, cap, include_origin, map_points, map_count, pair_off};
     TVG_CUDA(tvg::launch_map_accumulate(p, nseq, (cudaStream_t)stream));
     ctx->launches += 1;
@@ -529,6 +566,7 @@ int tvg_extract_points(tvg_ctx* ctx, const uint8_t* images, int batch, int heigh
     if (cell > 15 || (size_t)gw * gh * slots > 200u * 1024u)
         return fail(-2, "tvg_extract_points: min_distance > 15.5 or image too large for the shared-memory corner grid");
     DeviceGuard g(ctx->device);
+    ctx->cur_stream = (cudaStream_t)stream;
     cudaStream_t st = (cudaStream_t)stream;
     const size_t B = (size_t)batch, HW = (size_t)height * width;
     tvg::FrontendParams p{};
@@ -563,6 +601,7 @@ int tvg_cheirality(tvg_ctx* ctx, const double* E, const double* src, const doubl
     if (batch == 0) return 0;
     if (!E || !src || !dst || !votes || !Rts || !choice) return fail(-3, "tvg_cheirality: NULL array");
     DeviceGuard g(ctx->device);
+    ctx->cur_stream = (cudaStream_t)stream;
     tvg::CheiralityParams p{E, src, dst, mask, m_count, n_max, m, votes, Rts, choice, nullptr};
     TVG_CUDA(tvg::launch_cheirality(p, batch, (cudaStream_t)stream));
     ctx->launches += 1;
@@ -577,20 +616,16 @@ static int pairs_device_impl(tvg_ctx* ctx, const tvg_pairs_io* io, const double*
     if (!io->words && !io->samples) return fail(-3, "tvg_pairs_device: need words or samples");
     if ((io->pair_q == nullptr) != (io->pair_t == nullptr)) return fail(-3, "tvg_pairs_device: give both pair_q and pair_t or neither");
     DeviceGuard g(ctx->device);
+    ctx->cur_stream = (cudaStream_t)stream;
     cudaStream_t st = (cudaStream_t)stream;
     const size_t B = (size_t)io->batch, N = (size_t)io->n_max;
     const int nseq = io->seq_off ? io->nseq : 1;
     if (nseq < 1) return fail(-2, "tvg_pairs_device: nseq must be >= 1");
 
     // sequence offsets + default consecutive-frame pairing
+    // (seq_off == NULL is one sequence [0, batch): the kernels handle it, no host-side table is uploaded, so the
+    // call stays capturable into a CUDA graph)
     const int32_t* seq_off = io->seq_off;
-    if (!seq_off) {
-        int32_t* so;
-        TVG_GET(ctx, S_SEQOFF, 2 * sizeof(int32_t), so, int32_t*);
-        const int32_t h[2] = {0, io->batch};
-        TVG_CUDA(cudaMemcpyAsync(so, h, sizeof(h), cudaMemcpyHostToDevice, st));
-        seq_off = so;
-    }
     const int32_t *pair_q = io->pair_q, *pair_t = io->pair_t;
     if (!pair_q) {
         int32_t *pq, *pt;
@@ -667,7 +702,7 @@ static int pairs_device_impl(tvg_ctx* ctx, const tvg_pairs_io* io, const double*
     TVG_OUT(ctx, io->points4d, S_POINTS, B * N * 4 * sizeof(double), points, double*);
     TVG_OUT(ctx, io->good, S_GOOD, B * N, good, uint8_t*);
     {
-        tvg::PoseChainParams pc{Rt, seq_off, io->init_pose, poses, pinv, first_init};
+        tvg::PoseChainParams pc{Rt, seq_off, io->init_pose, poses, pinv, first_init, io->batch};
         TVG_CUDA(tvg::launch_pose_chain(pc, nseq, st));
         ctx->launches += 1;
     }
@@ -713,7 +748,13 @@ int tvg_pairs_host_submit(tvg_ctx* ctx, const tvg_pairs_io* hio, int frames, lon
     if (hio->batch < 0 || hio->n_max <= 0 || hio->H <= 0 || frames <= 0) return fail(-2, "tvg_pairs_host: bad sizes");
     if (!hio->des || !hio->kps) return fail(-3, "tvg_pairs_host: NULL frame pools");
     if (!hio->words && !hio->samples) return fail(-3, "tvg_pairs_host: need words or samples");
+    if (ctx->in_flight)
+        return fail(-7, "tvg_pairs_host_submit: a batch is already in flight on this context (call tvg_pairs_host_wait "
+                        "first, or alternate two contexts)");
+    if (hio->sample_stride != 0 && hio->sample_stride != (long long)hio->H * 8)
+        return fail(-2, "tvg_pairs_host: sample_stride must be 0 (shared table) or H*8 (one table per pair)");
     DeviceGuard g(ctx->device);
+    ctx->cur_stream = (cudaStream_t)stream;
     cudaStream_t st = (cudaStream_t)stream;
     const size_t B = (size_t)hio->batch, N = (size_t)hio->n_max, H = (size_t)hio->H, F = (size_t)frames;
     const int nseq = hio->seq_off ? hio->nseq : 1;
@@ -922,12 +963,14 @@ int tvg_pairs_host_submit(tvg_ctx* ctx, const tvg_pairs_io* hio, int frames, lon
     TVG_CUDA(cudaEventRecord(ctx->done_event, st));
     if (bytes_h2d) *bytes_h2d = h2d;
     if (bytes_d2h) *bytes_d2h = d2h;
+    ctx->in_flight = true;
     return 0;
 }
 
 int tvg_pairs_host_wait(tvg_ctx* ctx) {
     if (!ctx) return fail(-1, "ctx is NULL");
     DeviceGuard g(ctx->device);
+    ctx->in_flight = false;
     if (ctx->s_out) TVG_CUDA(cudaStreamSynchronize(ctx->s_out));
     if (ctx->done_event) TVG_CUDA(cudaEventSynchronize(ctx->done_event));
     return 0;

@@ -30,7 +30,7 @@ cudaError_t launch_extract_rt(const ExtractRtParams& p, int batch, cudaStream_t 
 __global__ void pose_chain_kernel(const PoseChainParams p, int nseq) {
     const int s = blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= nseq) return;
-    const int b0 = p.seq_off[s], b1 = p.seq_off[s + 1];
+    const int b0 = p.seq_off ? p.seq_off[s] : 0, b1 = p.seq_off ? p.seq_off[s + 1] : p.batch;
     double cur[16], inv[16];
     const double* init = (s == 0 && p.first_init) ? p.first_init : (p.init_pose ? p.init_pose + (size_t)s * 16 : nullptr);
     for (int i = 0; i < 16; ++i) cur[i] = init ? init[i] : ((i % 5 == 0) ? 1.0 : 0.0);

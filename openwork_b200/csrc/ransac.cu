@@ -140,13 +140,21 @@ cudaError_t launch_ransac_fit(const RansacParams& p, int batch, cudaStream_t str
 
 // ------------------------------------------------------------------------------------ score (fp32)
 constexpr int SCORE_THREADS = 128;
+constexpr int SCORE_CHUNK = 256;          // correspondences per shared-memory stage (4 KB)
+constexpr int SCORE_MAX_ROWS = 32768;     // rows per work item: the packed 16-bit lane counters must not wrap
 
-// One Sampson evaluation in fp32: 19 FFMA (+ 1 MUFU.RCP + 1 FFMA when sum r^2 is wanted) + 2 sign-bit adds.
-// (Packed fma.rn.f32x2 / FFMA2 over the two hypotheses of a thread was measured: same time -- FFMA2 issues at
-// half the FFMA rate on B200, tools/microbench/fp32_pipes.cu -- so the scalar form stays.)
+// One Sampson evaluation in fp32: 19 FFMA (+ 1 MUFU.RCP + 1 FFMA when sum r^2 is wanted) + 2 integer-pipe
+// instructions for BOTH counters: the sign bits of t (inlier) and bt (inside the fp32 uncertainty band) are
+// replicated into the two 16-bit lanes of one word by a single PRMT (selector 0xFFBB: bytes 0,1 = sign of t, bytes
+// 2,3 = sign of bt), and one IADD subtracts that word from the packed accumulator:
+//     acc - 0x0000FFFF  ==  acc + 1 - 0x10000   -> low lane += 1, high lane -= 1
+//     acc - 0xFFFF0000  ==  acc + 0x10000       -> high lane += 1
+// so after <= 32768 rows  low = count, high = (band - count) mod 2^16.
+// (Measured alternatives: SHF + IADD per counter = 4 integer instructions per evaluation, round 1; packed
+// fma.rn.f32x2 over two hypotheses: FFMA2 issues at half the FFMA rate on B200, tools/microbench/fp32_pipes.cu.)
 template <bool SSE>
 __device__ __forceinline__ void score_eval(const float (&e)[9], const float4 c, float thr2, float band,
-                                           float c1, float k1, unsigned& cnt, unsigned& unc, float& sse) {
+                                           float c1, float k1, unsigned& acc, float& sse) {
     // c = (x, y, u, v): x = src (last), u = dst (curr)
     const float f0 = fmaf(e[0], c.x, fmaf(e[1], c.y, e[2]));
     const float f1 = fmaf(e[3], c.x, fmaf(e[4], c.y, e[5]));
@@ -164,8 +172,9 @@ __device__ __forceinline__ void score_eval(const float (&e)[9], const float4 c, 
     const float n2 = fmaf(num, num, k1);
     const float t = fmaf(-thr2, den, n2);              // r < thr  <=>  num^2 - thr^2 den < 0
     const float bt = fmaf(-band, den, fabsf(t));
-    cnt += __float_as_uint(t) >> 31;                   // sign bit == (t < 0)
-    unc += __float_as_uint(bt) >> 31;
+    unsigned w;
+    asm("prmt.b32 %0, %1, %2, 0xFFBB;" : "=r"(w) : "r"(__float_as_uint(t)), "r"(__float_as_uint(bt)));
+    acc -= w;
     if (SSE) {
         float rinv;
         asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(rinv) : "f"(den - c1));
@@ -173,104 +182,164 @@ __device__ __forceinline__ void score_eval(const float (&e)[9], const float4 c, 
     }
 }
 
-// thread = HPT hypotheses (E in registers); the CTA walks `cpc` chunks of CHUNK correspondences through a
-// two-stage shared-memory ring filled by TMA bulk copies; one broadcast LDS.128 feeds HPT evaluations.
-template <int HPT, int CHUNK, bool SSE>
-__global__ void __launch_bounds__(SCORE_THREADS) ransac_score_kernel(const RansacParams p, int cpc) {
-    __shared__ alignas(128) float4 corr[2][CHUNK];
+// Persistent CTAs pull work items from a device-side queue (atomic counter): item = (pair, row slot, block of
+// HPT * 128 hypotheses).  A thread owns HPT hypotheses (E in registers); the item's correspondences stream through a
+// two-stage shared-memory ring filled by TMA bulk copies; one broadcast LDS.128 feeds HPT evaluations.  Items whose
+// row slot lies beyond the pair's match count (known only on the device) cost one queue pop.
+template <int HPT, bool SSE>
+__global__ void __launch_bounds__(SCORE_THREADS) ransac_score_kernel(const RansacParams p, int items, int hblocks) {
+    extern __shared__ __align__(128) unsigned char score_smem[];
+    float4(*corr)[SCORE_CHUNK] = reinterpret_cast<float4(*)[SCORE_CHUNK]>(score_smem);
     __shared__ alignas(8) uint64_t bar[2];
-    const int b = blockIdx.z, slot = blockIdx.y;
-    const int M = p.m_count ? min(p.m_count[b], p.n_max) : p.m;
-    const int r_begin = slot * cpc * CHUNK;
-    const int r_end = min(M, r_begin + cpc * CHUNK);
-    const int n = (r_end > r_begin) ? (r_end - r_begin + CHUNK - 1) / CHUNK : 0;
-    const size_t oc = ((size_t)b * p.chunks + slot) * p.H;
-    const float4* __restrict__ src = p.corr32 + (size_t)b * p.n_max + r_begin;
-
+    __shared__ int s_item;
     if (threadIdx.x == 0) {
         mbar_init(&bar[0], 1);
         mbar_init(&bar[1], 1);
         fence_mbar_init();
     }
-    __syncthreads();
-    auto issue = [&](int i) {
-        const int rows = min(CHUNK, r_end - r_begin - i * CHUNK);
-        mbar_arrive_expect_tx(&bar[i & 1], (uint32_t)rows * 16u);
-        tma_load_1d(corr[i & 1], src + (size_t)i * CHUNK, (uint32_t)rows * 16u, &bar[i & 1]);
-    };
-    if (threadIdx.x == 0) {
-        if (n > 0) issue(0);
-        if (n > 1) issue(1);
-    }
-    float e[HPT][9];
-    int h[HPT];
-    unsigned cnt[HPT], unc[HPT];
-    float sse[HPT];
-#pragma unroll
-    for (int k = 0; k < HPT; ++k) {
-        h[k] = (blockIdx.x * HPT + k) * SCORE_THREADS + threadIdx.x;
-#pragma unroll
-        for (int i = 0; i < 9; ++i) e[k][i] = (h[k] < p.H) ? p.E32[((size_t)b * 9 + i) * p.H + h[k]] : 0.0f;
-        cnt[k] = 0; unc[k] = 0; sse[k] = 0.0f;
-    }
     const float thr2 = (float)(p.thr * p.thr);
     const float band = p.band_rel * thr2;
     const float c1 = p.band_floor / band;   // den offset that realises the absolute floor
     const float k1 = thr2 * c1;             // matching num^2 offset: t stays num^2 - thr^2 den
-    for (int i = 0; i < n; ++i) {
-        mbar_wait(&bar[i & 1], (uint32_t)((i >> 1) & 1));
-        const int rows = min(CHUNK, r_end - r_begin - i * CHUNK);
-        const float4* __restrict__ cp = corr[i & 1];
-#pragma unroll 4
-        for (int j = 0; j < rows; ++j) {
-            const float4 c = cp[j];
-#pragma unroll
-            for (int k = 0; k < HPT; ++k) score_eval<SSE>(e[k], c, thr2, band, c1, k1, cnt[k], unc[k], sse[k]);
+    uint32_t g = 0;                         // chunks consumed so far by this CTA: stage = g & 1, parity = (g >> 1) & 1
+    for (;;) {
+        __syncthreads();                    // barrier init visible / previous item's s_item and stages released
+        if (threadIdx.x == 0) s_item = (int)atomicAdd(p.score_queue, 1u);
+        __syncthreads();
+        const int item = s_item;
+        if (item >= items) break;
+        const int hb = item % hblocks;
+        const int slot = (item / hblocks) % p.chunks;
+        const int b = item / (hblocks * p.chunks);
+        const int M = p.m_count ? min(p.m_count[b], p.n_max) : p.m;
+        const int r_begin = slot * p.chunk;
+        const int r_end = min(M, r_begin + p.chunk);
+        if (r_end <= r_begin && slot > 0) continue;     // slot 0 always writes (zero counts when M == 0)
+        const int n = (r_end > r_begin) ? (r_end - r_begin + SCORE_CHUNK - 1) / SCORE_CHUNK : 0;
+        const size_t oc = ((size_t)b * p.chunks + slot) * p.H;
+        const float4* __restrict__ src = p.corr32 + (size_t)b * p.n_max + r_begin;
+        auto issue = [&](int i) {
+            const int rows = min(SCORE_CHUNK, r_end - r_begin - i * SCORE_CHUNK);
+            const uint32_t st = (g + (uint32_t)i) & 1u;
+            mbar_arrive_expect_tx(&bar[st], (uint32_t)rows * 16u);
+            tma_load_1d(corr[st], src + (size_t)i * SCORE_CHUNK, (uint32_t)rows * 16u, &bar[st]);
+        };
+        if (threadIdx.x == 0) {
+            if (n > 0) issue(0);
+            if (n > 1) issue(1);
         }
-        __syncthreads();   // everyone is done with this stage before TMA refills it
-        if (threadIdx.x == 0 && i + 2 < n) issue(i + 2);
+        float e[HPT][9];
+        int h[HPT];
+        unsigned acc[HPT];
+        float sse[HPT];
+#pragma unroll
+        for (int k = 0; k < HPT; ++k) {
+            h[k] = (hb * HPT + k) * SCORE_THREADS + threadIdx.x;
+#pragma unroll
+            for (int i = 0; i < 9; ++i) e[k][i] = (h[k] < p.H) ? p.E32[((size_t)b * 9 + i) * p.H + h[k]] : 0.0f;
+            acc[k] = 0u; sse[k] = 0.0f;
+        }
+        for (int i = 0; i < n; ++i) {
+            const uint32_t gi = g + (uint32_t)i;
+            mbar_wait(&bar[gi & 1u], (gi >> 1) & 1u);
+            const int rows = min(SCORE_CHUNK, r_end - r_begin - i * SCORE_CHUNK);
+            const float4* __restrict__ cp = corr[gi & 1u];
+#pragma unroll(16 / HPT)
+            for (int j = 0; j < rows; ++j) {
+                const float4 c = cp[j];
+#pragma unroll
+                for (int k = 0; k < HPT; ++k) score_eval<SSE>(e[k], c, thr2, band, c1, k1, acc[k], sse[k]);
+            }
+            __syncthreads();   // everyone is done with this stage before TMA refills it
+            if (threadIdx.x == 0 && i + 2 < n) issue(i + 2);
+        }
+        g += (uint32_t)n;
+#pragma unroll
+        for (int k = 0; k < HPT; ++k)
+            if (h[k] < p.H) {
+                const unsigned cnt = acc[k] & 0xFFFFu;
+                const unsigned unc = ((acc[k] >> 16) + cnt) & 0xFFFFu;
+                p.part_cnt[oc + h[k]] = make_int2((int)cnt, (int)unc);
+                p.part_sse[oc + h[k]] = sse[k];
+            }
     }
-#pragma unroll
-    for (int k = 0; k < HPT; ++k)
-        if (h[k] < p.H) {
-            p.part_cnt[oc + h[k]] = make_int2((int)cnt[k], (int)unc[k]);
-            p.part_sse[oc + h[k]] = sse[k];
-        }
 }
 
-// Partial slots per hypothesis (p.chunks) and correspondences per slot (p.chunk) for a batch: large
-// batches walk all correspondences in one CTA (no partial sums to merge), small ones split M for parallelism.
-void ransac_score_plan(int batch, int n_max, int H, int sm_count, int* slots, int* rows_per_slot, int* mode) {
-    const long long big = (long long)batch * ((H + 2 * SCORE_THREADS - 1) / (2 * SCORE_THREADS));
-    if (big >= 4LL * sm_count) {
-        *mode = 0;                         // <HPT 2, CHUNK 256>, one slot
-        *slots = 1;
-        *rows_per_slot = ((n_max + 255) / 256) * 256;
-    } else {
-        *mode = 1;                         // <HPT 1, CHUNK 128>, split M
-        const int chunks = (n_max + 127) / 128;
-        const long long hb = (long long)batch * ((H + SCORE_THREADS - 1) / SCORE_THREADS);
-        long long want = (4LL * sm_count + hb - 1) / hb;
-        if (want < 1) want = 1;
-        if (want > chunks) want = chunks;
-        const int cpc = (chunks + (int)want - 1) / (int)want;
-        *slots = (chunks + cpc - 1) / cpc;
-        *rows_per_slot = cpc * 128;
+// Work decomposition of the scoring launch.  hpt hypotheses per thread; `slots` row ranges of `rows_per_slot`
+// correspondences each (partial sums merged by the reduce kernel); persistent grid of `ctas_per_sm` CTAs per SM
+// (dynamic shared memory is padded so that no more fit), chosen so that the item count fills whole rounds.
+static int score_max_ctas(int hpt) {
+    static int cached[5] = {0, 0, 0, 0, 0};
+    if (!cached[hpt]) {
+        int n = 0;
+        cudaError_t e = (hpt == 4)
+            ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, ransac_score_kernel<4, false>, SCORE_THREADS, 2 * SCORE_CHUNK * 16)
+            : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, ransac_score_kernel<2, false>, SCORE_THREADS, 2 * SCORE_CHUNK * 16);
+        if (e != cudaSuccess || n < 1) { cudaGetLastError(); n = hpt == 4 ? 5 : 8; }
+        cached[hpt] = n;
     }
+    return cached[hpt];
 }
 
-cudaError_t launch_ransac_score(const RansacParams& p, int batch, int mode, cudaStream_t stream) {
+void ransac_score_plan(int batch, int n_max, int H, int sm_count, int cfg_hpt, int cfg_ctas, ScorePlan* out) {
+    ScorePlan pl{};
+    pl.hpt = (cfg_hpt == 4) ? 4 : 2;
+    const int per_block = pl.hpt * SCORE_THREADS;
+    pl.hblocks = (H + per_block - 1) / per_block;
+    const int chunks = (n_max + SCORE_CHUNK - 1) / SCORE_CHUNK > 0 ? (n_max + SCORE_CHUNK - 1) / SCORE_CHUNK : 1;
+    int max_c = score_max_ctas(pl.hpt);
+    if (cfg_ctas > 0 && cfg_ctas < max_c) max_c = cfg_ctas;
+    // row slots: one when (pair, hypothesis block) items alone give >= 4 rounds of the persistent grid, else split
+    // the rows (a single huge pair); never more than SCORE_MAX_ROWS rows per slot
+    const long long base = (long long)batch * pl.hblocks;
+    long long want = (4LL * sm_count * max_c + base - 1) / base;
+    const long long need = ((long long)chunks * SCORE_CHUNK + SCORE_MAX_ROWS - 1) / SCORE_MAX_ROWS;
+    if (want < need) want = need;
+    if (want < 1) want = 1;
+    if (want > chunks) want = chunks;
+    const int cps = (chunks + (int)want - 1) / (int)want;       // chunks per slot
+    pl.slots = (chunks + cps - 1) / cps;
+    pl.rows_per_slot = cps * SCORE_CHUNK;
+    pl.items = (int)(base * pl.slots);
+    // CTAs per SM: the largest count (>= 60 % of the maximum) whose rounds are filled best
+    int best_c = max_c;
+    double best_eff = 0.0;
+    for (int c = max_c; c >= 1 && c * 10 >= max_c * 6; --c) {
+        const long long per_round = (long long)sm_count * c;
+        const long long rounds = (pl.items + per_round - 1) / per_round;
+        const double eff = (double)pl.items / (double)(rounds * per_round);
+        if (eff > best_eff + 0.01) { best_eff = eff; best_c = c; }
+    }
+    if (cfg_ctas > 0) best_c = cfg_ctas < score_max_ctas(pl.hpt) ? cfg_ctas : score_max_ctas(pl.hpt);
+    pl.ctas_per_sm = best_c;
+    const long long g = (long long)sm_count * best_c;
+    pl.grid = (int)(pl.items < g ? pl.items : g);
+    if (pl.grid < 1) pl.grid = 1;
+    // pad the dynamic shared memory so that exactly ctas_per_sm CTAs fit on an SM (228 KB, 1 KB reserved per CTA)
+    int smem = (int)((228 * 1024) / best_c) - 1024 - 256;
+    smem &= ~127;
+    if (smem < 2 * SCORE_CHUNK * 16) smem = 2 * SCORE_CHUNK * 16;
+    if (smem > 200 * 1024) smem = 200 * 1024;
+    pl.smem = smem;
+    *out = pl;
+}
+
+cudaError_t launch_ransac_score(const RansacParams& p, int batch, const ScorePlan& pl, cudaStream_t stream) {
     // the fp32 sum of squared residuals is diagnostic (selection uses the exact fp64 re-score): computed
     // only when the caller asked for it
-    if (mode == 0) {
-        dim3 grid((p.H + 2 * SCORE_THREADS - 1) / (2 * SCORE_THREADS), p.chunks, batch);
-        if (p.want_sse) ransac_score_kernel<2, 256, true><<<grid, SCORE_THREADS, 0, stream>>>(p, p.chunk / 256);
-        else ransac_score_kernel<2, 256, false><<<grid, SCORE_THREADS, 0, stream>>>(p, p.chunk / 256);
+    (void)batch;
+#define TVG_SCORE_LAUNCH(HPT, SSE)                                                                                    \
+    do {                                                                                                              \
+        cudaError_t e__ = cudaFuncSetAttribute(ransac_score_kernel<HPT, SSE>, cudaFuncAttributeMaxDynamicSharedMemorySize, pl.smem); \
+        if (e__ != cudaSuccess) return e__;                                                                           \
+        ransac_score_kernel<HPT, SSE><<<pl.grid, SCORE_THREADS, pl.smem, stream>>>(p, pl.items, pl.hblocks);         \
+    } while (0)
+    if (pl.hpt == 4) {
+        if (p.want_sse) TVG_SCORE_LAUNCH(4, true); else TVG_SCORE_LAUNCH(4, false);
     } else {
-        dim3 grid((p.H + SCORE_THREADS - 1) / SCORE_THREADS, p.chunks, batch);
-        if (p.want_sse) ransac_score_kernel<1, 128, true><<<grid, SCORE_THREADS, 0, stream>>>(p, p.chunk / 128);
-        else ransac_score_kernel<1, 128, false><<<grid, SCORE_THREADS, 0, stream>>>(p, p.chunk / 128);
+        if (p.want_sse) TVG_SCORE_LAUNCH(2, true); else TVG_SCORE_LAUNCH(2, false);
     }
+#undef TVG_SCORE_LAUNCH
     return cudaGetLastError();
 }
 
@@ -323,7 +392,10 @@ __global__ void __launch_bounds__(REDUCE_THREADS) ransac_reduce_kernel(const Ran
         }
     }
     __syncthreads();
-    if (tid == 0) p.n_cand[b] = s_ncand;
+    if (tid == 0) {
+        p.n_cand[b] = s_ncand;
+        if (b == 0) *p.score_queue = 0u;   // the scoring kernel's work queue, ready for the next launch
+    }
 }
 
 cudaError_t launch_ransac_reduce(const RansacParams& p, int batch, cudaStream_t stream) {
@@ -385,6 +457,40 @@ cudaError_t launch_ransac_rescore(const RansacParams& p, int batch, cudaStream_t
 
 // ------------------------------------------------------------------------------------ select + mask + refit
 constexpr int REFIT_THREADS = 256;
+
+// skimage's selection rule as a TOTAL order, so that the winner does not depend on the order
+// in which candidates are visited: most inliers, then smallest sum of squared residuals (NaN counts as +inf), then
+// earliest trial.  The scan starts from skimage's initial state (0 inliers, rss = inf, no model): a hypothesis
+// with 0 inliers is a model only when its rss is finite (`rss < inf`).
+struct BestSel {
+    int c, h;
+    double s;
+};
+__device__ __forceinline__ BestSel best_init() { return BestSel{0, 0x7fffffff, __longlong_as_double(0x7ff0000000000000LL)}; }
+__device__ __forceinline__ double sse_key(double s) { return (s == s) ? s : __longlong_as_double(0x7ff0000000000000LL); }
+__device__ __forceinline__ void best_update(BestSel& b, int c, double s, int h) {
+    s = sse_key(s);
+    if ((c > b.c) || (c == b.c && (s < b.s || (s == b.s && h < b.h)))) { b.c = c; b.s = s; b.h = h; }
+}
+__device__ __forceinline__ bool best_is_model(const BestSel& b) {
+    return b.h != 0x7fffffff && (b.c > 0 || b.s < __longlong_as_double(0x7ff0000000000000LL));
+}
+// block-wide reduction of per-thread BestSel (REFIT_THREADS threads); the result is valid on thread 0
+__device__ __forceinline__ BestSel best_block_reduce(BestSel v, int* s_bc, int* s_bh, double* s_bs) {
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+#pragma unroll
+    for (int m = 16; m > 0; m >>= 1) {
+        const int oc = __shfl_xor_sync(0xffffffffu, v.c, m);
+        const int ohh = __shfl_xor_sync(0xffffffffu, v.h, m);
+        const double os = shfl_xor_f64(v.s, m);
+        best_update(v, oc, os, ohh);
+    }
+    if (lane == 0) { s_bc[warp] = v.c; s_bs[warp] = v.s; s_bh[warp] = v.h; }
+    __syncthreads();
+    if (tid == 0)
+        for (int w = 1; w < REFIT_THREADS / 32; ++w) best_update(v, s_bc[w], s_bs[w], s_bh[w]);
+    return v;
+}
 constexpr int REFIT_WS = 64;   // doubles of hand-off per pair between the accumulate and solve kernels
 int ransac_refit_ws_doubles() { return REFIT_WS; }
 
@@ -464,34 +570,17 @@ __global__ void __launch_bounds__(REFIT_THREADS, 2) ransac_refit_kernel(const Ra
     const double qnan = __longlong_as_double(0x7ff8000000000000LL);
 
     // ---- best = (max count, min sum r^2, earliest) over the exactly re-scored candidates
-    int bc = -1, bh = 0x7fffffff;
-    double bs = 0.0;
+    BestSel sel = best_init();
     for (int ci = tid; ci < ncand; ci += REFIT_THREADS) {
         const int h = p.cand[oh + ci];
-        const int c = p.cand_cnt[oh + h];
-        const double s = p.cand_sse[oh + h];
-        // NaN sums never win a tie (python: `rss < best_rss` is False)
-        const bool better = (c > bc) || (c == bc && (s < bs || (s == bs && h < bh)));
-        if (better) { bc = c; bs = s; bh = h; }
+        best_update(sel, p.cand_cnt[oh + h], p.cand_sse[oh + h], h);
     }
-#pragma unroll
-    for (int m = 16; m > 0; m >>= 1) {
-        const int oc = __shfl_xor_sync(0xffffffffu, bc, m);
-        const int ohh = __shfl_xor_sync(0xffffffffu, bh, m);
-        const double os = shfl_xor_f64(bs, m);
-        if ((oc > bc) || (oc == bc && (os < bs || (os == bs && ohh < bh)))) { bc = oc; bs = os; bh = ohh; }
-    }
-    if (lane == 0) { s_bc[warp] = bc; s_bs[warp] = bs; s_bh[warp] = bh; }
-    __syncthreads();
+    sel = best_block_reduce(sel, s_bc, s_bh, s_bs);
     if (tid == 0) {
-        for (int w = 1; w < REFIT_THREADS / 32; ++w) {
-            const int oc = s_bc[w], ohh = s_bh[w];
-            const double os = s_bs[w];
-            if ((oc > bc) || (oc == bc && (os < bs || (os == bs && ohh < bh)))) { bc = oc; bs = os; bh = ohh; }
-        }
-        s_best = (bc >= 0) ? bh : -1;
+        const bool have = best_is_model(sel);
+        s_best = have ? sel.h : -1;
         p.best[b] = s_best;
-        p.best_sse[b] = (bc >= 0) ? bs : qnan;
+        p.best_sse[b] = have ? p.cand_sse[oh + sel.h] : qnan;
     }
     __syncthreads();
     const int best = s_best;
@@ -642,33 +731,17 @@ __global__ void __launch_bounds__(REFIT_THREADS) ransac_refit_big_select_kernel(
     const size_t oh = (size_t)b * p.H;
     const int ncand = p.n_cand[b];
     const double qnan = __longlong_as_double(0x7ff8000000000000LL);
-    int bc = -1, bh = 0x7fffffff;
-    double bs = 0.0;
+    BestSel sel = best_init();
     for (int ci = tid; ci < ncand; ci += REFIT_THREADS) {
         const int h = p.cand[oh + ci];
-        const int c = p.cand_cnt[oh + h];
-        const double s = p.cand_sse[oh + h];
-        const bool better = (c > bc) || (c == bc && (s < bs || (s == bs && h < bh)));
-        if (better) { bc = c; bs = s; bh = h; }
+        best_update(sel, p.cand_cnt[oh + h], p.cand_sse[oh + h], h);
     }
-#pragma unroll
-    for (int m = 16; m > 0; m >>= 1) {
-        const int oc = __shfl_xor_sync(0xffffffffu, bc, m);
-        const int ohh = __shfl_xor_sync(0xffffffffu, bh, m);
-        const double os = shfl_xor_f64(bs, m);
-        if ((oc > bc) || (oc == bc && (os < bs || (os == bs && ohh < bh)))) { bc = oc; bs = os; bh = ohh; }
-    }
-    if (lane == 0) { s_bc[warp] = bc; s_bs[warp] = bs; s_bh[warp] = bh; }
-    __syncthreads();
+    sel = best_block_reduce(sel, s_bc, s_bh, s_bs);
     if (tid == 0) {
-        for (int w = 1; w < REFIT_THREADS / 32; ++w) {
-            const int oc = s_bc[w], ohh = s_bh[w];
-            const double os = s_bs[w];
-            if ((oc > bc) || (oc == bc && (os < bs || (os == bs && ohh < bh)))) { bc = oc; bs = os; bh = ohh; }
-        }
-        const int best = (bc >= 0) ? bh : -1;
+        const bool have = best_is_model(sel);
+        const int best = have ? sel.h : -1;
         p.best[b] = best;
-        p.best_sse[b] = (bc >= 0) ? bs : qnan;
+        p.best_sse[b] = have ? p.cand_sse[oh + sel.h] : qnan;
         if (best < 0) {
             p.n_inl[b] = 0;
             p.status[b] = (M <= 8) ? 1 : 2;

@@ -75,6 +75,7 @@ struct RansacParams {
     float* E32;                // [batch][9][H]  Frobenius-normalised, SoA
     int32_t* valid;            // [batch][H]
     int chunks, chunk;         // partial-sum slots per hypothesis, correspondences covered by one slot
+    unsigned int* score_queue; // work-item counter of the scoring kernel: zero on entry, zeroed again by the reduce kernel
     int2* part_cnt;            // [batch][chunks][H] (count, band)
     float* part_sse;           // [batch][chunks][H]
     int32_t* counts;           // [batch][H]  (-1 = failed fit)
@@ -106,8 +107,14 @@ struct RansacParams {
     double* refit_big;         // [batch][ransac_refit_big_blocks(n_max)][ransac_refit_big_stride()] (NULL -> single-CTA refit)
 };
 cudaError_t launch_ransac_fit(const RansacParams& p, int batch, cudaStream_t stream);
-cudaError_t launch_ransac_score(const RansacParams& p, int batch, int mode, cudaStream_t stream);
-void ransac_score_plan(int batch, int n_max, int H, int sm_count, int* slots, int* rows_per_slot, int* mode);
+// scoring launch plan: hypotheses per thread, row slots (p.chunks) x rows per slot (p.chunk), persistent grid
+struct ScorePlan {
+    int hpt, hblocks, slots, rows_per_slot, items, ctas_per_sm, grid, smem;
+};
+// cfg_hpt in {0 (default 2), 2, 4}; cfg_ctas > 0 forces the resident CTAs per SM
+void ransac_score_plan(int batch, int n_max, int H, int sm_count, int cfg_hpt, int cfg_ctas, ScorePlan* out);
+// queue: one zeroed unsigned int (the work-item counter; the reduce kernel zeroes it again)
+cudaError_t launch_ransac_score(const RansacParams& p, int batch, const ScorePlan& plan, cudaStream_t stream);
 cudaError_t launch_ransac_reduce(const RansacParams& p, int batch, cudaStream_t stream);
 cudaError_t launch_ransac_rescore(const RansacParams& p, int batch, cudaStream_t stream);
 cudaError_t launch_ransac_refit(const RansacParams& p, int batch, cudaStream_t stream);
@@ -118,11 +125,12 @@ int ransac_refit_big_stride();
 // ---------------------------------------------------------------- pose + triangulation (pose_tri.cu)
 struct PoseChainParams {
     const double* Rt;          // [batch][16]
-    const int32_t* seq_off;    // [nseq+1] pair offsets of each sequence
+    const int32_t* seq_off;    // [nseq+1] pair offsets of each sequence (NULL -> {0, batch})
     const double* init_pose;   // [nseq][16] (NULL -> identity)
     double* poses;             // [batch + nseq][16]  pose of pair b's LAST frame at [b + s], CURR at [b + s + 1]
     double* pair_pinv;         // [batch][2][16] inv(last pose), inv(curr pose) per pair (may be NULL)
     const double* first_init;  // device 4x4 overriding the initial pose of sequence 0 of this launch (may be NULL)
+    int batch;                 // used when seq_off == NULL: one sequence holding pairs [0, batch)
 };
 cudaError_t launch_pose_chain(const PoseChainParams& p, int nseq, cudaStream_t stream);
 
