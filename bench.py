@@ -297,6 +297,120 @@ def frontend_rate(ops, ctx, dev, frames=256):
             "keypoints_per_frame": float(n.float().mean().item())}
 
 
+# ----------------------------------------------------------------------------------------- C4 / C5
+
+C4_SEQS, C4_PAIRS = 64, 500       # BASELINE.json config C4: 64 sequences x 500 frame pairs at 2k keypoints
+C5_N, C5_H = 65536, 65536         # config C5: one 64k x 64k pair, 65536 hypotheses
+
+
+def c4_sequences(ops, ctx, K, dev, rank, world, barrier, reps=2, seqs_per_call=2):
+    """Config C4: sequence s -> rank s mod G, NO data-path collective.  Frames are shared between consecutive pairs
+    (slam.py:243, 271: pair (t-1, t) of a sequence), whole sequences per call, pose chain on the device.  Each rank
+    synthesises two distinct 501-frame sequences and places copies at distinct HBM addresses for the rest of its
+    share (timing needs the bytes, not new scenes).  Returns (local ms per sweep, info dict)."""
+    import torch
+    from openwork_b200 import dist as tdist, synth
+    mine = tdist.shard_sequences(C4_SEQS, rank, world)
+    F = C4_PAIRS + 1
+    base = []
+    for d in range(min(2, len(mine))):
+        frames, _ = synth.make_sequence(F, N_KPTS, seed=4000 + mine[d])       # seed = 1000*config + sequence_id
+        base.append((np.stack([f[1] for f in frames]), np.stack([f[0] for f in frames])))
+    des = torch.empty((len(mine), F, N_KPTS, 32), dtype=torch.uint8, device=dev)
+    kps = torch.empty((len(mine), F, N_KPTS, 2), dtype=torch.float64, device=dev)
+    for i in range(len(mine)):
+        d, k = base[i % len(base)]
+        des[i].copy_(torch.from_numpy(d))
+        kps[i].copy_(torch.from_numpy(k))
+    words = torch.from_numpy(synth.sample_words(N_HYP, 4004).view(np.int32)).to(dev)
+    outs = ("m_count", "n_inl", "E", "Rt", "poses", "points4d", "good", "status")
+    bufs = {}
+
+    def sweep():
+        for s0 in range(0, len(mine), seqs_per_call):
+            ns = min(seqs_per_call, len(mine) - s0)
+            seq_off = torch.arange(0, ns + 1, dtype=torch.int32, device=dev) * C4_PAIRS
+            bufs[ns] = ops.process_pairs_device(des[s0:s0 + ns].reshape(ns * F, N_KPTS, 32),
+                                                kps[s0:s0 + ns].reshape(ns * F, N_KPTS, 2), K, words=words,
+                                                seq_off=seq_off, ratio=RATIO, residual_threshold=THR, outputs=outs,
+                                                out=bufs.get(ns), batch=ns * C4_PAIRS, ctx=ctx)
+    sweep()
+    torch.cuda.synchronize()
+    bad = sum(int((b["status"] != 0).sum().item()) for b in bufs.values())
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        sweep()
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1) / reps
+    info = {"sequences": C4_SEQS, "pairs_per_sequence": C4_PAIRS, "sequences_this_rank": len(mine),
+            "frames_shared_between_pairs": True, "pairs_per_call": seqs_per_call * C4_PAIRS,
+            "status_nonzero_rank0": bad, "collectives": 0}
+    del des, kps
+    return ms, info
+
+
+def c5_huge_pair(ops, K, dev, rank, world, local, barrier, reps=5):
+    """Config C5: ONE 64k x 64k pair, 65536 hypotheses, query rows + hypotheses split over the ranks (tvg_huge_pair
+    over the context's NCCL communicator: two fixed-size all-gathers).  Returns (local ms per pair, stage ms,
+    equals_single_rank, info): equals_single_rank compares, on every rank, the G-rank outputs bit for bit with the
+    same call on a context without a communicator."""
+    import torch
+    from openwork_b200 import _lib, dist as tdist, synth
+    lk, ld, ck, cd = synth.make_pair_large(C5_N, 5005)
+    words = torch.from_numpy(synth.sample_words(C5_H, 5005).view(np.int32)).to(dev)
+    ldd, cdd = torch.from_numpy(ld).to(dev), torch.from_numpy(cd).to(dev)
+    lkd, ckd = torch.from_numpy(lk).to(dev), torch.from_numpy(ck).to(dev)
+    ctx = tdist.init_comm(ops.context(local))
+    outs = ("idx", "dist", "qidx", "tidx", "m_count", "E", "E_best", "best", "best_sse", "mask", "n_inl", "inl_idx", "Rt",
+            "poses", "points4d", "good", "status")
+    out = None
+
+    def run(c, o):
+        return ops.huge_pair(ckd, cdd, lkd, ldd, K, words=words, ratio=RATIO, residual_threshold=THR, outputs=outs,
+                             out=o, ctx=c)
+    for _ in range(3):
+        out = run(ctx, out)
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    l0 = ctx.launches
+    e0.record()
+    for _ in range(reps):
+        out = run(ctx, out)
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1) / reps
+    launches = (ctx.launches - l0) // reps
+    ctx.set_profile(True)
+    acc = None
+    for _ in range(3):
+        out = run(ctx, out)
+        sm = ctx.stage_ms()
+        acc = sm if acc is None else {k: acc[k] + v for k, v in sm.items()}
+    ctx.set_profile(False)
+    stage = {k: v / 3 for k, v in acc.items()}
+    M, n_in = int(out["m_count"].item()), int(out["n_inl"].item())
+    same = None
+    if world > 1:
+        solo = _lib.Context(local)                       # no communicator: the one-rank run of the same call
+        ref = run(solo, None)
+        torch.cuda.synchronize()
+        same = int(ref["m_count"].item()) == M and int(ref["n_inl"].item()) == n_in
+        for k in ("best", "best_sse", "E", "E_best", "Rt", "poses", "status"):
+            same = same and bool(torch.equal(ref[k], out[k]))
+        for k, n in (("idx", C5_N), ("dist", C5_N), ("qidx", M), ("tidx", M), ("mask", M), ("inl_idx", n_in),
+                     ("points4d", n_in), ("good", n_in)):
+            same = same and bool(torch.equal(ref[k][:n], out[k][:n]))
+        solo.close()
+    info = {"kpts": C5_N, "hypotheses": C5_H, "matches": M, "inliers": n_in, "best": int(out["best"].item()),
+            "status": int(out["status"].item()), "launches_per_pair": int(launches),
+            "collectives_per_pair": 2 if world > 1 else 0,
+            "exchange": "all-gather of idx/dist/keep blocks (17 B per query row) + all-gather of one 96-byte record per rank"}
+    return ms, stage, same, info
+
+
 # ----------------------------------------------------------------------------------------- our arm
 def run_ours(args):
     import torch
@@ -433,37 +547,100 @@ def run_ours(args):
     # alternate, so the H2D copies of step i+1 overlap the kernels of step i; every step still moves its own
     # inputs host->device and its own results device->host inside the timed region)
     from openwork_b200 import _lib
-    e2e_outs = ("m_count", "E", "n_inl", "Rt", "poses", "status")
-    ctxs = [ctx, _lib.Context(local)]
+    # everything process_frame hands on (slam.py:259-269): the pose, the matches, the inlier mask, the triangulated
+    # points and their z > 0 flags -- padded per-pair arrays, copied device -> host inside the timed region
+    e2e_outs = ("m_count", "E", "n_inl", "Rt", "poses", "status", "qidx", "tidx", "mask", "points4d", "good")
+    NC = max(2, args.e2e_contexts)
+    ctxs = [ctx] + [_lib.Context(local) for _ in range(NC - 1)]
     for c in ctxs:
         if args.knn_variant is not None:
             c.set_matcher_config(args.knn_r or 4, args.knn_variant, args.knn_ctas)
         c.set_host_chunk(args.host_chunk)
-    host_out = [None, None]
+    host_out = [None] * NC
     h2d = d2h = 0
     pq_h, pt_h, so_h = pair_q.cpu(), pair_t.cpu(), seq_off.cpu()
 
     def e2e_submit(i):
         nonlocal h2d, d2h
-        host_out[i % 2], h2d, d2h = ops.process_pairs_host(des_pin, kps_pin, K, words=words_pin, pair_q=pq_h,
-                                                           pair_t=pt_h, seq_off=so_h, ratio=RATIO,
-                                                           residual_threshold=THR, outputs=e2e_outs,
-                                                           out=host_out[i % 2], ctx=ctxs[i % 2], wait=False)
-    for i in range(4):
+        host_out[i % NC], h2d, d2h = ops.process_pairs_host(des_pin, kps_pin, K, words=words_pin, pair_q=pq_h,
+                                                            pair_t=pt_h, seq_off=so_h, ratio=RATIO,
+                                                            residual_threshold=THR, outputs=e2e_outs,
+                                                            out=host_out[i % NC], ctx=ctxs[i % NC], wait=False)
+
+    def e2e_loop(submit, steps):
+        """NC batches in flight: the copies of step i overlap the kernels of step i-1 and the result copies of step
+        i-2; the results of step i-NC+1 are on the host before step i+1 is submitted."""
+        t0 = time.perf_counter()
+        for i in range(steps):
+            submit(i)
+            if i >= NC - 1:
+                ops.wait_pairs_host(ctxs[(i - NC + 1) % NC])
+        for i in range(max(steps - NC + 1, 0), steps):
+            ops.wait_pairs_host(ctxs[i % NC])
+        barrier()
+        return time.perf_counter() - t0
+    for i in range(2 * NC):
         e2e_submit(i)
-        ops.wait_pairs_host(ctxs[i % 2])
+        ops.wait_pairs_host(ctxs[i % NC])
     barrier()
     e2e_steps = max(4, min(2 * args.steps, 20))
-    t0 = time.perf_counter()
-    e2e_submit(0)
-    for i in range(1, e2e_steps):
-        e2e_submit(i)
-        ops.wait_pairs_host(ctxs[(i - 1) % 2])          # results of step i-1 are on the host now
-    ops.wait_pairs_host(ctxs[(e2e_steps - 1) % 2])
-    barrier()
-    e2e_s = time.perf_counter() - t0
-    if (host_out[0]["status"].numpy() != 0).any() or (host_out[1]["status"].numpy() != 0).any():
+    e2e_s = e2e_loop(e2e_submit, e2e_steps)
+    if any((o["status"].numpy() != 0).any() for o in host_out):
         raise SystemExit("bench.py: e2e pipeline reported status != 0")
+
+    # ---- e2e on C4-shaped input: sequences whose consecutive pairs share a frame (slam.py:243, 271), so a pair
+    # costs one frame of host->device traffic instead of two.  Same streaming entry, same outputs.
+    n_seq_e2e = 8
+    ppseq = max(P // n_seq_e2e, 1)
+    from openwork_b200 import synth as _synth
+    seq_frames = []
+    for sidx in range(2):
+        fr, _ = _synth.make_sequence(ppseq + 1, N_KPTS, seed=4000 + 100 * rank + sidx)
+        seq_frames.append((np.stack([f[1] for f in fr]), np.stack([f[0] for f in fr])))
+    des4 = torch.from_numpy(np.concatenate([seq_frames[i % 2][0] for i in range(n_seq_e2e)])).pin_memory()
+    kps4 = torch.from_numpy(np.concatenate([seq_frames[i % 2][1] for i in range(n_seq_e2e)])).pin_memory()
+    so4 = torch.arange(0, n_seq_e2e + 1, dtype=torch.int32) * ppseq
+    host_out4 = [None] * NC
+    h2d4 = d2h4 = 0
+
+    def e2e4_submit(i):
+        nonlocal h2d4, d2h4
+        host_out4[i % NC], h2d4, d2h4 = ops.process_pairs_host(des4, kps4, K, words=words_pin, seq_off=so4, ratio=RATIO,
+                                                               residual_threshold=THR, outputs=e2e_outs,
+                                                               out=host_out4[i % NC], ctx=ctxs[i % NC], wait=False)
+    for c in ctxs:
+        c.set_host_chunk(args.host_chunk_c4)
+    for i in range(NC):
+        e2e4_submit(i)
+        ops.wait_pairs_host(ctxs[i % NC])
+    barrier()
+    e2e4_s = e2e_loop(e2e4_submit, e2e_steps)
+    ctx.set_host_chunk(args.host_chunk)
+    if any((o["status"].numpy() != 0).any() for o in host_out4):
+        raise SystemExit("bench.py: C4-shaped e2e pipeline reported status != 0")
+    del ctxs[1:]
+
+    # ---- bare host->device bandwidth with every rank copying at once (what bounds e2e when ranks share the host)
+    probe = torch.empty(256 << 20, dtype=torch.uint8).pin_memory()
+    probe_d = torch.empty_like(probe, device=dev)
+    probe_d.copy_(probe, non_blocking=True)
+    barrier()
+    p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    p0.record()
+    for _ in range(4):
+        probe_d.copy_(probe, non_blocking=True)
+    p1.record()
+    barrier()
+    h2d_gbs = 4 * probe.numel() / (p0.elapsed_time(p1) / 1e3) / 1e9
+    del probe, probe_d
+
+    # ---- the sharded configs of BASELINE.json: C4 (sequences, no collective) and C5 (one huge pair over NCCL)
+    c4_ms = c5_ms = 0.0
+    c4_info = c5_info = c5_stage = c5_same = None
+    if not args.no_c4:
+        c4_ms, c4_info = c4_sequences(ops, ctx, K, dev, rank, world, barrier)
+    if not args.no_c5:
+        c5_ms, c5_stage, c5_same, c5_info = c5_huge_pair(ops, K, dev, rank, world, local, barrier)
 
     single = None
     if rank == 0 and not args.no_single_pair:
@@ -474,10 +651,14 @@ def run_ours(args):
     if rank == 0 and not args.no_frontend:
         frontend = frontend_rate(ops, ctx, dev)
 
-    t = torch.tensor([ms, knn_ms, e2e_s], dtype=torch.float64, device=dev)
+    t = torch.tensor([ms, knn_ms, e2e_s, e2e4_s, c4_ms, c5_ms, -h2d_gbs, 0.0 if c5_same in (None, True) else 1.0],
+                     dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms, knn_ms, e2e_s = [float(x) for x in t.cpu()]
+    ms, knn_ms, e2e_s, e2e4_s, c4_ms, c5_ms, h2d_min, c5_diff = [float(x) for x in t.cpu()]
+    h2d_min = -h2d_min
+    if c5_same is not None:
+        c5_same = c5_diff == 0.0                      # every rank compared its own copy
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -559,6 +740,25 @@ def run_ours(args):
                         "note": "64 B/point (2 x (x,y) f64 in, (x,y,z,1) f64 out) + 1 B flag; per-point fp64 Jacobi SVD "
                                 "keeps it far below the HBM roofline"},
     }
+    # `roofline` names the dominant kernel of the step (by the stage events of the timed configuration); the other
+    # one stays beside it
+    score_roofline = {
+        "kernel": "ransac_score_kernel<2,false> (fp32 Sampson scoring of H x M (hypothesis, correspondence) pairs; "
+                  "persistent CTAs on a device-side work queue, correspondences staged by TMA bulk copies)",
+        "bound": "fp32", "achieved": score_tflops, "peak": fp32_peak, "unit": "TFLOP/s", "frac": score_tflops / fp32_peak,
+        "peak_note": "FP32 FMA pipe: %d SMs x 128 lanes x 2 flop x sm_max_mhz (%s clock; MEASURED_PEAKS.json holds no "
+                     "fp32 figure); tools/microbench/ffma_operands.cu measures 0.93 of it for FFMAs with two fresh "
+                     "register operands and 0.46 with three (register-file read bandwidth)" % (n_sm, peak_kind),
+        "ms_per_launch": stage_ms["score"], "evaluations_per_launch": evals, "flop_per_evaluation": 36,
+        "algorithmic_flop_per_launch": evals * 36, "sm_mhz_during_run": f_mhz,
+        # dram__bytes_read.sum + dram__bytes_write.sum at P=1024 (profiles/r2_kernels_score_fit_tri.md)
+        "traffic": (62.87e6 + 7.18e6) * P / 1024,
+        "traffic_note": "algorithmic bytes: fp32 correspondences (16 B x sum M) + E32 (36 B x H) per pair = %.1f MB" %
+                        ((16.0 * sum_m + 36.0 * N_HYP * P) / 1e6),
+    }
+    dominant = "score" if stage_ms["score"] >= stage_ms["knn2"] else "knn2"
+    roofline_other = roofline if dominant == "score" else score_roofline
+    roofline = score_roofline if dominant == "score" else roofline
     cores = len(os.sched_getaffinity(0))
     if args.no_cpu_baseline or world > 1:
         cpu = None
@@ -582,8 +782,21 @@ def run_ours(args):
                                else args.knn_variant, "r": args.knn_r, "ctas_per_sm": args.knn_ctas}},
         "hamming_gcmp_s": gcmp_s * world, "clocks": clocks, "gpu_launches": int(launches),
         "e2e": {"value": e2e_value, "unit": "pairs/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-                "steps": e2e_steps, "mode": "tvg_pairs_host_submit/_wait, 2 contexts alternating"},
-        "roofline": roofline, "kernels": kernels, "cpu_baseline": cpu, "single_pair": single,
+                "steps": e2e_steps, "mode": "tvg_pairs_host_submit/_wait, %d contexts in rotation, host chunk %d pairs" % (NC, args.host_chunk)},
+        "e2e_c4_shared_frames": {"value": world * n_seq_e2e * ppseq * e2e_steps / e2e4_s, "unit": "pairs/s",
+                                 "h2d_bytes_per_step": int(h2d4), "d2h_bytes_per_step": int(d2h4), "steps": e2e_steps,
+                                 "sequences_per_step": n_seq_e2e, "pairs_per_sequence": ppseq,
+                                 "host_chunk_pairs": args.host_chunk_c4,
+                                 "note": "same entry and outputs; consecutive pairs of a sequence share a frame, so a "
+                                         "pair costs one frame (98 KB) of host->device traffic instead of two"},
+        "h2d_gbs_per_rank_all_ranks_copying": h2d_min,
+        "c4": None if c4_info is None else dict(c4_info, ms_per_sweep=c4_ms, n_gpus=world,
+                                                value=C4_SEQS * C4_PAIRS / (c4_ms / 1e3), unit="pairs/s"),
+        "c5": None if c5_info is None else dict(c5_info, ms_per_pair=c5_ms, n_gpus=world, stage_ms_rank0=c5_stage,
+                                                equals_single_rank=c5_same,
+                                                hamming_gcmp_s=C5_N * C5_N / (c5_ms / 1e3) / 1e9),
+        "roofline": roofline, "roofline_second_kernel": roofline_other, "kernels": kernels, "cpu_baseline": cpu,
+        "single_pair": single,
         "frontend_outside_metric": frontend,
     }
     print(json.dumps(line))
@@ -608,11 +821,16 @@ def main():
     ap.add_argument("--knn-variant", type=int, default=None,
                     help="matcher variant (default: library auto; 16 = tensor cores, 0..11 = integer-pipe variants)")
     ap.add_argument("--knn-ctas", type=int, default=6)
-    ap.add_argument("--host-chunk", type=int, default=4096,
-                    help="pairs per chunk of the e2e host pipeline (streaming mode overlaps across batches, so large)")
+    ap.add_argument("--host-chunk", type=int, default=1024,
+                    help="pairs per chunk of the e2e host pipeline, independent pairs (measured best of 128..4096)")
+    ap.add_argument("--host-chunk-c4", type=int, default=4096,
+                    help="pairs per chunk of the e2e host pipeline, C4-shaped input (shared frames)")
+    ap.add_argument("--e2e-contexts", type=int, default=3, help="batches in flight in the e2e measurement")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-single-pair", action="store_true")
     ap.add_argument("--no-frontend", action="store_true")
+    ap.add_argument("--no-c4", action="store_true", help="skip the C4 extra (64 sequences x 500 pairs, sharded)")
+    ap.add_argument("--no-c5", action="store_true", help="skip the C5 extra (one 64k x 64k pair over the ranks)")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)

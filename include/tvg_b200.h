@@ -280,6 +280,69 @@ TVG_API int tvg_pairs_host_submit(tvg_ctx* ctx, const tvg_pairs_io* io, int fram
                           long long* bytes_d2h, void* stream);
 TVG_API int tvg_pairs_host_wait(tvg_ctx* ctx);
 
+/* ---- multi-GPU (one process per GPU) ---------------------------------------------------------------------------
+ * An NCCL communicator bound to a context ("context create/destroy for workspace + NCCL communicator").
+ * Rank 0 calls tvg_comm_unique_id and hands the 128 bytes to the other ranks over any host channel (the Python
+ * layer broadcasts them through torch.distributed); every rank then calls tvg_comm_init (collective).  NCCL is
+ * resolved at run time (libnccl.so.2); the single-GPU entry points never need it. */
+#define TVG_COMM_ID_BYTES 128
+TVG_API int tvg_comm_unique_id(void* id_out);
+TVG_API int tvg_comm_init(tvg_ctx* ctx, const void* id_bytes, int rank, int world);
+TVG_API int tvg_comm_destroy(tvg_ctx* ctx);
+TVG_API int tvg_comm_info(const tvg_ctx* ctx, int* rank, int* world);
+
+/* Contiguous block [lo, hi) of n items owned by `rank` (the first n % world ranks own one more). */
+TVG_API void tvg_shard_range(int n, int rank, int world, int* lo, int* hi);
+/* Rows every per-row array of tvg_huge_pair must hold: max(ceil(nq / world) * world, nt). */
+TVG_API int tvg_huge_pair_rows(int nq, int nt, int world);
+
+/* ONE huge keyframe pair (BASELINE.json config C5: 64k x 64k descriptors, 65536 hypotheses) split over the ranks of
+ * the context's communicator; the `else` branch of process_frame (slam.py:249-266) for that pair, device resident, no
+ * host synchronisation.  Inputs are replicated on every rank (descriptor sets are <= 2 MiB).
+ *   matcher     rank r matches query rows [r * per, (r + 1) * per), per = ceil(nq / world), against the whole train set
+ *   exchange 1  fixed-size all-gather of idx / dist / keep (rank order = ascending query order)
+ *   compaction  ratio loop + gathers + K-normalisation over all rows, on every rank (identical)
+ *   RANSAC      rank r fits and scores hypotheses tvg_shard_range(H, r, world) of the SAME table; exact fp64
+ *               re-score of its finalists; its best as a 96-byte record {count, hypothesis, sum r^2, E}
+ *   exchange 2  all-gather of the records; every rank applies the reference's selection rule (most inliers, then
+ *               smallest sum of squared residuals, then earliest trial; skimage ransac) to the same
+ *               list with exact keys: world ranks return bit for bit what one rank returns
+ *   refit ...   inlier mask, refit, extract_Rt, pose, triangulation, z > 0 on every rank (identical)
+ * Without a communicator (or world = 1) the same code runs with no exchange.  Every output is optional and, except
+ * `counts`, identical on all ranks.  Per-row arrays hold tvg_huge_pair_rows(nq, nt, world) rows. */
+typedef struct tvg_huge_pair_io {
+    const uint8_t* curr_des;   /* u8[nq][32]  query side (frame.curr_des) */
+    const uint8_t* last_des;   /* u8[nt][32]  train side (frame.last_des) */
+    const double* curr_kps;    /* f64[nq][2] pixels */
+    const double* last_kps;    /* f64[nt][2] pixels */
+    int nq, nt, H;
+    const uint32_t* words;     /* u32[H][8] the whole table, same on every rank (or samples) */
+    const int32_t* samples;    /* int32[H][8] */
+    double kinv[9];
+    double ratio, thr;
+    /* outputs */
+    int32_t* idx;        /* [rows][2] */
+    int32_t* dist;       /* [rows][2] */
+    int32_t* qidx;       /* [rows] */
+    int32_t* tidx;       /* [rows] */
+    int32_t* m_count;    /* [1] */
+    double* E;           /* [9] refit */
+    double* E_best;      /* [9] */
+    int32_t* best;       /* [1] GLOBAL hypothesis index */
+    double* best_sse;    /* [1] */
+    int32_t* counts;     /* [H]: this rank writes its own block only */
+    int32_t* n_cand;     /* [1] finalists this rank re-scored in fp64 */
+    uint8_t* mask;       /* [rows] */
+    int32_t* n_inl;      /* [1] */
+    int32_t* inl_idx;    /* [rows] */
+    double* Rt;          /* [16] */
+    double* poses;       /* [2][16]: identity, Rt @ identity */
+    double* points4d;    /* [rows][4] */
+    uint8_t* good;       /* [rows] */
+    int32_t* status;     /* [1] */
+} tvg_huge_pair_io;
+TVG_API int tvg_huge_pair(tvg_ctx* ctx, const tvg_huge_pair_io* io, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

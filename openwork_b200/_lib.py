@@ -46,6 +46,20 @@ class PairsIO(C.Structure):
     ]
 
 
+class HugePairIO(C.Structure):
+    """tvg_huge_pair_io"""
+    _fields_ = [
+        ("curr_des", c_vp), ("last_des", c_vp), ("curr_kps", c_vp), ("last_kps", c_vp),
+        ("nq", C.c_int), ("nt", C.c_int), ("H", C.c_int), ("words", c_vp), ("samples", c_vp),
+        ("kinv", C.c_double * 9), ("ratio", C.c_double), ("thr", C.c_double),
+        ("idx", c_vp), ("dist", c_vp), ("qidx", c_vp), ("tidx", c_vp), ("m_count", c_vp), ("E", c_vp), ("E_best", c_vp),
+        ("best", c_vp), ("best_sse", c_vp), ("counts", c_vp), ("n_cand", c_vp), ("mask", c_vp), ("n_inl", c_vp),
+        ("inl_idx", c_vp), ("Rt", c_vp), ("poses", c_vp), ("points4d", c_vp), ("good", c_vp), ("status", c_vp),
+    ]
+
+
+COMM_ID_BYTES = 128
+
 # name -> (restype, argtypes); also the list tests check against include/tvg_b200.h
 SIGNATURES = {
     "tvg_ctx_create": (C.c_int, [C.POINTER(c_vp), C.c_int]),
@@ -85,6 +99,13 @@ SIGNATURES = {
     "tvg_pairs_host_submit": (C.c_int, [c_vp, C.POINTER(PairsIO), C.c_int, C.POINTER(C.c_longlong),
                                         C.POINTER(C.c_longlong), c_vp]),
     "tvg_pairs_host_wait": (C.c_int, [c_vp]),
+    "tvg_comm_unique_id": (C.c_int, [c_vp]),
+    "tvg_comm_init": (C.c_int, [c_vp, c_vp, C.c_int, C.c_int]),
+    "tvg_comm_destroy": (C.c_int, [c_vp]),
+    "tvg_comm_info": (C.c_int, [c_vp, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
+    "tvg_shard_range": (None, [C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
+    "tvg_huge_pair_rows": (C.c_int, [C.c_int, C.c_int, C.c_int]),
+    "tvg_huge_pair": (C.c_int, [c_vp, C.POINTER(HugePairIO), c_vp]),
 }
 
 _lib = None
@@ -121,6 +142,13 @@ def check(rc, what):
     if rc != 0:
         msg = load().tvg_last_error()
         raise TvgError("%s failed (code %d): %s" % (what, rc, msg.decode() if msg else "?"))
+
+
+def comm_unique_id():
+    """128 bytes identifying a new communicator (rank 0 creates them and hands them to every rank)."""
+    buf = (C.c_ubyte * COMM_ID_BYTES)()
+    check(load().tvg_comm_unique_id(buf), "tvg_comm_unique_id")
+    return bytes(buf)
 
 
 class Context:
@@ -161,6 +189,19 @@ class Context:
 
     def set_matcher_l2_budget(self, nbytes=0):
         check(self.lib.tvg_set_matcher_l2_budget(self.handle, int(nbytes)), "tvg_set_matcher_l2_budget")
+
+    def comm_init(self, id_bytes, rank, world):
+        """Bind an NCCL communicator to this context (collective over all ranks; id from :func:`comm_unique_id`)."""
+        buf = (C.c_ubyte * COMM_ID_BYTES).from_buffer_copy(bytes(id_bytes))
+        check(self.lib.tvg_comm_init(self.handle, buf, int(rank), int(world)), "tvg_comm_init")
+
+    def comm_destroy(self):
+        check(self.lib.tvg_comm_destroy(self.handle), "tvg_comm_destroy")
+
+    def comm_info(self):
+        r, w = C.c_int(0), C.c_int(1)
+        check(self.lib.tvg_comm_info(self.handle, C.byref(r), C.byref(w)), "tvg_comm_info")
+        return r.value, w.value
 
     def set_score_config(self, hyp_per_thread=0, ctas_per_sm=0):
         """Scoring kernel tuning: hypotheses per thread (0 = default, 2, 4), resident CTAs per SM (0 = automatic)."""

@@ -15,7 +15,11 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT_DIR = os.path.join(HERE, "_lib")
 LIB = os.path.join(OUT_DIR, "libtvg_b200.so")
-SOURCES = ["hamming_knn2.cu", "hamming_tc.cu", "compact.cu", "ransac.cu", "pose_tri.cu", "bundle.cu", "frontend.cu", "c_api.cu"]
+SOURCES = ["hamming_knn2.cu", "hamming_tc.cu", "compact.cu", "ransac.cu", "ransac_score.cu", "pose_tri.cu", "bundle.cu",
+           "frontend.cu", "c_api.cu", "c_api_dist.cu"]
+# per-source extra flags: the scoring kernel's instruction order is chosen by hand for the register file, and
+# ptxas keeps the source order only at -O1 (see csrc/ransac_score.cu)
+EXTRA_FLAGS = {"ransac_score.cu": ["-Xptxas", "-O1"]}
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden"]
 
@@ -36,6 +40,7 @@ def _digest():
             h.update(os.path.basename(p).encode())
             h.update(open(p, "rb").read())
     h.update(" ".join(NVCC_FLAGS).encode())
+    h.update(repr(sorted(EXTRA_FLAGS.items())).encode())
     return h.hexdigest()
 
 
@@ -51,7 +56,7 @@ def build(force=False, verbose=False):
     procs = []
     for src in SOURCES:
         obj = os.path.join(OUT_DIR, src.replace(".cu", ".o"))
-        cmd = [nvcc, *NVCC_FLAGS, "-c", os.path.join(CSRC, src), "-o", obj]
+        cmd = [nvcc, *NVCC_FLAGS, *EXTRA_FLAGS.get(src, []), "-c", os.path.join(CSRC, src), "-o", obj]
         if verbose:
             print(" ".join(cmd), file=sys.stderr)
         procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
@@ -60,7 +65,7 @@ def build(force=False, verbose=False):
         out, _ = p.communicate()
         if p.returncode != 0:
             raise RuntimeError("nvcc failed on %s:\n%s" % (src, out))
-    cmd = [nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", LIB, *objs]
+    cmd = [nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", LIB, *objs, "-ldl"]
     r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     if r.returncode != 0:
         raise RuntimeError("link failed:\n" + r.stdout)

@@ -7,14 +7,13 @@
 #include <string>
 #include <vector>
 
-#include "../../include/tvg_b200.h"
-#include "tvg_common.cuh"
-#include "tvg_kernels.h"
+#include "tvg_ctx.h"
 
 namespace {
-
 thread_local std::string g_err;
+}  // namespace
 
+namespace tvgapi {
 int fail(int code, const std::string& msg) {
     g_err = msg;
     return code;
@@ -23,146 +22,9 @@ int cuda_fail(cudaError_t e, const char* where) {
     g_err = std::string(where) + ": " + cudaGetErrorString(e);
     return (int)e > 0 ? (int)e : 1;
 }
-#define TVG_CUDA(x)                                   \
-    do {                                              \
-        cudaError_t e__ = (x);                        \
-        if (e__ != cudaSuccess) return cuda_fail(e__, #x); \
-    } while (0)
-
-enum Slot {
-    S_PARTIAL, S_COUNTERS, S_IDX, S_DIST, S_KEEP, S_QIDX, S_TIDX, S_MCOUNT, S_SRC, S_DST, S_CORR32,
-    S_E64, S_E32, S_VALID, S_PARTCNT, S_PARTSSE, S_COUNTS, S_BAND, S_SSE32, S_CAND, S_NCAND, S_CANDSSE,
-    S_CANDCNT, S_BEST, S_BESTSSE, S_EBEST, S_MASK, S_NINL, S_INLIDX, S_PIXLAST, S_PIXCURR, S_E, S_RT,
-    S_STATUS, S_POSES, S_POSESINV, S_POINTS, S_GOOD, S_PAIRQ, S_PAIRT, S_SEQOFF, S_VOTES, S_RTS, S_CHOICE, S_REFITWS, S_FE_IMG, S_FE_GRAY, S_FE_COV, S_FE_EIG, S_FE_MAX, S_FE_KEYS, S_FE_NCAND,
-    S_FE_CORNERS, S_FE_NCORNERS, S_FE_BLURTMP, S_FE_BLUR,
-    // host-entry staging
-    S_H_DES, S_H_KPS, S_H_FCOUNT, S_H_PAIRQ, S_H_PAIRT, S_H_SEQOFF, S_H_INIT, S_H_WORDS, S_H_SAMPLES,
-    S_KNN_TC, S_BA_TRIAL, S_REFITBIG, S_COMPACTBIG, S_SCOREQ,
-    S_NUM
-};
-
-}  // namespace
-
-// stage marks of the pair pipeline: before knn, compact, fit, score, reduce, rescore, refit+solve,
-// pose stage (cheirality + pose chain), triangulate, and after triangulate
-#define TVG_PROF_MARKS 10
-// tvg_knn2_hamming256 switches to the tensor-core matcher from this many descriptor comparisons per call
-#define TVG_TC_MIN_CMP (16ll << 20)
-
-struct tvg_ctx {
-    int device = 0;
-    int sm_count = 148;
-    int knn_r = 4, knn_variant = 11, knn_ctas_per_sm = 6;
-    int score_hpt = 0, score_ctas = 0;   // scoring kernel tuning (0 = automatic), tvg_set_score_config
-    size_t knn_tc_l2_budget = 0;   // 0 = one unpack + one match launch per call; > 0 = L2-resident sub-batches
-    bool knn_auto = true;      // until tvg_set_matcher_config is called: r = 2 when the train rows get split
-    long long launches = 0;
-    int host_chunk_pairs = 256;
-    cudaStream_t s_in = nullptr, s_out = nullptr;
-    cudaEvent_t done_event = nullptr;
-    // optional stage timing of tvg_pairs_device (tvg_set_profile): events at the stage boundaries
-    bool profile = false;
-    cudaEvent_t prof[TVG_PROF_MARKS] = {};
-    int mark(int i, cudaStream_t st) {
-        if (!profile) return 0;
-        if (!prof[i]) {
-            cudaError_t e = cudaEventCreate(&prof[i]);
-            if (e != cudaSuccess) return cuda_fail(e, "cudaEventCreate");
-        }
-        cudaError_t e = cudaEventRecord(prof[i], st);
-        return e == cudaSuccess ? 0 : cuda_fail(e, "cudaEventRecord");
-    }
-    std::vector<cudaEvent_t> events;
-    unsigned char* pin = nullptr;   // pinned host staging for the small uploads of the host entry
-    size_t pin_bytes = 0, pin_used = 0;
-
-    // copy `bytes` of pageable caller memory into pinned staging; returns the pinned address (or nullptr)
-    void* stage(const void* src, size_t bytes) {
-        const size_t need = (pin_used + bytes + 255) & ~size_t(255);
-        if (need > pin_bytes) return nullptr;
-        void* dst = pin + pin_used;
-        memcpy(dst, src, bytes);
-        pin_used = need;
-        return dst;
-    }
-    int reserve_pinned(size_t bytes) {
-        pin_used = 0;
-        if (bytes <= pin_bytes) return 0;
-        cudaError_t e = cudaDeviceSynchronize();
-        if (e != cudaSuccess) return cuda_fail(e, "cudaDeviceSynchronize");
-        if (pin) cudaFreeHost(pin);
-        pin = nullptr; pin_bytes = 0;
-        e = cudaMallocHost((void**)&pin, bytes + bytes / 2 + 4096);
-        if (e != cudaSuccess) return cuda_fail(e, "cudaMallocHost(staging)");
-        pin_bytes = bytes + bytes / 2 + 4096;
-        return 0;
-    }
-    void* slot[S_NUM] = {};
-    size_t slot_bytes[S_NUM] = {};
-    cudaStream_t cur_stream = nullptr;   // stream of the entry point being served (set by every stream-taking call)
-    bool in_flight = false;              // tvg_pairs_host_submit without its tvg_pairs_host_wait yet
-
-    // grow-only scratch; zero_on_grow for buffers the kernels expect zeroed (tile counters): the memset is ordered
-    // on the caller's stream, like the kernels that read the buffer.  Growing synchronises the device and
-    // (re)allocates, which is illegal while `cur_stream` is being captured into a CUDA graph: warm the context up
-    // at the same sizes before capturing.
-    int get(Slot s, size_t bytes, void** out, bool zero_on_grow = false) {
-        if (bytes == 0) bytes = 16;
-        if (slot_bytes[s] < bytes) {
-            cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
-            if (cudaStreamIsCapturing(cur_stream, &cap) == cudaSuccess && cap != cudaStreamCaptureStatusNone)
-                return fail(-6, "scratch must grow while the stream is being captured: run the call once eagerly at "
-                                "the same sizes before capturing it into a CUDA graph");
-            if (slot[s]) {
-                cudaError_t e = cudaDeviceSynchronize();
-                if (e != cudaSuccess) return cuda_fail(e, "cudaDeviceSynchronize");
-                cudaFree(slot[s]);
-                slot[s] = nullptr;
-                slot_bytes[s] = 0;
-            }
-            const size_t want = bytes + bytes / 4 + 256;
-            cudaError_t e = cudaMalloc(&slot[s], want);
-            if (e != cudaSuccess) return cuda_fail(e, "cudaMalloc(scratch)");
-            if (zero_on_grow) {
-                e = cudaMemsetAsync(slot[s], 0, want, cur_stream);
-                if (e != cudaSuccess) return cuda_fail(e, "cudaMemsetAsync(scratch)");
-            }
-            slot_bytes[s] = want;
-        }
-        *out = slot[s];
-        return 0;
-    }
-};
-
-#define TVG_GET(ctx, s, bytes, ptr, type)                              \
-    do {                                                               \
-        void* v__ = nullptr;                                           \
-        int rc__ = (ctx)->get(s, (bytes), &v__);                       \
-        if (rc__) return rc__;                                         \
-        ptr = reinterpret_cast<type>(v__);                             \
-    } while (0)
-// output pointer if the caller gave one, scratch otherwise
-#define TVG_OUT(ctx, user, s, bytes, ptr, type)                        \
-    do {                                                               \
-        if (user) ptr = reinterpret_cast<type>(user);                  \
-        else TVG_GET(ctx, s, bytes, ptr, type);                        \
-    } while (0)
+}  // namespace tvgapi
 
 namespace {
-
-bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
-
-struct DeviceGuard {
-    int prev = -1;
-    explicit DeviceGuard(int dev) {
-        cudaGetDevice(&prev);
-        if (prev != dev) cudaSetDevice(dev);
-        else prev = -1;
-    }
-    ~DeviceGuard() {
-        if (prev >= 0) cudaSetDevice(prev);
-    }
-};
 
 __global__ void make_pairs_kernel(const int32_t* seq_off, int nseq, int batch, int32_t* pair_q, int32_t* pair_t) {
     const int b = blockIdx.x * blockDim.x + threadIdx.x;
@@ -201,6 +63,7 @@ void tvg_ctx_destroy(tvg_ctx* ctx) {
     if (!ctx) return;
     DeviceGuard g(ctx->device);
     cudaDeviceSynchronize();
+    tvg_comm_release(ctx);
     for (int i = 0; i < S_NUM; ++i)
         if (ctx->slot[i]) cudaFree(ctx->slot[i]);
     for (cudaEvent_t e : ctx->events) cudaEventDestroy(e);
@@ -343,20 +206,24 @@ int tvg_ratio_compact(tvg_ctx* ctx, const uint8_t* keep, const int32_t* idx, int
     return 0;
 }
 
-int tvg_ransac_essential(tvg_ctx* ctx, const tvg_ransac_io* io, void* stream) {
+}  // extern "C"
+
+// Fills the launch parameters and scratch of one RANSAC call.  force_big selects the grid-wide re-score / select /
+// refit kernels whatever n_max is (tvg_huge_pair: results must not depend on the number of ranks); rec != NULL makes
+// the selection publish this rank's record for the exchange instead of p.best / p.E_best; h_off = global index of
+// hypothesis 0 of this call.
+int tvg_ransac_prepare(tvg_ctx* ctx, const tvg_ransac_io* io, bool force_big, int h_off, tvg::BestRec* rec, RansacRun* run) {
     if (!ctx || !io) return fail(-1, "ctx / io is NULL");
     if (io->batch < 0 || io->n_max <= 0 || io->H <= 0 || io->m < 0 || io->m > io->n_max)
         return fail(-2, "tvg_ransac_essential: bad sizes");
-    if (io->batch == 0) return 0;
     if (!io->src || !io->dst || !io->corr32) return fail(-3, "tvg_ransac_essential: NULL correspondences");
     if (!io->samples && !io->words) return fail(-3, "tvg_ransac_essential: need samples or words");
     if (!(io->thr > 0.0)) return fail(-2, "tvg_ransac_essential: residual threshold must be > 0");
     if (!aligned16(io->src) || !aligned16(io->dst) || !aligned16(io->corr32))
         return fail(-4, "tvg_ransac_essential: correspondences must be 16-byte aligned");
-    DeviceGuard g(ctx->device);
-    ctx->cur_stream = (cudaStream_t)stream;
     const size_t B = (size_t)io->batch, N = (size_t)io->n_max, H = (size_t)io->H;
-    tvg::RansacParams p{};
+    tvg::RansacParams& p = run->p;
+    p = tvg::RansacParams{};
     p.src = io->src; p.dst = io->dst; p.corr32 = reinterpret_cast<const float4*>(io->corr32);
     p.m_count = io->m_count; p.n_max = io->n_max; p.m = io->m; p.H = io->H;
     p.samples = io->samples; p.words = io->samples ? nullptr : io->words;
@@ -365,9 +232,9 @@ int tvg_ransac_essential(tvg_ctx* ctx, const tvg_ransac_io* io, void* stream) {
     p.band_rel = 2e-3f;     // |num^2 - thr^2 den| <= band_rel * thr^2 den  <=>  |r - thr| <~ 1e-3 thr = 5e-6
     p.want_sse = io->sse32 ? 1 : 0;
     p.band_floor = 9e-11f;  // delta^2 / (band_rel / 2), delta = 3e-7: fp32 cancellation error of num
-    tvg::ScorePlan plan{};
-    tvg::ransac_score_plan(io->batch, io->n_max, io->H, ctx->sm_count, ctx->score_hpt, ctx->score_ctas, &plan);
-    p.chunks = plan.slots; p.chunk = plan.rows_per_slot;
+    tvg::ransac_score_constants(&p);
+    tvg::ransac_score_plan(io->batch, io->n_max, io->H, ctx->sm_count, ctx->score_hpt, ctx->score_ctas, &run->plan);
+    p.chunks = run->plan.slots; p.chunk = run->plan.rows_per_slot;
     {
         void* v = nullptr;
         int rcq = ctx->get(S_SCOREQ, sizeof(unsigned int), &v, true);
@@ -401,24 +268,56 @@ int tvg_ransac_essential(tvg_ctx* ctx, const tvg_ransac_io* io, void* stream) {
     TVG_OUT(ctx, io->Rt, S_RT, B * 16 * sizeof(double), p.Rt, double*);
     TVG_OUT(ctx, io->status, S_STATUS, B * sizeof(int32_t), p.status, int32_t*);
     TVG_GET(ctx, S_REFITWS, B * tvg::ransac_refit_ws_doubles() * sizeof(double), p.refit_ws, double*);
-    if (tvg::ransac_refit_big_blocks(io->n_max) > 0)
-        TVG_GET(ctx, S_REFITBIG, B * tvg::ransac_refit_big_blocks(io->n_max) * tvg::ransac_refit_big_stride() * sizeof(double),
-                p.refit_big, double*);
-    cudaStream_t st = (cudaStream_t)stream;
+    const int nblk = tvg::ransac_refit_big_blocks(io->n_max, force_big);
+    run->big = nblk > 0;
+    if (run->big) {
+        TVG_GET(ctx, S_REFITBIG, B * nblk * tvg::ransac_refit_big_stride() * sizeof(double), p.refit_big, double*);
+        TVG_GET(ctx, S_CANDPART, B * H * nblk * sizeof(double2), p.cand_part, double2*);
+    }
+    // few pairs with many hypotheses: grid-wide reduce instead of one CTA per pair
+    if (force_big || (io->batch < 32 && io->H >= 4096)) TVG_GET(ctx, S_LB, B * sizeof(int32_t), p.lb, int32_t*);
+    p.rec = rec;
+    p.h_off = h_off;
+    return 0;
+}
+
+int tvg_ransac_phase_a(tvg_ctx* ctx, RansacRun* run, int batch, cudaStream_t st) {
+    const tvg::RansacParams& p = run->p;
     int mrc = ctx->mark(2, st);
     if (mrc) return mrc;
-    TVG_CUDA(tvg::launch_ransac_fit(p, io->batch, st));
+    TVG_CUDA(tvg::launch_ransac_fit(p, batch, st));
     if ((mrc = ctx->mark(3, st))) return mrc;
-    TVG_CUDA(tvg::launch_ransac_score(p, io->batch, plan, st));
+    TVG_CUDA(tvg::launch_ransac_score(p, batch, run->plan, st));
     if ((mrc = ctx->mark(4, st))) return mrc;
-    TVG_CUDA(tvg::launch_ransac_reduce(p, io->batch, st));
+    TVG_CUDA(tvg::launch_ransac_reduce(p, batch, st));
     if ((mrc = ctx->mark(5, st))) return mrc;
-    TVG_CUDA(tvg::launch_ransac_rescore(p, io->batch, st));
-    if ((mrc = ctx->mark(6, st))) return mrc;
-    TVG_CUDA(tvg::launch_ransac_refit(p, io->batch, st));
-    if ((mrc = ctx->mark(7, st))) return mrc;
-    ctx->launches += 6 + (p.refit_big ? 4 : 0);
-    return 0;
+    TVG_CUDA(tvg::launch_ransac_rescore(p, batch, st));
+    ctx->launches += 3 + tvg::ransac_reduce_launches(p);
+    if (run->big) {
+        TVG_CUDA(tvg::launch_ransac_select_big(p, batch, st));
+        ctx->launches += 1;
+    }
+    return ctx->mark(6, st);
+}
+
+int tvg_ransac_phase_b(tvg_ctx* ctx, RansacRun* run, int batch, cudaStream_t st) {
+    TVG_CUDA(tvg::launch_ransac_refit(run->p, batch, st));
+    ctx->launches += run->big ? 5 : 2;
+    return ctx->mark(7, st);
+}
+
+extern "C" {
+
+int tvg_ransac_essential(tvg_ctx* ctx, const tvg_ransac_io* io, void* stream) {
+    if (!ctx || !io) return fail(-1, "ctx / io is NULL");
+    if (io->batch == 0) return 0;
+    DeviceGuard g(ctx->device);
+    ctx->cur_stream = (cudaStream_t)stream;
+    RansacRun run;
+    int rc = tvg_ransac_prepare(ctx, io, false, 0, nullptr, &run);
+    if (rc) return rc;
+    if ((rc = tvg_ransac_phase_a(ctx, &run, io->batch, (cudaStream_t)stream))) return rc;
+    return tvg_ransac_phase_b(ctx, &run, io->batch, (cudaStream_t)stream);
 }
 
 int tvg_extract_rt(tvg_ctx* ctx, const double* E, int batch, double* Rt, void* stream) {
@@ -443,8 +342,8 @@ int tvg_pose_chain(tvg_ctx* ctx, const double* Rt, const int32_t* seq_off, int n
     DeviceGuard g(ctx->device);
     ctx->cur_stream = (cudaStream_t)stream;
     tvg::PoseChainParams p{Rt, seq_off, init_pose, poses, pair_pinv, nullptr, 0};
-    TVG_CUDA(tvg::launch_pose_chain(p, nseq, (cudaStream_t)stream));
-    ctx->launches += 1;
+    TVG_CUDA(tvg::launch_pose_chain(p, nseq, 0, (cudaStream_t)stream));
+    ctx->launches += pair_pinv ? 2 : 1;
     return 0;
 }
 
@@ -703,8 +602,8 @@ static int pairs_device_impl(tvg_ctx* ctx, const tvg_pairs_io* io, const double*
     TVG_OUT(ctx, io->good, S_GOOD, B * N, good, uint8_t*);
     {
         tvg::PoseChainParams pc{Rt, seq_off, io->init_pose, poses, pinv, first_init, io->batch};
-        TVG_CUDA(tvg::launch_pose_chain(pc, nseq, st));
-        ctx->launches += 1;
+        TVG_CUDA(tvg::launch_pose_chain(pc, nseq, io->batch, st));
+        ctx->launches += 2;
     }
     if ((rc = ctx->mark(8, st))) return rc;
     // triangulate(frame.last_kps, frame.curr_kps, frame.last_pose, frame.curr_pose)  (slam.py:263)

@@ -26,37 +26,85 @@ cudaError_t launch_extract_rt(const ExtractRtParams& p, int batch, cudaStream_t 
     return cudaGetLastError();
 }
 
-// One thread per sequence: pose[f+1] = Rt[f] @ pose[f]  (slam.py:261), plus the inverses triangulate needs.
-__global__ void pose_chain_kernel(const PoseChainParams p, int nseq) {
-    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+// pose[f+1] = Rt[f] @ pose[f]  (slam.py:261): a sequential chain per sequence.  One warp per sequence: the lanes load
+// 32 consecutive Rt matrices at once (the loads do not depend on the chain), then the chain steps run on values
+// broadcast by shuffles -- every lane computes the same product, lane j keeps step j -- so a 500-pair sequence costs
+// 500 short register-resident steps instead of 500 dependent global round trips.  Same fma order as a plain loop.
+constexpr int POSE_WARPS = 4;
+
+__global__ void __launch_bounds__(POSE_WARPS * 32) pose_chain_kernel(const PoseChainParams p, int nseq) {
+    const int s = blockIdx.x * POSE_WARPS + (threadIdx.x >> 5), lane = threadIdx.x & 31;
     if (s >= nseq) return;
     const int b0 = p.seq_off ? p.seq_off[s] : 0, b1 = p.seq_off ? p.seq_off[s + 1] : p.batch;
-    double cur[16], inv[16];
+    double cur[16];
     const double* init = (s == 0 && p.first_init) ? p.first_init : (p.init_pose ? p.init_pose + (size_t)s * 16 : nullptr);
+#pragma unroll
     for (int i = 0; i < 16; ++i) cur[i] = init ? init[i] : ((i % 5 == 0) ? 1.0 : 0.0);
-    inverse4(cur, inv);
-    for (int i = 0; i < 16; ++i) p.poses[(size_t)(b0 + s) * 16 + i] = cur[i];
-    for (int b = b0; b < b1; ++b) {
-        double nxt[16];
-        const double* Rt = p.Rt + (size_t)b * 16;
-        for (int r = 0; r < 4; ++r)
-            for (int c = 0; c < 4; ++c) {
-                double a = 0.0;
-                for (int k = 0; k < 4; ++k) a = fma(Rt[r * 4 + k], cur[k * 4 + c], a);
-                nxt[r * 4 + c] = a;
+    if (lane < 16) p.poses[(size_t)(b0 + s) * 16 + lane] = init ? init[lane] : ((lane % 5 == 0) ? 1.0 : 0.0);
+    for (int base = b0; base < b1; base += 32) {
+        const int mine_b = base + lane;
+        double R[16], mine[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+            R[i] = (mine_b < b1) ? p.Rt[(size_t)mine_b * 16 + i] : 0.0;
+            mine[i] = 0.0;
+        }
+        const int steps = min(32, b1 - base);
+        for (int j = 0; j < steps; ++j) {
+            double Rj[16], nxt[16];
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+                const int lo = __shfl_sync(0xffffffffu, __double2loint(R[i]), j);
+                const int hi = __shfl_sync(0xffffffffu, __double2hiint(R[i]), j);
+                Rj[i] = __hiloint2double(hi, lo);
             }
-        if (p.pair_pinv)
-            for (int i = 0; i < 16; ++i) p.pair_pinv[(size_t)b * 32 + i] = inv[i];
-        for (int i = 0; i < 16; ++i) cur[i] = nxt[i];
-        inverse4(cur, inv);
-        for (int i = 0; i < 16; ++i) p.poses[(size_t)(b + s + 1) * 16 + i] = cur[i];
-        if (p.pair_pinv)
-            for (int i = 0; i < 16; ++i) p.pair_pinv[(size_t)b * 32 + 16 + i] = inv[i];
+#pragma unroll
+            for (int r = 0; r < 4; ++r)
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    double a = 0.0;
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) a = fma(Rj[r * 4 + k], cur[k * 4 + c], a);
+                    nxt[r * 4 + c] = a;
+                }
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+                cur[i] = nxt[i];
+                if (lane == j) mine[i] = nxt[i];
+            }
+        }
+        if (mine_b < b1) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) p.poses[(size_t)(mine_b + s + 1) * 16 + i] = mine[i];
+        }
     }
 }
 
-cudaError_t launch_pose_chain(const PoseChainParams& p, int nseq, cudaStream_t stream) {
-    pose_chain_kernel<<<(nseq + 31) / 32, 32, 0, stream>>>(p, nseq);
+// np.linalg.inv of the two poses of every pair (slam.py:204-205), one thread per pair, after the chain.
+__global__ void pose_pair_inverse_kernel(const PoseChainParams p, int nseq) {
+    const int total = p.seq_off ? p.seq_off[nseq] : p.batch;
+    for (int b = blockIdx.x * blockDim.x + threadIdx.x; b < total; b += gridDim.x * blockDim.x) {
+        int s = 0;
+        if (p.seq_off) {   // last sequence whose first pair is <= b
+            int lo = 0, hi = nseq - 1;
+            while (lo < hi) {
+                const int mid = (lo + hi + 1) >> 1;
+                if (p.seq_off[mid] <= b) lo = mid; else hi = mid - 1;
+            }
+            s = lo;
+        }
+        inverse4(p.poses + (size_t)(b + s) * 16, p.pair_pinv + (size_t)b * 32);
+        inverse4(p.poses + (size_t)(b + s + 1) * 16, p.pair_pinv + (size_t)b * 32 + 16);
+    }
+}
+
+// batch_hint = total pairs when the host knows it (sizes the second grid), else 0
+cudaError_t launch_pose_chain(const PoseChainParams& p, int nseq, int batch_hint, cudaStream_t stream) {
+    pose_chain_kernel<<<(nseq + POSE_WARPS - 1) / POSE_WARPS, POSE_WARPS * 32, 0, stream>>>(p, nseq);
+    if (p.pair_pinv) {
+        const int blocks = batch_hint > 0 ? (batch_hint + 63) / 64 : 592;
+        pose_pair_inverse_kernel<<<blocks, 64, 0, stream>>>(p, nseq);
+    }
     return cudaGetLastError();
 }
 

@@ -86,6 +86,10 @@ __global__ void __launch_bounds__(FIT_THREADS) ransac_fit_kernel(const RansacPar
 #pragma unroll
         for (int k = 0; k < 8; ++k) p.samples_out[oh * 8 + k] = ok ? idx[k] : -1;
     }
+    if (h == 0) {   // per-pair state of the grid-wide reduce (few pairs, many hypotheses)
+        p.n_cand[b] = 0;
+        if (p.lb) p.lb[b] = -1;
+    }
 
     double E[9];
     if (ok) {
@@ -138,210 +142,7 @@ cudaError_t launch_ransac_fit(const RansacParams& p, int batch, cudaStream_t str
     return cudaGetLastError();
 }
 
-// ------------------------------------------------------------------------------------ score (fp32)
-constexpr int SCORE_THREADS = 128;
-constexpr int SCORE_CHUNK = 256;          // correspondences per shared-memory stage (4 KB)
-constexpr int SCORE_MAX_ROWS = 32768;     // rows per work item: the packed 16-bit lane counters must not wrap
-
-// One Sampson evaluation in fp32: 19 FFMA (+ 1 MUFU.RCP + 1 FFMA when sum r^2 is wanted) + 2 integer-pipe
-// instructions for BOTH counters: the sign bits of t (inlier) and bt (inside the fp32 uncertainty band) are
-// replicated into the two 16-bit lanes of one word by a single PRMT (selector 0xFFBB: bytes 0,1 = sign of t, bytes
-// 2,3 = sign of bt), and one IADD subtracts that word from the packed accumulator:
-//     acc - 0x0000FFFF  ==  acc + 1 - 0x10000   -> low lane += 1, high lane -= 1
-//     acc - 0xFFFF0000  ==  acc + 0x10000       -> high lane += 1
-// so after <= 32768 rows  low = count, high = (band - count) mod 2^16.
-// (Measured alternatives: SHF + IADD per counter = 4 integer instructions per evaluation, round 1; packed
-// fma.rn.f32x2 over two hypotheses: FFMA2 issues at half the FFMA rate on B200, tools/microbench/fp32_pipes.cu.)
-template <bool SSE>
-__device__ __forceinline__ void score_eval(const float (&e)[9], const float4 c, float thr2, float band,
-                                           float c1, float k1, unsigned& acc, float& sse) {
-    // c = (x, y, u, v): x = src (last), u = dst (curr)
-    const float f0 = fmaf(e[0], c.x, fmaf(e[1], c.y, e[2]));
-    const float f1 = fmaf(e[3], c.x, fmaf(e[4], c.y, e[5]));
-    const float f2 = fmaf(e[6], c.x, fmaf(e[7], c.y, e[8]));
-    const float g0 = fmaf(e[0], c.z, fmaf(e[3], c.w, e[6]));
-    const float g1 = fmaf(e[1], c.z, fmaf(e[4], c.w, e[7]));
-    const float num = fmaf(c.z, f0, fmaf(c.w, f1, f2));
-    // too close for fp32 to call:  |t| < band*den + floor.  The relative part covers rounding of num^2 and
-    // thr^2*den; the absolute floor covers cancellation in num for points near the epipole (den -> 0):
-    // 2*thr*sqrt(den)*delta <= (band_rel/2)*thr^2*den + delta^2/(band_rel/2)  with  delta ~ 3e-7 (|E|_F = 1,
-    // |x| <~ 1); the other half of band_rel is the rounding allowance.  The floor costs no instruction: with
-    // c1 = floor/band added to den and thr^2*c1 added to num^2 (two FMULs become FFMAs), t is unchanged and
-    // band*den' = band*den + floor.
-    const float den = fmaf(f0, f0, fmaf(f1, f1, fmaf(g0, g0, fmaf(g1, g1, c1))));
-    const float n2 = fmaf(num, num, k1);
-    const float t = fmaf(-thr2, den, n2);              // r < thr  <=>  num^2 - thr^2 den < 0
-    const float bt = fmaf(-band, den, fabsf(t));
-    unsigned w;
-    asm("prmt.b32 %0, %1, %2, 0xFFBB;" : "=r"(w) : "r"(__float_as_uint(t)), "r"(__float_as_uint(bt)));
-    acc -= w;
-    if (SSE) {
-        float rinv;
-        asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(rinv) : "f"(den - c1));
-        sse = fmaf(n2 - k1, rinv, sse);
-    }
-}
-
-// Persistent CTAs pull work items from a device-side queue (atomic counter): item = (pair, row slot, block of
-// HPT * 128 hypotheses).  A thread owns HPT hypotheses (E in registers); the item's correspondences stream through a
-// two-stage shared-memory ring filled by TMA bulk copies; one broadcast LDS.128 feeds HPT evaluations.  Items whose
-// row slot lies beyond the pair's match count (known only on the device) cost one queue pop.
-template <int HPT, bool SSE>
-__global__ void __launch_bounds__(SCORE_THREADS) ransac_score_kernel(const RansacParams p, int items, int hblocks) {
-    extern __shared__ __align__(128) unsigned char score_smem[];
-    float4(*corr)[SCORE_CHUNK] = reinterpret_cast<float4(*)[SCORE_CHUNK]>(score_smem);
-    __shared__ alignas(8) uint64_t bar[2];
-    __shared__ int s_item;
-    if (threadIdx.x == 0) {
-        mbar_init(&bar[0], 1);
-        mbar_init(&bar[1], 1);
-        fence_mbar_init();
-    }
-    const float thr2 = (float)(p.thr * p.thr);
-    const float band = p.band_rel * thr2;
-    const float c1 = p.band_floor / band;   // den offset that realises the absolute floor
-    const float k1 = thr2 * c1;             // matching num^2 offset: t stays num^2 - thr^2 den
-    uint32_t g = 0;                         // chunks consumed so far by this CTA: stage = g & 1, parity = (g >> 1) & 1
-    for (;;) {
-        __syncthreads();                    // barrier init visible / previous item's s_item and stages released
-        if (threadIdx.x == 0) s_item = (int)atomicAdd(p.score_queue, 1u);
-        __syncthreads();
-        const int item = s_item;
-        if (item >= items) break;
-        const int hb = item % hblocks;
-        const int slot = (item / hblocks) % p.chunks;
-        const int b = item / (hblocks * p.chunks);
-        const int M = p.m_count ? min(p.m_count[b], p.n_max) : p.m;
-        const int r_begin = slot * p.chunk;
-        const int r_end = min(M, r_begin + p.chunk);
-        if (r_end <= r_begin && slot > 0) continue;     // slot 0 always writes (zero counts when M == 0)
-        const int n = (r_end > r_begin) ? (r_end - r_begin + SCORE_CHUNK - 1) / SCORE_CHUNK : 0;
-        const size_t oc = ((size_t)b * p.chunks + slot) * p.H;
-        const float4* __restrict__ src = p.corr32 + (size_t)b * p.n_max + r_begin;
-        auto issue = [&](int i) {
-            const int rows = min(SCORE_CHUNK, r_end - r_begin - i * SCORE_CHUNK);
-            const uint32_t st = (g + (uint32_t)i) & 1u;
-            mbar_arrive_expect_tx(&bar[st], (uint32_t)rows * 16u);
-            tma_load_1d(corr[st], src + (size_t)i * SCORE_CHUNK, (uint32_t)rows * 16u, &bar[st]);
-        };
-        if (threadIdx.x == 0) {
-            if (n > 0) issue(0);
-            if (n > 1) issue(1);
-        }
-        float e[HPT][9];
-        int h[HPT];
-        unsigned acc[HPT];
-        float sse[HPT];
-#pragma unroll
-        for (int k = 0; k < HPT; ++k) {
-            h[k] = (hb * HPT + k) * SCORE_THREADS + threadIdx.x;
-#pragma unroll
-            for (int i = 0; i < 9; ++i) e[k][i] = (h[k] < p.H) ? p.E32[((size_t)b * 9 + i) * p.H + h[k]] : 0.0f;
-            acc[k] = 0u; sse[k] = 0.0f;
-        }
-        for (int i = 0; i < n; ++i) {
-            const uint32_t gi = g + (uint32_t)i;
-            mbar_wait(&bar[gi & 1u], (gi >> 1) & 1u);
-            const int rows = min(SCORE_CHUNK, r_end - r_begin - i * SCORE_CHUNK);
-            const float4* __restrict__ cp = corr[gi & 1u];
-#pragma unroll(16 / HPT)
-            for (int j = 0; j < rows; ++j) {
-                const float4 c = cp[j];
-#pragma unroll
-                for (int k = 0; k < HPT; ++k) score_eval<SSE>(e[k], c, thr2, band, c1, k1, acc[k], sse[k]);
-            }
-            __syncthreads();   // everyone is done with this stage before TMA refills it
-            if (threadIdx.x == 0 && i + 2 < n) issue(i + 2);
-        }
-        g += (uint32_t)n;
-#pragma unroll
-        for (int k = 0; k < HPT; ++k)
-            if (h[k] < p.H) {
-                const unsigned cnt = acc[k] & 0xFFFFu;
-                const unsigned unc = ((acc[k] >> 16) + cnt) & 0xFFFFu;
-                p.part_cnt[oc + h[k]] = make_int2((int)cnt, (int)unc);
-                p.part_sse[oc + h[k]] = sse[k];
-            }
-    }
-}
-
-// Work decomposition of the scoring launch.  hpt hypotheses per thread; `slots` row ranges of `rows_per_slot`
-// correspondences each (partial sums merged by the reduce kernel); persistent grid of `ctas_per_sm` CTAs per SM
-// (dynamic shared memory is padded so that no more fit), chosen so that the item count fills whole rounds.
-static int score_max_ctas(int hpt) {
-    static int cached[5] = {0, 0, 0, 0, 0};
-    if (!cached[hpt]) {
-        int n = 0;
-        cudaError_t e = (hpt == 4)
-            ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, ransac_score_kernel<4, false>, SCORE_THREADS, 2 * SCORE_CHUNK * 16)
-            : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, ransac_score_kernel<2, false>, SCORE_THREADS, 2 * SCORE_CHUNK * 16);
-        if (e != cudaSuccess || n < 1) { cudaGetLastError(); n = hpt == 4 ? 5 : 8; }
-        cached[hpt] = n;
-    }
-    return cached[hpt];
-}
-
-void ransac_score_plan(int batch, int n_max, int H, int sm_count, int cfg_hpt, int cfg_ctas, ScorePlan* out) {
-    ScorePlan pl{};
-    pl.hpt = (cfg_hpt == 4) ? 4 : 2;
-    const int per_block = pl.hpt * SCORE_THREADS;
-    pl.hblocks = (H + per_block - 1) / per_block;
-    const int chunks = (n_max + SCORE_CHUNK - 1) / SCORE_CHUNK > 0 ? (n_max + SCORE_CHUNK - 1) / SCORE_CHUNK : 1;
-    int max_c = score_max_ctas(pl.hpt);
-    if (cfg_ctas > 0 && cfg_ctas < max_c) max_c = cfg_ctas;
-    // row slots: one when (pair, hypothesis block) items alone give >= 4 rounds of the persistent grid, else split
-    // the rows (a single huge pair); never more than SCORE_MAX_ROWS rows per slot
-    const long long base = (long long)batch * pl.hblocks;
-    long long want = (4LL * sm_count * max_c + base - 1) / base;
-    const long long need = ((long long)chunks * SCORE_CHUNK + SCORE_MAX_ROWS - 1) / SCORE_MAX_ROWS;
-    if (want < need) want = need;
-    if (want < 1) want = 1;
-    if (want > chunks) want = chunks;
-    const int cps = (chunks + (int)want - 1) / (int)want;       // chunks per slot
-    pl.slots = (chunks + cps - 1) / cps;
-    pl.rows_per_slot = cps * SCORE_CHUNK;
-    pl.items = (int)(base * pl.slots);
-    // CTAs per SM: the largest count (>= 60 % of the maximum) whose rounds are filled best
-    int best_c = max_c;
-    double best_eff = 0.0;
-    for (int c = max_c; c >= 1 && c * 10 >= max_c * 6; --c) {
-        const long long per_round = (long long)sm_count * c;
-        const long long rounds = (pl.items + per_round - 1) / per_round;
-        const double eff = (double)pl.items / (double)(rounds * per_round);
-        if (eff > best_eff + 0.01) { best_eff = eff; best_c = c; }
-    }
-    if (cfg_ctas > 0) best_c = cfg_ctas < score_max_ctas(pl.hpt) ? cfg_ctas : score_max_ctas(pl.hpt);
-    pl.ctas_per_sm = best_c;
-    const long long g = (long long)sm_count * best_c;
-    pl.grid = (int)(pl.items < g ? pl.items : g);
-    if (pl.grid < 1) pl.grid = 1;
-    // pad the dynamic shared memory so that exactly ctas_per_sm CTAs fit on an SM (228 KB, 1 KB reserved per CTA)
-    int smem = (int)((228 * 1024) / best_c) - 1024 - 256;
-    smem &= ~127;
-    if (smem < 2 * SCORE_CHUNK * 16) smem = 2 * SCORE_CHUNK * 16;
-    if (smem > 200 * 1024) smem = 200 * 1024;
-    pl.smem = smem;
-    *out = pl;
-}
-
-cudaError_t launch_ransac_score(const RansacParams& p, int batch, const ScorePlan& pl, cudaStream_t stream) {
-    // the fp32 sum of squared residuals is diagnostic (selection uses the exact fp64 re-score): computed
-    // only when the caller asked for it
-    (void)batch;
-#define TVG_SCORE_LAUNCH(HPT, SSE)                                                                                    \
-    do {                                                                                                              \
-        cudaError_t e__ = cudaFuncSetAttribute(ransac_score_kernel<HPT, SSE>, cudaFuncAttributeMaxDynamicSharedMemorySize, pl.smem); \
-        if (e__ != cudaSuccess) return e__;                                                                           \
-        ransac_score_kernel<HPT, SSE><<<pl.grid, SCORE_THREADS, pl.smem, stream>>>(p, pl.items, pl.hblocks);         \
-    } while (0)
-    if (pl.hpt == 4) {
-        if (p.want_sse) TVG_SCORE_LAUNCH(4, true); else TVG_SCORE_LAUNCH(4, false);
-    } else {
-        if (p.want_sse) TVG_SCORE_LAUNCH(2, true); else TVG_SCORE_LAUNCH(2, false);
-    }
-#undef TVG_SCORE_LAUNCH
-    return cudaGetLastError();
-}
+// (fp32 scoring: ransac_score.cu)
 
 // ------------------------------------------------------------------------------------ reduce + candidates
 constexpr int REDUCE_THREADS = 1024;
@@ -398,10 +199,68 @@ __global__ void __launch_bounds__(REDUCE_THREADS) ransac_reduce_kernel(const Ran
     }
 }
 
+// Grid-wide form for few pairs with many hypotheses (one huge pair: H = 65536): the per-hypothesis sums and the
+// best lower bound (atomicMax), then the candidate list (atomicAdd slots: the list order is arbitrary, the selection
+// rule downstream is a total order).  p.lb / p.n_cand are initialised by the fit kernel.
+constexpr int REDUCE_BIG_THREADS = 256;
+
+__global__ void __launch_bounds__(REDUCE_BIG_THREADS) ransac_reduce_big_sum_kernel(const RansacParams p) {
+    __shared__ int s_red[REDUCE_BIG_THREADS / 32];
+    const int b = blockIdx.y, tid = threadIdx.x;
+    const int h = blockIdx.x * REDUCE_BIG_THREADS + tid;
+    const int M = p.m_count ? min(p.m_count[b], p.n_max) : p.m;
+    const int nchunks = min(p.chunks, (M + p.chunk - 1) / p.chunk);
+    const size_t oh = (size_t)b * p.H;
+    int lb = -1;
+    if (h < p.H) {
+        int c = 0, u = 0;
+        float s = 0.0f;
+        for (int k = 0; k < nchunks; ++k) {
+            const size_t o = ((size_t)b * p.chunks + k) * p.H + h;
+            const int2 v = p.part_cnt[o];
+            c += v.x;
+            u += v.y;
+            s += p.part_sse[o];
+        }
+        const bool ok = p.valid[oh + h] != 0;
+        p.counts[oh + h] = ok ? c : -1;
+        p.band[oh + h] = ok ? u : 0;
+        p.sse32[oh + h] = ok ? s : __int_as_float(0x7f800000);
+        if (ok) lb = c - u;
+    }
+#pragma unroll
+    for (int m = 16; m > 0; m >>= 1) lb = max(lb, __shfl_xor_sync(0xffffffffu, lb, m));
+    if ((tid & 31) == 0) s_red[tid >> 5] = lb;
+    __syncthreads();
+    if (tid == 0) {
+#pragma unroll
+        for (int w = 1; w < REDUCE_BIG_THREADS / 32; ++w) lb = max(lb, s_red[w]);
+        if (lb >= 0) atomicMax(&p.lb[b], lb);
+    }
+}
+
+__global__ void __launch_bounds__(REDUCE_BIG_THREADS) ransac_reduce_big_list_kernel(const RansacParams p) {
+    const int b = blockIdx.y;
+    const int h = blockIdx.x * REDUCE_BIG_THREADS + threadIdx.x;
+    const size_t oh = (size_t)b * p.H;
+    if (h < p.H) {
+        const int c = p.counts[oh + h];
+        if (c >= 0 && c + p.band[oh + h] >= p.lb[b]) p.cand[oh + atomicAdd(&p.n_cand[b], 1)] = h;
+    }
+    if (blockIdx.x == 0 && b == 0 && threadIdx.x == 0) *p.score_queue = 0u;
+}
+
 cudaError_t launch_ransac_reduce(const RansacParams& p, int batch, cudaStream_t stream) {
+    if (p.lb) {
+        dim3 grid((p.H + REDUCE_BIG_THREADS - 1) / REDUCE_BIG_THREADS, batch);
+        ransac_reduce_big_sum_kernel<<<grid, REDUCE_BIG_THREADS, 0, stream>>>(p);
+        ransac_reduce_big_list_kernel<<<grid, REDUCE_BIG_THREADS, 0, stream>>>(p);
+        return cudaGetLastError();
+    }
     ransac_reduce_kernel<<<batch, REDUCE_THREADS, 0, stream>>>(p);
     return cudaGetLastError();
 }
+int ransac_reduce_launches(const RansacParams& p) { return p.lb ? 2 : 1; }
 
 // ------------------------------------------------------------------------------------ rescore (fp64)
 constexpr int RESCORE_THREADS = 256;
@@ -448,7 +307,46 @@ __global__ void __launch_bounds__(RESCORE_THREADS) ransac_rescore_kernel(const R
     }
 }
 
+// Large-M form (p.cand_part != NULL): a block re-scores one candidate over one range of REFIT_BIG_ROWS correspondences;
+// the per-range (count, sum r^2) partials are summed in range order by ransac_select_big_kernel, so the exact sums do
+// not depend on the launch geometry (nor on how many ranks share the hypotheses in tvg_huge_pair).
+constexpr int RESCORE_BIG_ROWS = 2048;   // == REFIT_BIG_ROWS
+constexpr int RESCORE_BIG_SLOTS = 64;
+
+__global__ void __launch_bounds__(RESCORE_THREADS) ransac_rescore_big_kernel(const RansacParams p, int nblk) {
+    __shared__ double s_buf[RESCORE_THREADS / 32];
+    const int b = blockIdx.z, blk = blockIdx.y;
+    const int M = p.m_count ? min(p.m_count[b], p.n_max) : p.m;
+    const int ncand = p.n_cand[b];
+    const size_t ob = (size_t)b * p.n_max, oh = (size_t)b * p.H;
+    const double2* src = reinterpret_cast<const double2*>(p.src) + ob;
+    const double2* dst = reinterpret_cast<const double2*>(p.dst) + ob;
+    const int lo = blk * RESCORE_BIG_ROWS, hi = min(M, lo + RESCORE_BIG_ROWS);
+    for (int ci = blockIdx.x; ci < ncand; ci += gridDim.x) {
+        const int h = p.cand[oh + ci];
+        double E[9];
+#pragma unroll
+        for (int i = 0; i < 9; ++i) E[i] = p.E64[(oh + h) * 9 + i];
+        double cnt = 0.0, sse = 0.0;
+        for (int m = lo + threadIdx.x; m < hi; m += RESCORE_THREADS) {
+            const double2 s = src[m], d = dst[m];
+            const double r = sampson_residual(E, s.x, s.y, d.x, d.y);
+            cnt += (r < p.thr) ? 1.0 : 0.0;
+            sse = fma(r, r, sse);
+        }
+        cnt = block_sum_f64<RESCORE_THREADS>(cnt, s_buf);
+        sse = block_sum_f64<RESCORE_THREADS>(sse, s_buf);
+        if (threadIdx.x == 0) p.cand_part[(oh + ci) * nblk + blk] = make_double2(cnt, sse);
+    }
+}
+
 cudaError_t launch_ransac_rescore(const RansacParams& p, int batch, cudaStream_t stream) {
+    if (p.cand_part) {
+        const int nblk = (p.n_max + RESCORE_BIG_ROWS - 1) / RESCORE_BIG_ROWS > 0 ? (p.n_max + RESCORE_BIG_ROWS - 1) / RESCORE_BIG_ROWS : 1;
+        dim3 grid(p.H < RESCORE_BIG_SLOTS ? p.H : RESCORE_BIG_SLOTS, nblk, batch);
+        ransac_rescore_big_kernel<<<grid, RESCORE_THREADS, 0, stream>>>(p, nblk);
+        return cudaGetLastError();
+    }
     const int gx = batch >= 148 ? 4 : (p.H < 592 ? p.H : 592);
     dim3 grid(gx, batch);
     ransac_rescore_kernel<<<grid, RESCORE_THREADS, 0, stream>>>(p);
@@ -720,36 +618,87 @@ __global__ void __launch_bounds__(REFIT_THREADS, 2) ransac_refit_kernel(const Ra
 constexpr int REFIT_BIG_N = 4096;
 constexpr int REFIT_BIG_ROWS = 2048;
 constexpr int REFIT_BIG_STRIDE = 64;    // doubles per (pair, block): [0] count, [1..4] sums, [5..6] q sums, [8..52] A^T A
-int ransac_refit_big_blocks(int n_max) { return n_max > REFIT_BIG_N ? (n_max + REFIT_BIG_ROWS - 1) / REFIT_BIG_ROWS : 0; }
+static int refit_nblk(int n_max) { return n_max > REFIT_BIG_ROWS ? (n_max + REFIT_BIG_ROWS - 1) / REFIT_BIG_ROWS : 1; }
+int ransac_refit_big_blocks(int n_max, bool force) { return (n_max > REFIT_BIG_N || force) ? refit_nblk(n_max) : 0; }
 int ransac_refit_big_stride() { return REFIT_BIG_STRIDE; }
 
-__global__ void __launch_bounds__(REFIT_THREADS) ransac_refit_big_select_kernel(const RansacParams p) {
+// "no model" outputs of a pair (fewer than 9 correspondences, or every hypothesis degenerate)
+__device__ void write_no_model(const RansacParams& p, int b, int M) {
+    const double qnan = __longlong_as_double(0x7ff8000000000000LL);
+    p.best[b] = -1;
+    p.best_sse[b] = qnan;
+    p.n_inl[b] = 0;
+    p.status[b] = (M <= 8) ? 1 : 2;
+    for (int i = 0; i < 9; ++i) { p.E[b * 9 + i] = qnan; p.E_best[b * 9 + i] = qnan; }
+    for (int i = 0; i < 16; ++i) p.Rt[b * 16 + i] = qnan;
+    p.refit_ws[(size_t)b * REFIT_WS + 51] = 0.0;
+}
+
+// Sums the per-range re-score partials of every candidate in range order, applies the selection rule and publishes
+// the winner: p.best / p.best_sse / p.E_best, or -- when the hypotheses of this pair are shared between ranks
+// (p.rec != NULL, tvg_huge_pair) -- this rank's record {count, global hypothesis index, sum r^2, E} for the exchange.
+__global__ void __launch_bounds__(REFIT_THREADS) ransac_select_big_kernel(const RansacParams p, int nblk) {
     __shared__ int s_bc[REFIT_THREADS / 32], s_bh[REFIT_THREADS / 32];
     __shared__ double s_bs[REFIT_THREADS / 32];
-    const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int b = blockIdx.x, tid = threadIdx.x;
     const int M = p.m_count ? min(p.m_count[b], p.n_max) : p.m;
     const size_t oh = (size_t)b * p.H;
     const int ncand = p.n_cand[b];
-    const double qnan = __longlong_as_double(0x7ff8000000000000LL);
     BestSel sel = best_init();
     for (int ci = tid; ci < ncand; ci += REFIT_THREADS) {
         const int h = p.cand[oh + ci];
-        best_update(sel, p.cand_cnt[oh + h], p.cand_sse[oh + h], h);
+        double cnt = 0.0, sse = 0.0;
+        for (int k = 0; k < nblk; ++k) {
+            const double2 v = p.cand_part[(oh + ci) * nblk + k];
+            cnt += v.x;
+            sse += v.y;
+        }
+        p.cand_cnt[oh + h] = (int)cnt;
+        p.cand_sse[oh + h] = sse;
+        p.counts[oh + h] = (int)cnt;   // candidates report their exact count
+        best_update(sel, (int)cnt, sse, h);
     }
     sel = best_block_reduce(sel, s_bc, s_bh, s_bs);
     if (tid == 0) {
         const bool have = best_is_model(sel);
-        const int best = have ? sel.h : -1;
-        p.best[b] = best;
-        p.best_sse[b] = have ? p.cand_sse[oh + sel.h] : qnan;
-        if (best < 0) {
-            p.n_inl[b] = 0;
-            p.status[b] = (M <= 8) ? 1 : 2;
-            for (int i = 0; i < 9; ++i) { p.E[b * 9 + i] = qnan; p.E_best[b * 9 + i] = qnan; }
-            for (int i = 0; i < 16; ++i) p.Rt[b * 16 + i] = qnan;
-            p.refit_ws[(size_t)b * REFIT_WS + 51] = 0.0;
+        if (p.rec) {
+            BestRec r;
+            r.count = have ? sel.c : 0;
+            r.hyp = have ? sel.h + p.h_off : -1;
+            r.sse = have ? p.cand_sse[oh + sel.h] : 0.0;
+            for (int i = 0; i < 9; ++i) r.E[i] = have ? p.E64[(oh + sel.h) * 9 + i] : 0.0;
+            r.pad = 0.0;
+            p.rec[b] = r;
+        } else if (have) {
+            p.best[b] = sel.h;
+            p.best_sse[b] = p.cand_sse[oh + sel.h];
+            for (int i = 0; i < 9; ++i) p.E_best[b * 9 + i] = p.E64[(oh + sel.h) * 9 + i];
+        } else {
+            write_no_model(p, b, M);
         }
     }
+}
+
+// After the exchange: the global winner among the ranks' records (same total order) becomes p.best / p.E_best on
+// every rank.  One pair per launch (tvg_huge_pair).
+__global__ void ransac_merge_records_kernel(const RansacParams p, const BestRec* recs, int world) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    const int M = p.m_count ? min(p.m_count[0], p.n_max) : p.m;
+    BestSel sel = best_init();
+    int who = -1;
+    for (int r = 0; r < world; ++r) {
+        if (recs[r].hyp < 0) continue;
+        const int before = sel.h;
+        best_update(sel, recs[r].count, recs[r].sse, recs[r].hyp);
+        if (sel.h != before) who = r;
+    }
+    if (who < 0) {
+        write_no_model(p, 0, M);
+        return;
+    }
+    p.best[0] = recs[who].hyp;
+    p.best_sse[0] = recs[who].sse;
+    for (int i = 0; i < 9; ++i) p.E_best[i] = recs[who].E[i];
 }
 
 __global__ void __launch_bounds__(REFIT_THREADS) ransac_refit_big_mask_kernel(const RansacParams p, int nblk) {
@@ -766,7 +715,7 @@ __global__ void __launch_bounds__(REFIT_THREADS) ransac_refit_big_mask_kernel(co
     }
     double Eb[9];
 #pragma unroll
-    for (int i = 0; i < 9; ++i) Eb[i] = p.E64[((size_t)b * p.H + best) * 9 + i];
+    for (int i = 0; i < 9; ++i) Eb[i] = p.E_best[b * 9 + i];
     const double2* src = reinterpret_cast<const double2*>(p.src) + ob;
     const double2* dst = reinterpret_cast<const double2*>(p.dst) + ob;
     double cnt = 0.0, sum[4] = {0.0, 0.0, 0.0, 0.0};
@@ -817,8 +766,6 @@ __global__ void __launch_bounds__(REFIT_THREADS) ransac_refit_big_scatter_kernel
     if (blk == 0 && tid == 0) {
         p.n_inl[b] = total;
         p.status[b] = 0;
-#pragma unroll
-        for (int i = 0; i < 9; ++i) p.E_best[b * 9 + i] = p.E64[((size_t)b * p.H + best) * 9 + i];
     }
     const double2* src = reinterpret_cast<const double2*>(p.src) + ob;
     const double2* dst = reinterpret_cast<const double2*>(p.dst) + ob;
@@ -923,7 +870,7 @@ __global__ void __launch_bounds__(64) ransac_refit_big_combine_kernel(const Rans
     if (total < 8) {
         if (tid == 0) {
             ws[51] = 1.0;
-            for (int i = 0; i < 9; ++i) ws[52 + i] = p.E64[((size_t)b * p.H + best) * 9 + i];
+            for (int i = 0; i < 9; ++i) ws[52 + i] = p.E_best[b * 9 + i];
         }
         return;
     }
@@ -938,7 +885,7 @@ __global__ void __launch_bounds__(64) ransac_refit_big_combine_kernel(const Rans
         ws[45] = 1.4142135623730951 / sqrt(qs / (double)total); ws[46] = c[0]; ws[47] = c[1];
         ws[48] = 1.4142135623730951 / sqrt(qd / (double)total); ws[49] = c[2]; ws[50] = c[3];
         ws[51] = 2.0;
-        for (int i = 0; i < 9; ++i) ws[52 + i] = p.E64[((size_t)b * p.H + best) * 9 + i];
+        for (int i = 0; i < 9; ++i) ws[52 + i] = p.E_best[b * 9 + i];
     }
 }
 
@@ -993,11 +940,23 @@ __global__ void __launch_bounds__(SOLVE_WARPS * 32) ransac_solve_kernel(const Ra
     }
 }
 
+// big path only: candidate sums + selection (publishes the winner, or this rank's record when p.rec is set)
+cudaError_t launch_ransac_select_big(const RansacParams& p, int batch, cudaStream_t stream) {
+    ransac_select_big_kernel<<<batch, REFIT_THREADS, 0, stream>>>(p, refit_nblk(p.n_max));
+    return cudaGetLastError();
+}
+
+cudaError_t launch_ransac_merge_records(const RansacParams& p, const BestRec* recs, int world, cudaStream_t stream) {
+    ransac_merge_records_kernel<<<1, 32, 0, stream>>>(p, recs, world);
+    return cudaGetLastError();
+}
+
+// mask + inlier compaction + refit accumulation + solve.  Big path (p.refit_big): p.best / p.E_best are already
+// published (launch_ransac_select_big, or launch_ransac_merge_records after an exchange).
 cudaError_t launch_ransac_refit(const RansacParams& p, int batch, cudaStream_t stream) {
-    const int nblk = p.refit_big ? ransac_refit_big_blocks(p.n_max) : 0;
-    if (nblk > 0) {
+    if (p.refit_big) {
+        const int nblk = refit_nblk(p.n_max);
         dim3 grid(nblk, batch);
-        ransac_refit_big_select_kernel<<<batch, REFIT_THREADS, 0, stream>>>(p);
         ransac_refit_big_mask_kernel<<<grid, REFIT_THREADS, 0, stream>>>(p, nblk);
         ransac_refit_big_scatter_kernel<<<grid, REFIT_THREADS, 0, stream>>>(p, nblk);
         ransac_refit_big_ata_kernel<<<grid, REFIT_THREADS, 0, stream>>>(p, nblk);

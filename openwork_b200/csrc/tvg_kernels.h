@@ -56,6 +56,16 @@ int compact_big_blocks(int n_max);   // 0 when the single-CTA form is used
 cudaError_t launch_compact(const CompactParams& p, int batch, cudaStream_t stream);
 
 // ---------------------------------------------------------------- RANSAC (ransac.cu)
+// One rank's best hypothesis of a pair whose hypotheses are shared between ranks (tvg_huge_pair): what the ranks
+// exchange.  96 bytes.
+struct BestRec {
+    int32_t count;             // exact (fp64) inlier count
+    int32_t hyp;               // GLOBAL hypothesis index, -1 = this rank has no model
+    double sse;                // exact sum of squared residuals over all correspondences
+    double E[9];               // the hypothesis' model (pre-refit)
+    double pad;
+};
+
 struct RansacParams {
     const double* src;         // [batch][n_max][2]
     const double* dst;         // [batch][n_max][2]
@@ -70,6 +80,9 @@ struct RansacParams {
     float band_rel;            // fp32 uncertainty band, relative to thr^2*den
     int want_sse;              // compute the fp32 sum r^2 per hypothesis (diagnostic output)
     float band_floor;          // ... plus an absolute floor (cancellation in num when den -> 0)
+    // scoring constants derived from the three above on the host (ransac_score_constants): as kernel parameters they
+    // are constant-bank operands of the FFMAs and cost no register-file read
+    float s_nthr2, s_nband, s_c1, s_k1;
     // outputs / scratch
     double* E64;               // [batch][H][9]
     float* E32;                // [batch][9][H]  Frobenius-normalised, SoA
@@ -105,6 +118,11 @@ struct RansacParams {
     int32_t* status;           // [batch] 0 ok, 1 = fewer than 9 correspondences
     double* refit_ws;          // [batch][ransac_refit_ws_doubles()] accumulate -> solve hand-off
     double* refit_big;         // [batch][ransac_refit_big_blocks(n_max)][ransac_refit_big_stride()] (NULL -> single-CTA refit)
+    // grid-wide forms (few pairs, many hypotheses / many correspondences)
+    int32_t* lb;               // [batch] best lower bound of the count (NULL -> single-CTA reduce per pair)
+    double2* cand_part;        // [batch][H][blocks] per-range re-score partials; set together with refit_big
+    BestRec* rec;              // [batch] this rank's record instead of p.best / p.E_best (NULL unless distributed)
+    int h_off;                 // global index of this rank's hypothesis 0
 };
 cudaError_t launch_ransac_fit(const RansacParams& p, int batch, cudaStream_t stream);
 // scoring launch plan: hypotheses per thread, row slots (p.chunks) x rows per slot (p.chunk), persistent grid
@@ -115,11 +133,15 @@ struct ScorePlan {
 void ransac_score_plan(int batch, int n_max, int H, int sm_count, int cfg_hpt, int cfg_ctas, ScorePlan* out);
 // queue: one zeroed unsigned int (the work-item counter; the reduce kernel zeroes it again)
 cudaError_t launch_ransac_score(const RansacParams& p, int batch, const ScorePlan& plan, cudaStream_t stream);
+void ransac_score_constants(RansacParams* p);   // fills s_nthr2 / s_nband / s_c1 / s_k1 from thr, band_rel, band_floor
 cudaError_t launch_ransac_reduce(const RansacParams& p, int batch, cudaStream_t stream);
 cudaError_t launch_ransac_rescore(const RansacParams& p, int batch, cudaStream_t stream);
+int ransac_reduce_launches(const RansacParams& p);
+cudaError_t launch_ransac_select_big(const RansacParams& p, int batch, cudaStream_t stream);
+cudaError_t launch_ransac_merge_records(const RansacParams& p, const BestRec* recs, int world, cudaStream_t stream);
 cudaError_t launch_ransac_refit(const RansacParams& p, int batch, cudaStream_t stream);
 int ransac_refit_ws_doubles();
-int ransac_refit_big_blocks(int n_max);   // 0 when the single-CTA refit is used
+int ransac_refit_big_blocks(int n_max, bool force = false);   // 0 when the single-CTA refit is used
 int ransac_refit_big_stride();
 
 // ---------------------------------------------------------------- pose + triangulation (pose_tri.cu)
@@ -132,7 +154,8 @@ struct PoseChainParams {
     const double* first_init;  // device 4x4 overriding the initial pose of sequence 0 of this launch (may be NULL)
     int batch;                 // used when seq_off == NULL: one sequence holding pairs [0, batch)
 };
-cudaError_t launch_pose_chain(const PoseChainParams& p, int nseq, cudaStream_t stream);
+// batch_hint = total pairs when the host knows it (0: unknown); two launches when pair_pinv is wanted
+cudaError_t launch_pose_chain(const PoseChainParams& p, int nseq, int batch_hint, cudaStream_t stream);
 
 struct TriParams {
     const double* pix1;        // [batch][n_max][2] pixel coords in the first view

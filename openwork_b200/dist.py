@@ -1,19 +1,21 @@
-"""Multi-GPU partitioning of the two-view path (one process per GPU, torch.distributed).
+"""Multi-GPU partitioning of the two-view path (one process per GPU, torch.distributed for the plumbing).
 
 Two levels shard naturally:
 
 * independent sequences / frame pairs (config C4): sequence s -> rank s mod G, NO data-path collective
   (``shard_sequences``); results are gathered on the host if wanted.
-* one huge keyframe pair (config C5): query rows are split into G contiguous blocks for the matcher
-  (train set replicated), hypotheses are split into G contiguous blocks for RANSAC.  The only exchange
-  steps are (1) an all-gather of the per-rank match slices -- concatenation in rank order preserves the
-  reference's ascending-query order -- and (2) ONE all-reduce(MAX) of a 63-bit packed key
-  ``count | ~sse | ~hypothesis`` that implements the reference's selection rule (most inliers, then
-  smallest sum of squared residuals, then earliest trial).  The rank that owns
-  the winning hypothesis then broadcasts its inlier mask, refit E and Rt (one small message).
+* one huge keyframe pair (config C5): query rows are split into G contiguous blocks for the matcher (train set
+  replicated), hypotheses into G contiguous blocks for RANSAC.  The exchange steps are two FIXED-SIZE all-gathers:
+  (1) the matcher outputs of the padded query blocks -- rank order is ascending query order, so every rank
+  compacts the same match list -- and (2) one 96-byte record per rank ``{count, hypothesis, sum r^2 (fp64), E}``;
+  every rank applies the reference's selection rule (most inliers, then smallest sum of squared residuals, then
+  earliest trial; skimage ``ransac``) to the same G records with exact keys, so G ranks
+  return bit for bit what one rank returns.  Mask, refit, pose and triangulation are then computed on every rank.
 
-The compute calls go through a ``backend`` (default: ``openwork_b200.ops``, i.e. the CUDA kernels).
-Tests inject a CPU stand-in to exercise this host logic over gloo without a GPU.
+The product path is ``huge_pair``: one C call (``tvg_huge_pair``) over the NCCL communicator that ``init_comm``
+binds to the context -- kernels and collectives on one stream, no host synchronisation.  ``huge_pair_protocol`` is
+the same protocol written over ``torch.distributed`` with the compute calls injected through a ``backend``: the
+CPU tests run it over gloo (world size 2) with an oracle stand-in to exercise the host logic without a GPU.
 """
 from __future__ import annotations
 
@@ -21,11 +23,9 @@ import numpy as np
 import torch
 import torch.distributed as dist
 
-COUNT_BITS, SSE_BITS, HYP_BITS = 17, 30, 16      # 63 bits: fits a signed int64 for NCCL MAX
-
 
 def shard_range(n, rank, world):
-    """Contiguous block [lo, hi) of n items for `rank` (first n % world ranks get one extra)."""
+    """Contiguous block [lo, hi) of n items for `rank` (first n % world ranks get one extra); == tvg_shard_range."""
     base, extra = divmod(n, world)
     lo = rank * base + min(rank, extra)
     return lo, lo + base + (1 if rank < extra else 0)
@@ -36,24 +36,26 @@ def shard_sequences(nseq, rank, world):
     return list(range(rank, nseq, world))
 
 
-def pack_best_key(count, sse, hyp):
-    """int64 key whose MAX is the reference's best hypothesis: most inliers, then smallest sse
-    (compared at fp32 resolution minus one mantissa bit), then smallest hypothesis index."""
-    count = torch.as_tensor(count).to(torch.int64)
-    hyp = torch.as_tensor(hyp).to(torch.int64)
-    sse32 = torch.as_tensor(sse).to(torch.float32).clamp_min(0)
-    sse32 = torch.nan_to_num(sse32, nan=float("inf"))
-    bits = sse32.view(torch.int32).to(torch.int64) >> 1              # monotone for non-negative floats
-    inv_sse = ((1 << SSE_BITS) - 1) - bits.clamp(0, (1 << SSE_BITS) - 1)
-    inv_hyp = ((1 << HYP_BITS) - 1) - hyp
-    return (count << (SSE_BITS + HYP_BITS)) | (inv_sse << HYP_BITS) | inv_hyp
+def query_block(nq, rank, world):
+    """Padded query block of the matcher: per = ceil(nq / world) rows per rank; returns (lo, hi, per)."""
+    per = -(-nq // world)
+    lo = min(nq, rank * per)
+    return lo, min(nq, lo + per), per
 
 
-def unpack_best_key(key):
-    key = int(key)
-    count = key >> (SSE_BITS + HYP_BITS)
-    hyp = ((1 << HYP_BITS) - 1) - (key & ((1 << HYP_BITS) - 1))
-    return count, hyp
+def select_best_record(records):
+    """The reference's selection rule over per-rank records ``(count, hypothesis, sse)`` (hypothesis < 0 = the rank
+    has no model): most inliers, then smallest sum of squared residuals (NaN counts as +inf), then earliest trial.
+    Returns the index of the winning record, or -1.  Mirrors ``ransac_merge_records_kernel``."""
+    best, key = -1, None
+    for i, (count, hyp, sse) in enumerate(records):
+        if hyp < 0:
+            continue
+        s = float("inf") if sse != sse else float(sse)
+        k = (-int(count), s, int(hyp))
+        if key is None or k < key:
+            best, key = i, k
+    return best
 
 
 def _world(group):
@@ -62,103 +64,107 @@ def _world(group):
     return 0, 1
 
 
-def all_gather_varlen(x, group=None):
-    """Concatenate per-rank tensors of different first-dim length in RANK ORDER (one size exchange,
-    one padded all_gather)."""
+def all_gather_fixed(x, group=None):
+    """Concatenate equally-shaped per-rank tensors in RANK ORDER (one all_gather, no size exchange)."""
     rank, world = _world(group)
     if world == 1:
         return x
-    n = torch.tensor([x.shape[0]], dtype=torch.int64, device=x.device)
-    sizes = [torch.zeros_like(n) for _ in range(world)]
-    dist.all_gather(sizes, n, group=group)
-    sizes = [int(s.item()) for s in sizes]
-    mx = max(max(sizes), 1)
-    pad = torch.zeros((mx,) + tuple(x.shape[1:]), dtype=x.dtype, device=x.device)
-    pad[: x.shape[0]] = x
-    bufs = [torch.empty_like(pad) for _ in range(world)]
-    dist.all_gather(bufs, pad, group=group)
-    return torch.cat([b[:s] for b, s in zip(bufs, sizes)], dim=0)
+    bufs = [torch.empty_like(x) for _ in range(world)]
+    dist.all_gather(bufs, x.contiguous(), group=group)
+    return torch.cat(bufs, dim=0)
 
 
-def allreduce_best(key, group=None):
-    """The single all-reduce(MAX) that picks the global best hypothesis."""
+# ------------------------------------------------------------------------------------------ product path
+def init_comm(ctx=None, group=None):
+    """Bind an NCCL communicator spanning `group` (default: the world) to the context (``tvg_comm_init``): rank 0
+    creates the 128-byte id, torch.distributed carries it to the other ranks, every rank joins.  Idempotent."""
+    from . import _lib, ops
+    ctx = ctx or ops.context()
     rank, world = _world(group)
+    if ctx.comm_info()[1] == world and (world == 1 or getattr(ctx, "_comm_group", None) is group):
+        return ctx
+    box = [_lib.comm_unique_id() if rank == 0 else None]
     if world > 1:
-        dist.all_reduce(key, op=dist.ReduceOp.MAX, group=group)
-    return key
+        src = dist.get_global_rank(group, 0) if group is not None else 0
+        dist.broadcast_object_list(box, src=src, group=group)
+    ctx.comm_init(box[0], rank, world)
+    ctx._comm_group = group
+    return ctx
 
 
-def huge_pair(curr_kps, curr_des, last_kps, last_des, K, words, ratio=0.75, residual_threshold=0.005,
-              backend=None, group=None):
-    """Config C5: one keyframe pair split over the ranks of `group`.
+def huge_pair(curr_kps, curr_des, last_kps, last_des, K, words, ratio=0.75, residual_threshold=0.005, ctx=None,
+              group=None, out=None, sync=True):
+    """Config C5 on the GPUs of `group`: ``tvg_huge_pair`` over the context's communicator.  Inputs are replicated
+    on every rank.  With ``sync`` the per-row outputs are trimmed to their valid lengths (one host synchronisation
+    after the call) and the same dict is returned on every rank: qidx, tidx, M, best, count, best_sse, E, E_best,
+    mask, Rt, points4d, good, status; without, the raw device tensors of ``ops.huge_pair``."""
+    from . import ops
+    ctx = init_comm(ctx, group)
+    o = ops.huge_pair(curr_kps, curr_des, last_kps, last_des, K, words=words, ratio=ratio,
+                      residual_threshold=residual_threshold, ctx=ctx, out=out)
+    if not sync:
+        return o
+    M, n = int(o["m_count"].item()), int(o["n_inl"].item())
+    if int(o["status"].item()) == 1:
+        raise ValueError("`min_samples` must be in range (0, <number-of-samples>)")
+    return dict(qidx=o["qidx"][:M], tidx=o["tidx"][:M], M=M, best=int(o["best"].item()), count=n,
+                best_sse=float(o["best_sse"].item()), E=o["E"], E_best=o["E_best"], mask=o["mask"][:M].bool(),
+                Rt=o["Rt"], points4d=o["points4d"][:n], good=o["good"][:n].bool(), status=int(o["status"].item()),
+                raw=o)
 
-    Inputs are replicated on every rank (descriptor sets are <= 2 MiB).  Returns the same dict on
-    every rank: qidx, tidx (all matches, ascending query order), best (global hypothesis index),
-    count, E (refit), mask, Rt, points4d (all inliers, match order), good.
-    """
-    if backend is None:
-        from . import ops as backend
+
+# ------------------------------------------------------------------------------------------ protocol model
+def huge_pair_protocol(curr_kps, curr_des, last_kps, last_des, K, words, backend, ratio=0.75, residual_threshold=0.005,
+                       group=None):
+    """The protocol of ``tvg_huge_pair`` over ``torch.distributed`` collectives with the compute calls injected:
+    ``backend`` provides knn2_hamming256, ratio_compact, ransac_essential, refit_essential and triangulate (the
+    CPU tests pass an oracle stand-in and run this over gloo).  Returns the same dict on every rank."""
     rank, world = _world(group)
     nq = curr_des.shape[0]
     H = words.shape[0]
-    if H > (1 << HYP_BITS):
-        raise ValueError("at most 65536 hypotheses fit the packed key")
-
-    # 1. matcher: this rank's block of query rows against the whole train set
-    q_lo, q_hi = shard_range(nq, rank, world)
-    idx, dist_, keep = backend.knn2_hamming256(curr_des[q_lo:q_hi], last_des, ratio=ratio, return_keep=True)
-    loc = backend.ratio_compact(idx, keep, curr_kps[q_lo:q_hi], last_kps, K)
-    # 2. exchange step 1: all-gather the match slices (rank order == ascending query order), packed into
-    #    one buffer per rank: [qidx+q_lo, tidx] as two f64-exact columns next to src / dst  -> f64[M_loc, 6]
-    packed = torch.cat([(loc["qidx"] + q_lo).to(torch.float64)[:, None], loc["tidx"].to(torch.float64)[:, None],
-                        loc["src"], loc["dst"]], dim=1)
-    packed = all_gather_varlen(packed, group)
-    qidx = packed[:, 0].to(torch.int32)
-    tidx = packed[:, 1].to(torch.int32)
-    src = packed[:, 2:4].contiguous()
-    dst = packed[:, 4:6].contiguous()
+    if H < world:
+        raise ValueError("fewer hypotheses than ranks")
+    # 1. matcher on the padded query block of this rank
+    q_lo, q_hi, per = query_block(nq, rank, world)
+    blk = torch.zeros((per, 3), dtype=torch.int32)           # idx0, idx1, keep per query row (fixed size)
+    if q_hi > q_lo:
+        idx, dist_, keep = backend.knn2_hamming256(curr_des[q_lo:q_hi], last_des, ratio=ratio, return_keep=True)
+        blk[: q_hi - q_lo, 0] = torch.as_tensor(idx)[:, 0].to(torch.int32)
+        blk[: q_hi - q_lo, 1] = torch.as_tensor(idx)[:, 1].to(torch.int32)
+        blk[: q_hi - q_lo, 2] = torch.as_tensor(keep).to(torch.int32)
+    # 2. exchange step 1: fixed-size all-gather, rank order == ascending query order; every rank compacts all rows
+    full = all_gather_fixed(blk, group)[:nq]
+    loc = backend.ratio_compact(full[:, :2].contiguous(), full[:, 2].bool(), curr_kps, last_kps, K)
+    qidx, tidx, src, dst = loc["qidx"], loc["tidx"], loc["src"], loc["dst"]
     M = src.shape[0]
     if M <= 8:
         raise ValueError("`min_samples` must be in range (0, <number-of-samples>)")
-
-    # 3. RANSAC over this rank's block of hypotheses (rows of the same global word table everywhere;
-    #    the word -> index mapping depends only on the row and on M, so slices map identically)
+    # 3. RANSAC over this rank's block of hypotheses (rows of the same global word table everywhere; the
+    #    word -> index mapping depends only on the row and on M, so blocks map identically)
     words = np.ascontiguousarray(np.asarray(words, dtype=np.uint32))
     h_lo, h_hi = shard_range(H, rank, world)
-    key = torch.zeros(1, dtype=torch.int64, device=src.device)
-    if h_hi > h_lo:
-        r = backend.ransac_essential(src, dst, words=words[h_lo:h_hi], residual_threshold=residual_threshold)
-        if r["best"] >= 0 and r["n_inl"] >= 0:
-            key = pack_best_key(torch.tensor([r["n_inl"]]), torch.tensor([r["best_sse"]]),
-                                torch.tensor([r["best"] + h_lo])).to(src.device)
-    # 4. exchange step 2: ONE all-reduce(MAX) of the packed key
-    key = allreduce_best(key, group)
-    count, best = unpack_best_key(key.item())
+    rec = torch.zeros((1, 12), dtype=torch.float64)
+    rec[0, 1] = -1.0
+    r = backend.ransac_essential(src, dst, words=words[h_lo:h_hi], residual_threshold=residual_threshold)
+    if r["best"] >= 0 and r["n_inl"] >= 0:
+        rec[0, 0], rec[0, 1], rec[0, 2] = float(r["n_inl"]), float(r["best"] + h_lo), float(r["best_sse"])
+        rec[0, 3:] = torch.as_tensor(r["E_best"], dtype=torch.float64).reshape(-1)
+    # 4. exchange step 2: ONE all-gather of the records; the same exact rule on every rank
+    recs = all_gather_fixed(rec, group)
+    win = select_best_record([(int(x[0]), int(x[1]), float(x[2])) for x in recs.tolist()])
+    if win < 0:
+        return dict(qidx=qidx, tidx=tidx, M=M, best=-1, count=0, status=2)
+    best, E_best = int(recs[win, 1]), recs[win, 3:].reshape(3, 3).clone()
+    # 5. inlier mask of the winner, refit, extract_Rt, triangulation: on every rank, identical
+    w = backend.refit_essential(src, dst, E_best, residual_threshold)
+    mask = torch.as_tensor(w["mask"]).bool()
 
-    # 5. the rank that owns the winning hypothesis already holds its mask / refit E / Rt (its local best IS
-    #    the global best); it broadcasts them in one message.  (world == 1: nothing to do.)
-    owner = next(rk for rk in range(world) if shard_range(H, rk, world)[0] <= best < shard_range(H, rk, world)[1])
-    if world > 1:
-        msg = torch.empty(M + 8 * (9 + 9 + 16), dtype=torch.uint8, device=src.device)
-        if rank == owner:
-            msg[:M] = r["mask"].to(torch.uint8)
-            msg[M:] = torch.cat([r["E"].reshape(-1), r["E_best"].reshape(-1), r["Rt"].reshape(-1)]).view(torch.uint8)
-        dist.broadcast(msg, src=dist.get_global_rank(group, owner) if group is not None else owner, group=group)
-        mask = msg[:M].bool()
-        tail = msg[M:].clone().view(torch.float64)
-        w = dict(E=tail[:9].view(3, 3), E_best=tail[9:18].view(3, 3), Rt=tail[18:34].view(4, 4))
-    else:
-        w, mask = r, r["mask"]
-    # 6. triangulation of the inliers, split by points, gathered back in match order
     def _t(x):
-        return (x if isinstance(x, torch.Tensor) else torch.as_tensor(np.asarray(x))).to(src.device)
+        return x if isinstance(x, torch.Tensor) else torch.as_tensor(np.asarray(x))
     ck = _t(curr_kps)[qidx.long()][mask]
     lk = _t(last_kps)[tidx.long()][mask]
-    p_lo, p_hi = shard_range(ck.shape[0], rank, world)
-    Rt = w["Rt"]
-    pose0 = np.eye(4)
-    pose1 = np.asarray(Rt.cpu()) @ pose0
-    X = backend.triangulate(lk[p_lo:p_hi].contiguous(), ck[p_lo:p_hi].contiguous(), pose0, pose1, K)
-    X = all_gather_varlen(X.to(src.device), group)
-    return dict(qidx=qidx, tidx=tidx, M=M, best=best, count=count, E=w["E"], E_best=w["E_best"], mask=mask,
-                Rt=Rt, points4d=X, good=X[:, 2] > 0)
+    Rt = torch.as_tensor(w["Rt"])
+    X = backend.triangulate(lk.contiguous(), ck.contiguous(), np.eye(4), np.asarray(Rt) @ np.eye(4), K)
+    X = torch.as_tensor(X)
+    return dict(qidx=qidx, tidx=tidx, M=M, best=best, count=int(mask.sum()), best_sse=float(recs[win, 2]),
+                E=torch.as_tensor(w["E"]), E_best=E_best, mask=mask, Rt=Rt, points4d=X, good=X[:, 2] > 0, status=0)

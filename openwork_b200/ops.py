@@ -13,7 +13,7 @@ import numpy as np
 import torch
 
 from . import _lib
-from ._lib import PairsIO, RansacIO, check
+from ._lib import HugePairIO, PairsIO, RansacIO, check
 
 RATIO = 0.75                # slam.py:131
 RESIDUAL_THRESHOLD = 0.005  # slam.py:158
@@ -632,3 +632,70 @@ def wait_pairs_host(ctx):
     """Block until the batch submitted with ``process_pairs_host(..., wait=False)`` on ``ctx`` is complete."""
     check(ctx.lib.tvg_pairs_host_wait(ctx.handle), "tvg_pairs_host_wait")
     ctx._inflight = None
+
+
+# ------------------------------------------------------------------------------- one huge pair (config C5)
+HUGE_PAIR_OUTPUTS = ("idx", "dist", "qidx", "tidx", "m_count", "E", "E_best", "best", "best_sse", "counts", "n_cand",
+                     "mask", "n_inl", "inl_idx", "Rt", "poses", "points4d", "good", "status")
+
+
+def huge_pair_rows(nq, nt, world):
+    """Rows of every per-row output of :func:`huge_pair` (query rows padded to a multiple of the world size)."""
+    return int(_lib.load().tvg_huge_pair_rows(int(nq), int(nt), int(world)))
+
+
+def shard_range(n, rank, world):
+    """Contiguous block [lo, hi) of n items for `rank` (tvg_shard_range: the first n % world ranks own one more)."""
+    lo, hi = C.c_int(0), C.c_int(0)
+    _lib.load().tvg_shard_range(int(n), int(rank), int(world), C.byref(lo), C.byref(hi))
+    return lo.value, hi.value
+
+
+def huge_pair(curr_kps, curr_des, last_kps, last_des, K, words=None, samples=None, ratio=RATIO,
+              residual_threshold=RESIDUAL_THRESHOLD,
+              outputs=("qidx", "tidx", "m_count", "E", "E_best", "best", "best_sse", "mask", "n_inl", "Rt", "poses",
+                       "points4d", "good", "status"), out=None, ctx=None):
+    """The ``else`` branch of process_frame (slam.py:249-266) for ONE huge keyframe pair, split over the ranks of the
+    context's communicator (``tvg_huge_pair``; see ``openwork_b200.dist.init_comm``): query rows for the matcher,
+    hypotheses for RANSAC, two fixed-size all-gathers, no host synchronisation.  Inputs are replicated CUDA tensors
+    (or numpy arrays); ``words`` / ``samples`` is the whole [H,8] table on every rank.  Returns a dict of CUDA tensors
+    (identical on all ranks, except ``counts`` which holds this rank's hypothesis block); per-row outputs have
+    :func:`huge_pair_rows` rows, valid up to ``m_count`` / ``n_inl``."""
+    dev = _device_of(curr_des, last_des, curr_kps)
+    cd = _dev(curr_des, torch.uint8, dev)
+    ld = _dev(last_des, torch.uint8, dev)
+    ck = _dev(curr_kps, torch.float64, dev)
+    lk = _dev(last_kps, torch.float64, dev)
+    tab = samples if samples is not None else words
+    tab = _dev(np.asarray(tab, dtype=np.int32 if samples is not None else np.uint32)
+               if not isinstance(tab, torch.Tensor) else tab, torch.int32, dev)
+    H = tab.shape[0]
+    nq, nt = cd.shape[0], ld.shape[0]
+    ctx = ctx or context(dev.index)
+    _, world = ctx.comm_info()
+    rows = huge_pair_rows(nq, nt, world)
+    if out is None:
+        shapes = dict(idx=((rows, 2), torch.int32), dist=((rows, 2), torch.int32), qidx=((rows,), torch.int32),
+                      tidx=((rows,), torch.int32), m_count=((1,), torch.int32), E=((3, 3), torch.float64),
+                      E_best=((3, 3), torch.float64), best=((1,), torch.int32), best_sse=((1,), torch.float64),
+                      counts=((H,), torch.int32), n_cand=((1,), torch.int32), mask=((rows,), torch.uint8),
+                      n_inl=((1,), torch.int32), inl_idx=((rows,), torch.int32), Rt=((4, 4), torch.float64),
+                      poses=((2, 4, 4), torch.float64), points4d=((rows, 4), torch.float64), good=((rows,), torch.uint8),
+                      status=((1,), torch.int32))
+        out = {k: torch.zeros(shapes[k][0], dtype=shapes[k][1], device=dev) for k in outputs}
+    io = HugePairIO()
+    io.curr_des, io.last_des, io.curr_kps, io.last_kps = cd.data_ptr(), ld.data_ptr(), ck.data_ptr(), lk.data_ptr()
+    io.nq, io.nt, io.H = nq, nt, H
+    if samples is not None:
+        io.samples = tab.data_ptr()
+    else:
+        io.words = tab.data_ptr()
+    kinv, _ = _kinv(K)
+    for i in range(9):
+        io.kinv[i] = float(kinv.flat[i])
+    io.ratio, io.thr = float(ratio), float(residual_threshold)
+    for k, v in out.items():
+        setattr(io, k, v.data_ptr())
+    check(ctx.lib.tvg_huge_pair(ctx.handle, C.byref(io), _stream()), "tvg_huge_pair")
+    ctx._hp_keep = (cd, ld, ck, lk, tab)     # inputs stay alive until the next call (the call is asynchronous)
+    return out

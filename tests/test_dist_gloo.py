@@ -1,8 +1,9 @@
 """CPU tests of the multi-GPU host logic (openwork_b200/dist.py) over gloo, world_size 2.
 
-The compute calls are injected through a backend; here a CPU stand-in built on the oracle plays the
-kernels' role so the partitioning, the all-gather of match slices and the single all-reduce(MAX) of the
-packed key can be exercised without a GPU.  The sharded result must equal the single-rank result."""
+The product path is one C call (tvg_huge_pair over NCCL); dist.huge_pair_protocol is the same protocol over
+torch.distributed with the compute calls injected through a backend.  Here a CPU stand-in built on the oracle
+plays the kernels' role so the partitioning, the two fixed-size all-gathers and the exact record selection can be
+exercised without a GPU.  The sharded result must equal the single-rank result."""
 import os
 import sys
 
@@ -49,6 +50,14 @@ class OracleBackend:
                     Rt=torch.from_numpy(tv.extract_Rt(r["E"])))
 
     @staticmethod
+    def refit_essential(src, dst, E_best, thr):
+        src, dst, E_best = np.asarray(src), np.asarray(dst), np.asarray(E_best)
+        mask = np.abs(tv.essential_residuals(E_best, src, dst)) < thr
+        n_in = int(mask.sum())
+        E = tv.essential_estimate(src[mask], dst[mask], full_matrices=(n_in < 9)) if n_in >= 8 else E_best
+        return dict(E=torch.from_numpy(E), mask=torch.from_numpy(mask), Rt=torch.from_numpy(tv.extract_Rt(E)))
+
+    @staticmethod
     def triangulate(p1, p2, pose1, pose2, Kmat):
         if len(p1) == 0:
             return torch.zeros((0, 4), dtype=torch.float64)
@@ -66,7 +75,7 @@ def _worker(rank, world, port, out_dir):
     dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
         lk, ld, ck, cd, words = _inputs()
-        r = tdist.huge_pair(ck, cd, lk, ld, K, words, backend=OracleBackend)
+        r = tdist.huge_pair_protocol(ck, cd, lk, ld, K, words, backend=OracleBackend)
         np.savez(os.path.join(out_dir, "r%d.npz" % rank), qidx=r["qidx"].numpy(), tidx=r["tidx"].numpy(),
                  best=r["best"], count=r["count"], E=r["E"].numpy(), mask=r["mask"].numpy(), Rt=r["Rt"].numpy(),
                  X=r["points4d"].numpy())
@@ -78,7 +87,7 @@ def test_huge_pair_two_ranks_equals_single_rank(tmp_path):
     port = 29500 + (os.getpid() % 2000)
     mp.spawn(_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
     lk, ld, ck, cd, words = _inputs()
-    one = tdist.huge_pair(ck, cd, lk, ld, K, words, backend=OracleBackend)        # world 1, no process group
+    one = tdist.huge_pair_protocol(ck, cd, lk, ld, K, words, backend=OracleBackend)   # world 1, no process group
     ref = tv.process_pair(lk, ld, ck, cd, np.eye(4), K, words=words)
     for rank in range(2):
         g = np.load(os.path.join(str(tmp_path), "r%d.npz" % rank))
@@ -92,23 +101,49 @@ def test_huge_pair_two_ranks_equals_single_rank(tmp_path):
         np.testing.assert_allclose(g["X"], ref["points4d"], rtol=1e-9, atol=1e-9)
 
 
-def test_packed_key_implements_the_selection_rule():
+def test_record_selection_is_the_reference_rule_with_exact_keys():
+    """select_best_record == sequential skimage rule applied to the per-rank winners, including sums
+    of squared residuals that differ only in the last fp64 bit (the old fp32-resolution key could not tell them
+    apart) and ranks without a model."""
     rng = np.random.default_rng(0)
-    counts = rng.integers(0, 65537, 4000)
-    counts[:2000] = counts[2000:]                         # force count ties
-    sse = rng.uniform(0, 50, 4000)
-    sse[:500] = sse[2000:2500]                            # force (count, sse) ties
-    hyp = rng.permutation(65536)[:4000]
-    keys = tdist.pack_best_key(torch.from_numpy(counts), torch.from_numpy(sse), torch.from_numpy(hyp))
-    assert (keys >= 0).all()
-    best = int(torch.argmax(keys))
-    # oracle order: most inliers, then smallest sse (fp32 resolution, 1 ulp dropped), then smallest index
-    s32 = (sse.astype(np.float32).view(np.int32) >> 1)
-    order = sorted(range(4000), key=lambda i: (-counts[i], s32[i], hyp[i]))
-    assert best == order[0]
-    c, h = tdist.unpack_best_key(keys[best])
-    assert c == counts[best] and h == hyp[best]
-    assert tdist.unpack_best_key(tdist.pack_best_key(65536, 0.0, 65535)) == (65536, 65535)
+    for trial in range(300):
+        G = int(rng.integers(1, 9))
+        counts = rng.integers(0, 5, G)
+        sse = rng.uniform(1.0, 2.0, G)
+        if G > 1 and trial % 3 == 0:                       # plant equal counts with sse one ulp apart
+            i, j = rng.choice(G, 2, replace=False)
+            counts[j] = counts[i]
+            sse[j] = np.nextafter(sse[i], 0.0 if trial % 2 else 4.0)
+        if G > 1 and trial % 5 == 0:                       # plant an exact (count, sse) tie: earliest trial wins
+            i, j = rng.choice(G, 2, replace=False)
+            counts[j], sse[j] = counts[i], sse[i]
+        hyp = rng.permutation(65536)[:G]
+        hyp[rng.random(G) < 0.15] = -1                     # ranks whose block held no model
+        recs = [(int(c), int(h), float(s)) for c, h, s in zip(counts, hyp, sse)]
+        got = tdist.select_best_record(recs)
+        # the reference scans trials in hypothesis order with strict improvements
+        best, bn, bs = -1, 0, np.inf
+        for i in sorted(range(G), key=lambda i: hyp[i]):
+            if hyp[i] < 0:
+                continue
+            if counts[i] > bn or (counts[i] == bn and sse[i] < bs):
+                best, bn, bs = i, counts[i], sse[i]
+        assert got == best, (recs, got, best)
+    assert tdist.select_best_record([(3, -1, 1.0)]) == -1
+    assert tdist.select_best_record([(3, 7, float("nan")), (3, 9, 5.0)]) == 1     # NaN sum counts as +inf
+
+
+def test_shard_range_matches_the_c_abi():
+    from openwork_b200 import ops
+    for n, w in ((10, 3), (7, 8), (65536, 8), (65537, 8), (0, 4), (5, 1)):
+        for r in range(w):
+            assert ops.shard_range(n, r, w) == tdist.shard_range(n, r, w)
+    assert ops.huge_pair_rows(65536, 65536, 8) == 65536
+    assert ops.huge_pair_rows(10, 4, 4) == 12 and ops.huge_pair_rows(10, 40, 4) == 40
+    for nq, w in ((10, 4), (65536, 8), (3, 8)):
+        blocks = [tdist.query_block(nq, r, w) for r in range(w)]
+        assert blocks[0][0] == 0 and max(b[1] for b in blocks) == nq
+        assert all(b[2] * w >= nq for b in blocks)
 
 
 def test_shard_helpers():
