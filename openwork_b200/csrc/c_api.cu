@@ -376,8 +376,14 @@ int tvg_triangulate(tvg_ctx* ctx, const double* pix1, const double* pix2, int ba
     p.P1 = P1; p.P2 = P2; p.p1_stride = p1_stride; p.p2_stride = p2_stride;
     memcpy(p.kinv, kinv_host, sizeof(p.kinv));
     p.points4d = points4d; p.good = good;
+    {
+        void* v = nullptr;
+        int rcf = ctx->get(S_TRI_FALLBACK, sizeof(int), &v, true);
+        if (rcf) return rcf;
+        p.n_fallback = reinterpret_cast<int*>(v);
+    }
     TVG_CUDA(tvg::launch_triangulate(p, batch, (cudaStream_t)stream));
-    ctx->launches += 1;
+    ctx->launches += 3;
     return 0;
 }
 
@@ -398,8 +404,14 @@ int tvg_point_quality(tvg_ctx* ctx, const double* pix1, const double* pix2, int 
     p.P1 = P1; p.P2 = P2; p.p1_stride = p1_stride; p.p2_stride = p2_stride;
     memcpy(p.kinv, kinv_host, sizeof(p.kinv));
     p.points4d = points4d; p.good = good; p.reproj = reproj; p.parallax_cos = parallax_cos; p.focal = focal;
+    {
+        void* v = nullptr;
+        int rcf = ctx->get(S_TRI_FALLBACK, sizeof(int), &v, true);
+        if (rcf) return rcf;
+        p.n_fallback = reinterpret_cast<int*>(v);
+    }
     TVG_CUDA(tvg::launch_triangulate(p, batch, (cudaStream_t)stream));
-    ctx->launches += 1;
+    ctx->launches += 3;
     return 0;
 }
 

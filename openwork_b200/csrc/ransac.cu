@@ -31,8 +31,8 @@ __device__ __forceinline__ bool hartley8(const double (&x)[8], const double (&y)
     double sx = 0.0, sy = 0.0;
 #pragma unroll
     for (int k = 0; k < 8; ++k) { sx += x[k]; sy += y[k]; }
-    cx = sx / 8.0;
-    cy = sy / 8.0;
+    cx = sx * 0.125;
+    cy = sy * 0.125;
     double q = 0.0;
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
@@ -40,9 +40,9 @@ __device__ __forceinline__ bool hartley8(const double (&x)[8], const double (&y)
         q = fma(dx, dx, q);
         q = fma(dy, dy, q);
     }
-    const double rms = sqrt(q / 8.0);
-    if (!(rms > 0.0)) return false;
-    s = 1.4142135623730951 / rms;
+    const double ms = q * 0.125;                  // rms^2; s = sqrt(2) / rms
+    if (!(ms > 0.0)) return false;
+    s = 1.4142135623730951 * rsqrt(ms);
     return isfinite(s);
 }
 

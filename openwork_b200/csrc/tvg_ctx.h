@@ -33,7 +33,7 @@ enum Slot {
     S_H_DES, S_H_KPS, S_H_FCOUNT, S_H_PAIRQ, S_H_PAIRT, S_H_SEQOFF, S_H_INIT, S_H_WORDS, S_H_SAMPLES,
     S_KNN_TC, S_BA_TRIAL, S_REFITBIG, S_COMPACTBIG, S_SCOREQ, S_CANDPART, S_LB,
     // tvg_huge_pair
-    S_HP_RECS, S_HP_POSE,
+    S_HP_RECS, S_HP_POSE, S_TRI_FALLBACK,
     S_NUM
 };
 

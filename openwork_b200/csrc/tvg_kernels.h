@@ -171,6 +171,7 @@ struct TriParams {
     double* reproj;            // [batch][n_max] max reprojection error over both views, pixels (may be NULL)
     double* parallax_cos;      // [batch][n_max] cosine of the angle between the two viewing rays (may be NULL)
     double focal;              // pixels per normalised unit for `reproj` (K[0][0])
+    int* n_fallback;           // one zeroed int: points left to the Jacobi kernel (zeroed again by the launch)
 };
 cudaError_t launch_triangulate(const TriParams& p, int batch, cudaStream_t stream);
 cudaError_t launch_invert4(const double* in, double* out, int n, cudaStream_t stream);

@@ -6,6 +6,19 @@
 
 namespace tvg {
 
+// fp64 reciprocal / division / square root to ~1 ulp without the IEEE slow paths of the built-in operators (each of
+// those is 25-40 instructions with branches): MUFU seed (rcp.approx.ftz.f64, >= 20 bits) + two Newton steps.  Used
+// where a last-bit difference is immaterial: Jacobi rotation parameters, Householder reflectors, normalisations.
+// Denormal arguments are flushed (1 / denormal = inf); every caller guards the divisor.
+__device__ __forceinline__ double fast_rcp(double x) {
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+    r = fma(r, fma(-x, r, 1.0), r);
+    return fma(r, fma(-x, r, 1.0), r);
+}
+__device__ __forceinline__ double fast_div(double a, double b) { return a * fast_rcp(b); }
+__device__ __forceinline__ double fast_sqrt(double x) { return (x > 0.0) ? x * rsqrt(x) : 0.0; }
+
 // One-sided Jacobi SVD:  A V = G  with the columns of G mutually orthogonal on exit.
 // G[c][r] holds column c of A (length MR), V[c][r] column c of V (starts as identity).
 // Fully unrolled over column pairs so every index is static (register resident).
@@ -30,8 +43,8 @@ __device__ __forceinline__ void jacobi_onesided(double (&G)[N][MR], double (&V)[
                 }
                 if (gamma * gamma > 1e-26 * alpha * beta && gamma != 0.0) {
                     rotated = true;
-                    const double zeta = (beta - alpha) / (2.0 * gamma);
-                    const double t = copysign(1.0, zeta) / (fabs(zeta) + sqrt(fma(zeta, zeta, 1.0)));
+                    const double zeta = fast_div(beta - alpha, 2.0 * gamma);
+                    const double t = copysign(fast_rcp(fabs(zeta) + fast_sqrt(fma(zeta, zeta, 1.0))), zeta);
                     const double c = rsqrt(fma(t, t, 1.0));
                     const double s = c * t;
 #pragma unroll
@@ -71,7 +84,7 @@ __device__ __forceinline__ void svd3(const double (&M)[9], double (&u)[3][3], do
     jacobi_onesided<3, 3>(G, V, 30);
     double n[3];
 #pragma unroll
-    for (int c = 0; c < 3; ++c) n[c] = sqrt(G[c][0] * G[c][0] + G[c][1] * G[c][1] + G[c][2] * G[c][2]);
+    for (int c = 0; c < 3; ++c) n[c] = fast_sqrt(G[c][0] * G[c][0] + G[c][1] * G[c][1] + G[c][2] * G[c][2]);
     // order: i0 = largest, i1 = second (static-index selection via swaps)
 #define TVG_SWAPCOL(a, b)                                                            \
     {                                                                                \
@@ -87,7 +100,7 @@ __device__ __forceinline__ void svd3(const double (&M)[9], double (&u)[3][3], do
 #undef TVG_SWAPCOL
 #pragma unroll
     for (int c = 0; c < 2; ++c) {
-        const double inv = 1.0 / n[c];
+        const double inv = fast_rcp(n[c]);
 #pragma unroll
         for (int r = 0; r < 3; ++r) {
             u[c][r] = G[c][r] * inv;
@@ -139,10 +152,10 @@ __device__ __forceinline__ void null_vector_8x9(double (&a)[8][9], double (&n)[9
         double sig = 0.0;
 #pragma unroll
         for (int i = k; i < 9; ++i) sig = fma(a[k][i], a[k][i], sig);
-        const double nrm = sqrt(sig);
+        const double nrm = fast_sqrt(sig);
         const double alpha = (a[k][k] >= 0.0) ? -nrm : nrm;
         const double vtv = 2.0 * (sig - alpha * a[k][k]);
-        beta[k] = (vtv > 0.0) ? 2.0 / vtv : 0.0;
+        beta[k] = (vtv > 0.0) ? 2.0 * fast_rcp(vtv) : 0.0;
         a[k][k] -= alpha;
 #pragma unroll
         for (int j = k + 1; j < 8; ++j) {

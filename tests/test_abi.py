@@ -50,11 +50,31 @@ def test_ctypes_structs_mirror_the_c_structs(lib_built, tmp_path):
     assert vals[4] == _lib.PairsIO.kinv.offset and vals[5] == _lib.PairsIO.pose_votes.offset
 
 
-def test_sass_shows_tma_and_integer_pipe(lib_built):
-    """The matcher is LOP3 + POPC fed by TMA bulk copies (UBLKCP); no tensor-core reshaping."""
+def test_sass_shows_the_blackwell_units(lib_built):
+    """SASS evidence of what the kernels run on: the tensor-core matcher issues tcgen05.mma kind::f8f6f4 (UTCQMMA)
+    with accumulators read back from tensor memory (LDTM), every staged tile arrives by a bulk async copy (UBLKCP:
+    the 1-D bulk form -- the tiles are contiguous, no tensor map) signalled on mbarriers (SYNCS), the integer-pipe
+    matcher is LOP3 + POPC, and the scoring kernel counts with PRMT."""
     sass = subprocess.run(["cuobjdump", "-sass", lib_built], capture_output=True, text=True).stdout
-    assert "UBLKCP" in sass and "POPC" in sass and "LOP3" in sass and "SYNCS" in sass
+    for mnemonic in ("UTCQMMA", "LDTM", "UBLKCP", "SYNCS", "POPC", "LOP3", "PRMT", "DFMA"):
+        assert mnemonic in sass, mnemonic
+    assert "HMMA" not in sass and "HGMMA" not in sass          # no legacy tensor path
     assert "sm_100a" in sass or "SM100a" in sass or "EF_CUDA_SM100" in sass
+
+
+def test_huge_pair_struct_layout_matches_the_header(tmp_path):
+    import ctypes
+    from openwork_b200 import _lib
+    prog = tmp_path / "hp.c"
+    prog.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "tvg_b200.h"\n'
+                    'int main(void){printf("%zu %zu %zu %zu %d\\n", sizeof(tvg_huge_pair_io), offsetof(tvg_huge_pair_io, kinv),'
+                    ' offsetof(tvg_huge_pair_io, counts), offsetof(tvg_huge_pair_io, status), TVG_COMM_ID_BYTES); return 0;}\n')
+    exe = tmp_path / "hp"
+    subprocess.run(["gcc", "-I", os.path.join(ROOT, "include"), str(prog), "-o", str(exe)], check=True)
+    vals = [int(v) for v in subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.split()]
+    assert vals[0] == ctypes.sizeof(_lib.HugePairIO)
+    assert vals[1] == _lib.HugePairIO.kinv.offset and vals[2] == _lib.HugePairIO.counts.offset
+    assert vals[3] == _lib.HugePairIO.status.offset and vals[4] == _lib.COMM_ID_BYTES
 
 
 def test_product_never_imports_the_oracle():

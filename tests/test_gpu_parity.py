@@ -339,6 +339,35 @@ def test_triangulate_matches_reference(ops):
     assert np.array_equal(good.cpu().numpy()[safe], gr[safe])
 
 
+def test_triangulate_points_without_parallax_take_the_jacobi_path(ops):
+    """The fast solve (adjugate + repeated squaring) hands points it cannot separate to the Jacobi SVD kernel: with
+    identical poses and identical observations the 4x4 system has rank 2 (no unique answer, also for LAPACK), so
+    only A X = 0 can be asked of those; ordinary points in the same call must still equal the reference's."""
+    src, dst, (lk, ck, i1, i2) = _pair_correspondences(1024, 23)
+    samples = synth.sample_table(len(src), 128, 3)
+    ref = tv.ransac_essential(src, dst, samples, THR)
+    inl = ref["mask"]
+    pose0 = np.eye(4)
+    pose1 = tv.extract_Rt(ref["E"]) @ pose0
+    p1, p2 = lk[i2][inl], ck[i1][inl]
+    Xr = tv.triangulate(p1, p2, pose0, pose1, K)
+    X = ops.triangulate(p1, p2, pose0, pose1, K).cpu().numpy()
+    rel = np.linalg.norm(X[:, :3] - Xr[:, :3], axis=1) / np.maximum(np.linalg.norm(Xr[:, :3], axis=1), 1e-12)
+    assert rel.max() < X_TOL
+    # the same observations in both views, same pose: rank-2 systems
+    Xd = ops.triangulate(p1, p1, pose0, pose0, K).cpu().numpy()
+    n1 = tv.normalize(K, p1)
+    P = np.linalg.inv(pose0)
+    fin = np.isfinite(Xd).all(axis=1)
+    assert fin.mean() > 0.5
+    for x, (u, v) in zip(Xd[fin][:200], n1[fin][:200]):
+        A = np.stack([u * P[2] - P[0], v * P[2] - P[1], u * P[2] - P[0], v * P[2] - P[1]])
+        assert np.linalg.norm(A @ x) < 1e-9 * max(np.linalg.norm(x), 1.0)
+    # and the next ordinary call is unaffected (the fallback counter was reset)
+    X2 = ops.triangulate(p1, p2, pose0, pose1, K).cpu().numpy()
+    assert np.array_equal(X2, X)
+
+
 def test_cheirality_votes_match_oracle(ops):
     src, dst, _ = _pair_correspondences(1200, 31)
     samples = synth.sample_table(len(src), 128, 3)
@@ -515,7 +544,16 @@ def test_config_c3_keyframe_pair_8k_4096_hypotheses(ops):
     rc, gc = ref["ransac"]["counts"], out["counts"][0]
     ok = (cond > 1e-7) & (rc >= 0)
     assert ok.mean() > 0.95
-    assert (gc[ok] == rc[ok]).mean() > 0.98 and np.abs(gc[ok] - rc[ok]).max() <= 8
+    assert (gc[ok] == rc[ok]).mean() > 0.98
+    # the north star's bound, per hypothesis: the GPU count may differ from the oracle's only by correspondences
+    # whose residual lies within 1e-5 of the threshold (oracle model of the same 8 samples)
+    for h in np.flatnonzero(ok):
+        if gc[h] == rc[h]:
+            continue
+        r = np.abs(tv.essential_residuals(tv.essential_estimate(src[samples[h]], dst[samples[h]]), src, dst))
+        band = np.abs(r - THR) < BAND
+        lo, hi = rc[h] - int(np.sum(band & (r < THR))), rc[h] + int(np.sum(band & (r >= THR)))
+        assert lo <= gc[h] <= hi, (h, gc[h], rc[h], lo, hi)
     assert np.array_equal(out["mask"][0, :M].astype(bool), ref["inliers"])
     assert _fro_diff(out["E"][0], ref["E"]) < E_TOL
     np.testing.assert_allclose(out["Rt"][0], ref["Rt"], atol=1e-6)

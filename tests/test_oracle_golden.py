@@ -142,6 +142,46 @@ def test_essential_estimate_on_closed_form_scene():
     assert abs(sv[0] - sv[1]) < 1e-12 * sv[0] and sv[2] < 1e-12 * sv[0]
 
 
+def _dlt_fundamental(src, dst):
+    """The oracle's 8-point DLT up to (not including) the (s,s,0) step: T_d^T . null(A) . T_s."""
+    Ts, s = tv.center_and_normalize_points(src)
+    Td, d = tv.center_and_normalize_points(dst)
+    A = np.column_stack([d[:, 0] * s[:, 0], d[:, 0] * s[:, 1], d[:, 0], d[:, 1] * s[:, 0], d[:, 1] * s[:, 1],
+                         d[:, 1], s[:, 0], s[:, 1], np.ones(len(s))])
+    return Td.T @ np.linalg.svd(A)[2][-1].reshape(3, 3) @ Ts
+
+
+def _unit(F):
+    return F / np.linalg.norm(F)
+
+
+def test_minimal_dlt_null_vector_matches_cv2_8point():
+    """Independent (importable) check of essential_estimate's DLT stage -- the part skimage and OpenCV must agree on.
+    For exactly 8 correspondences the null vector of the 8x9 system does not depend on the coordinate normalisation,
+    so OpenCV's own normalised 8-point algorithm (cv2.findFundamentalMat(FM_8POINT): different normalisation,
+    eigen-solve of A^T A instead of an SVD of A) must return the same matrix wherever its rank-2 step changes
+    nothing, i.e. on exact correspondences; with noise the two differ only by that step (|sigma_3| of the null
+    vector), and both annihilate the 8 epipolar constraints before it."""
+    import cv2
+    for seed in range(6):
+        x1, x2, E_true, *_ = _closed_form_scene(8, 100 + seed)
+        F_cv, _ = cv2.findFundamentalMat(x1, x2, cv2.FM_8POINT)
+        F = _dlt_fundamental(x1, x2)
+        a, b, c = _unit(F), _unit(F_cv), _unit(E_true)
+        # oracle DLT == OpenCV (which solves the squared system A^T A: ~1e-6 is its own accuracy) == the true E
+        assert min(np.linalg.norm(a - b), np.linalg.norm(a + b)) < 1e-5, seed
+        assert min(np.linalg.norm(a - c), np.linalg.norm(a + c)) < 1e-8, seed
+    for seed in range(6):
+        x1, x2, *_ = _closed_form_scene(8, 200 + seed, noise=1e-4)
+        F = _dlt_fundamental(x1, x2)
+        F_cv, _ = cv2.findFundamentalMat(x1, x2, cv2.FM_8POINT)
+        x1h, x2h = np.column_stack([x1, np.ones(8)]), np.column_stack([x2, np.ones(8)])
+        assert np.abs(np.sum(x2h * (x1h @ _unit(F).T), axis=1)).max() < 1e-12       # exact null vector (x'^T F x = 0)
+        sv = np.linalg.svd(_unit(F), compute_uv=False)
+        a, b = _unit(F), _unit(F_cv)
+        assert min(np.linalg.norm(a - b), np.linalg.norm(a + b)) < 20 * sv[2] + 1e-5, (seed, sv)
+
+
 def test_residual_squared_is_cv2_sampson_distance():
     import cv2
     x1, x2, E_true, *_ = _closed_form_scene(50, 1, noise=0.01)
