@@ -280,6 +280,11 @@ TVG_API int tvg_pairs_host_submit(tvg_ctx* ctx, const tvg_pairs_io* io, int fram
                           long long* bytes_d2h, void* stream);
 TVG_API int tvg_pairs_host_wait(tvg_ctx* ctx);
 
+/* Measurement aid (not on the path): the e4m3 tensor-core peak of this device in TFLOP/s, from `iters` rounds of 8
+ * back-to-back tcgen05.mma kind::f8f6f4 (M=128, N=256, K=32, f16 accumulate) per SM with resident operands; best of 3.
+ * bench.py uses it as the roofline denominator of the tensor-core matcher. */
+TVG_API int tvg_measure_fp8_peak(tvg_ctx* ctx, int iters, double* tflops, double* ms);
+
 /* ---- multi-GPU (one process per GPU) ---------------------------------------------------------------------------
  * An NCCL communicator bound to a context ("context create/destroy for workspace + NCCL communicator").
  * Rank 0 calls tvg_comm_unique_id and hands the 128 bytes to the other ranks over any host channel (the Python

@@ -99,6 +99,7 @@ SIGNATURES = {
     "tvg_pairs_host_submit": (C.c_int, [c_vp, C.POINTER(PairsIO), C.c_int, C.POINTER(C.c_longlong),
                                         C.POINTER(C.c_longlong), c_vp]),
     "tvg_pairs_host_wait": (C.c_int, [c_vp]),
+    "tvg_measure_fp8_peak": (C.c_int, [c_vp, C.c_int, c_f64p, c_f64p]),
     "tvg_comm_unique_id": (C.c_int, [c_vp]),
     "tvg_comm_init": (C.c_int, [c_vp, c_vp, C.c_int, C.c_int]),
     "tvg_comm_destroy": (C.c_int, [c_vp]),
@@ -189,6 +190,12 @@ class Context:
 
     def set_matcher_l2_budget(self, nbytes=0):
         check(self.lib.tvg_set_matcher_l2_budget(self.handle, int(nbytes)), "tvg_set_matcher_l2_budget")
+
+    def measure_fp8_peak(self, iters=20000):
+        """Measured e4m3 tcgen05.mma peak of this device: (TFLOP/s, ms of the timed launch)."""
+        t, ms = C.c_double(0), C.c_double(0)
+        check(self.lib.tvg_measure_fp8_peak(self.handle, int(iters), C.byref(t), C.byref(ms)), "tvg_measure_fp8_peak")
+        return t.value, ms.value
 
     def comm_init(self, id_bytes, rank, world):
         """Bind an NCCL communicator to this context (collective over all ranks; id from :func:`comm_unique_id`)."""

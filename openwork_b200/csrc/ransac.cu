@@ -115,7 +115,7 @@ __global__ void __launch_bounds__(FIT_THREADS) ransac_fit_kernel(const RansacPar
             }
             double n[9], En[9];
             null_vector_8x9(a, n);
-            essential_project(n, En);
+            if (!essential_project_fast(n, En)) essential_project(n, En);
             essential_denormalise(En, ss, csx, csy, sd, cdx, cdy, E);
 #pragma unroll
             for (int i = 0; i < 9; ++i) ok = ok && isfinite(E[i]);
