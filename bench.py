@@ -239,7 +239,7 @@ def single_pair_latency(ops, ctx, K, n, H, dev, reps=30):
     knn_us = timed(knn, reps)
     ctx.set_matcher_config(4, 11, 6)
     knn_int_us = timed(knn, reps)
-    ctx.set_matcher_config(4, 16, 6)
+    ctx.set_matcher_config(4, 17, 6)
     knn_tc_us = timed(knn, reps)
     ctx.set_matcher_config()
     return {"matcher_us_int_pipe": knn_int_us, "matcher_us_tensor": knn_tc_us, "kpts": n, "hypotheses": H, "matches": int(out["m_count"][0]), "inliers": int(out["n_inl"][0]),
@@ -515,7 +515,7 @@ def run_ours(args):
     knn_ms = k0.elapsed_time(k1) / reps
     # the tensor-core matcher's L2-resident mode (sub-batches whose e4m3 expansion never leaves L2)
     knn_l2_ms = None
-    if args.knn_variant in (None, -1, 16):
+    if args.knn_variant == 16:
         ctx.set_matcher_l2_budget(40 << 20)
         for _ in range(2):
             knn()
@@ -675,7 +675,7 @@ def run_ours(args):
     popc_peak = 2.0 * n_sm * peaks.get("sm_max_mhz", 1965.0) * 1e6 / 1e9      # 8 POPC/cmp at 16 lanes/clk/SM
     alg_bytes = P * (2 * N_KPTS * 32 + N_KPTS * 17)                           # descriptors in, idx+dist+keep out
     hbm_gbs = alg_bytes / (knn_ms / 1e3) / 1e9
-    tensor_path = args.knn_variant in (None, -1, 16)
+    tensor_path = args.knn_variant in (None, -1, 16, 17)
     gcmp_int = cmp_per_launch / (knn_int_ms / 1e3) / 1e9
     matcher_int = {
         "kernel": "knn2_kernel (LOP3+POPC, variant 11), timed alone on the same batch", "gcmp_s": gcmp_int,
@@ -692,8 +692,9 @@ def run_ours(args):
         bf16 = peaks.get("bf16_tflops", 2250.0)
         fp8_peak, fp8_ms = ctx.measure_fp8_peak()
         roofline = {
-            "kernel": "knn2_tc_kernel (tcgen05.mma kind::f8f6f4, e4m3 +-1 operands, f16 accumulate, TMEM top-2 "
-                      "epilogue) + unpack_train_kernel, timed together",
+            "kernel": "knn2_tc2_kernel (CTA pairs: tcgen05.mma.cta_group::2 kind::f8f6f4, e4m3 operands expanded inside "
+                      "the kernel, f16 accumulate, TMEM top-2 epilogue)" if args.knn_variant != 16 else
+                      "knn2_tc_kernel (single-CTA tcgen05.mma) + unpack_train_kernel, timed together",
             "bound": "tensor", "achieved": tflops, "peak": fp8_peak, "unit": "TFLOP/s", "frac": tflops / fp8_peak,
             "peak_note": "measured live on this GPU: %.0f TF/s of e4m3 tcgen05.mma (M=128, N=256, K=32, f16 accumulate, "
                          "operands resident in shared memory, %.1f ms burst; tools/microbench/fp8_mma_peak.cu) -- nominal "
@@ -702,9 +703,12 @@ def run_ours(args):
             "ms_per_launch": knn_ms, "cmp_per_launch": cmp_per_launch, "gcmp_s": gcmp_s,
             "x_int32_popc_peak": gcmp_s / popc_peak, "x_measured_bf16_peak": tflops / bf16, "sm_mhz_during_run": f_mhz,
             # dram bytes of knn2_tc_kernel + unpack_train_kernel at P=1024 (profiles/r1_tensor_matcher_dram_traffic.md)
-            "traffic": TC_TRAFFIC_BYTES_P1024 * P / 1024 if TC_TRAFFIC_BYTES_P1024 else None,
-            "traffic_note": "7x the algorithmic bytes: the e4m3 expansion of the train side (512 KB per pair) is written "
-                            "and read back once; 20 % of HBM peak, the kernel is tensor-pipe / shared-memory bound",
+            # dram__bytes_read.sum + dram__bytes_write.sum at P=1024 from one ncu --set full capture
+            "traffic": (TC2_TRAFFIC_BYTES_P1024 if args.knn_variant != 16 else TC_TRAFFIC_BYTES_P1024) * P / 1024,
+            "traffic_note": ("0.93 x the algorithmic bytes (profiles/r2_kernels_matcher_tc2.md): the train rows are expanded "
+                             "inside the kernel; part of the re-read descriptors hit in L2") if args.knn_variant != 16 else
+                            ("7x the algorithmic bytes: the e4m3 expansion of the train side (512 KB per pair) is written "
+                             "and read back once"),
             "l2_resident_mode": {"ms_per_launch": knn_l2_ms, "gcmp_s": cmp_per_launch / (knn_l2_ms / 1e3) / 1e9,
                                  "traffic": TC_TRAFFIC_L2MODE_BYTES_P1024 * P / 1024,
                                  "note": "tvg_set_matcher_l2_budget(40 MiB): sub-batches whose expansion stays in L2; DRAM "
@@ -781,7 +785,7 @@ def run_ours(args):
                                "triangulate inliers", "pairs_per_step_per_gpu": P, "kpts": N_KPTS, "hypotheses": N_HYP,
                    "l2_policy": "inputs larger than L2 (%.0f MB of descriptors+keypoints per step)" %
                                 ((des_h.nbytes + kps_h.nbytes) / 1e6),
-                   "matcher": {"variant": "auto -> 16 (tensor cores) for this batch" if args.knn_variant is None
+                   "matcher": {"variant": "auto -> 17 (tensor cores, CTA pairs) for this batch" if args.knn_variant is None
                                else args.knn_variant, "r": args.knn_r, "ctas_per_sm": args.knn_ctas}},
         "hamming_gcmp_s": gcmp_s * world, "clocks": clocks, "gpu_launches": int(launches),
         "e2e": {"value": e2e_value, "unit": "pairs/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
@@ -811,6 +815,7 @@ def run_ours(args):
 # dram__bytes_read.sum + dram__bytes_write.sum of knn2_tc_kernel + unpack_train_kernel at P = 1024 (ncu --set full)
 TC_TRAFFIC_BYTES_P1024 = 671.3e6 + 571.7e6        # default mode, ncu --cache-control none (profiles/r1_tensor_matcher_dram_traffic.md)
 TC_TRAFFIC_L2MODE_BYTES_P1024 = 133.9e6 + 39.4e6   # L2-resident mode, 40 MiB budget
+TC2_TRAFFIC_BYTES_P1024 = 134.35e6 + 23.09e6       # CTA-pair kernel (variant 17), profiles/r2_kernels_matcher_tc2.md
 
 
 def main():

@@ -43,14 +43,16 @@ TVG_API int tvg_abi_version(void);
 /* Number of CUDA kernels this library has launched through `ctx` since creation (bench.py: gpu_launches). */
 TVG_API long long tvg_launch_count(const tvg_ctx* ctx);
 /* Matcher tuning.  variant -1 (the default state) = automatic: calls with >= 16 Mi descriptor comparisons run on
- * the tensor cores (variant 16: e4m3 +-1 operands, tcgen05.mma, exact f16 dot products, top-2 in the TMEM
- * epilogue), smaller calls on the integer pipe.  Integer-pipe variants: queries per thread r in {2,4,8}; popcount
+ * the tensor cores (variant 17: e4m3 +-1 / -+0.5 operands, tcgen05.mma.cta_group::2 over CTA pairs, train rows expanded
+ * inside the kernel, exact f16 accumulators holding 1024 + hamming, top-2 in the TMEM epilogue), smaller calls on the
+ * integer pipe.  Variant 16 = the single-CTA tensor-core form with a separate operand-expansion kernel (round 1).
+ * Integer-pipe variants: queries per thread r in {2,4,8}; popcount
  * variant 0 = 8xPOPC, 1 = Harley-Seal 4xPOPC, 2 = 5xPOPC, 3 = Harley-Seal with query/train-shared XOR combos
  * (14 LOP3 + 4 POPC); +4 (variants 5, 7) = lazy top-2 insertion, +8 (variants 9, 11) = two queries' chunk-local
  * 16-bit keys packed per register (VIMNMX.U16x2 top-2 updates); ctas_per_sm sizes the split-Nt grid.
  * Results are bit-identical for every setting. */
 TVG_API int tvg_set_matcher_config(tvg_ctx* ctx, int r, int variant, int ctas_per_sm);
-/* Tensor-core matcher only.  bytes = 0 (default): the e4m3 expansion of all train frames of a call is written once and
+/* Tensor-core matcher variant 16 only.  bytes = 0 (default): the e4m3 expansion of all train frames of a call is written once and
  * read back (fastest; 7x the algorithmic DRAM traffic, 20 % of HBM peak).  bytes > 0: the call is processed in
  * sub-batches whose expansion fits in `bytes` of L2 (40 MiB measured: DRAM traffic = the algorithmic bytes, +8 % time). */
 TVG_API int tvg_set_matcher_l2_budget(tvg_ctx* ctx, long long bytes);

@@ -88,8 +88,8 @@ int tvg_set_matcher_config(tvg_ctx* ctx, int r, int variant, int ctas_per_sm) {
         ctx->knn_ctas_per_sm = ctas_per_sm;
         return 0;
     }
-    if (!(r == 2 || r == 4 || r == 8) || !((variant >= 0 && variant <= 3) || variant == 5 || variant == 7 || variant == 9 || variant == 11 || variant == 16) || ctas_per_sm < 1 || ctas_per_sm > 16)
-        return fail(-2, "tvg_set_matcher_config: r in {2,4,8}, variant in {0,1,2,3,5,7,9,11,16}, ctas_per_sm in [1,16]");
+    if (!(r == 2 || r == 4 || r == 8) || !((variant >= 0 && variant <= 3) || variant == 5 || variant == 7 || variant == 9 || variant == 11 || variant == 16 || variant == 17) || ctas_per_sm < 1 || ctas_per_sm > 16)
+        return fail(-2, "tvg_set_matcher_config: r in {2,4,8}, variant in {0,1,2,3,5,7,9,11,16,17}, ctas_per_sm in [1,16]");
     ctx->knn_auto = false;
     ctx->knn_r = r;
     ctx->knn_variant = variant;
@@ -136,7 +136,20 @@ int tvg_knn2_hamming256(tvg_ctx* ctx, const uint8_t* q_des, const uint8_t* t_des
     // Tensor-core path (variant 16): e4m3 +-1 operands, exact f16 dot products, same results.  Chosen automatically
     // once the call holds enough comparisons to amortise the operand expansion (a single 2k x 2k pair stays on the
     // split integer-pipe kernel, which has the lower latency).
-    const bool use_tc = ctx->knn_auto ? (double)batch * q_rows_tc * t_rows_tc >= (double)TVG_TC_MIN_CMP : ctx->knn_variant == 16;
+    // Tensor-core paths, same results: variant 17 = CTA-pair form (tcgen05.mma.cta_group::2, train rows expanded inside
+    // the kernel, offset folded into a ninth MMA) -- the automatic choice once the call holds enough comparisons
+    // to amortise the operand expansion (a single 2k x 2k pair stays on the split integer-pipe kernel, which has the
+    // lower latency); variant 16 = the single-CTA form with a separate unpack kernel (round 1).
+    const bool big = (double)batch * q_rows_tc * t_rows_tc >= (double)TVG_TC_MIN_CMP;
+    const bool use_tc = !ctx->knn_auto && ctx->knn_variant == 16;
+    if (ctx->knn_auto ? big : ctx->knn_variant == 17) {
+        const int s2 = tvg::knn2_tc2_splits(batch, q_rows_tc, n_max, ctx->sm_count);
+        if (s2 > 1) TVG_GET(ctx, S_PARTIAL, (size_t)batch * n_max * s2 * sizeof(uint2), p.partial, uint2*);
+        int nl = 0;
+        TVG_CUDA(tvg::launch_knn2_tc2(p, batch, q_rows_tc, ctx->sm_count, &nl, (cudaStream_t)stream));
+        ctx->launches += nl;
+        return 0;
+    }
     if (use_tc) {
         uint8_t* ws = nullptr;
         TVG_GET(ctx, S_KNN_TC, tvg::knn2_tc_workspace_bytes(batch, n_max, ctx->knn_tc_l2_budget), ws, uint8_t*);

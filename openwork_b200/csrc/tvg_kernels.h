@@ -33,6 +33,10 @@ int knn2_tc_splits(int batch, int q_rows, int n_max, int sm_count);
 cudaError_t launch_knn2_tc(const KnnParams& p, int batch, int q_rows, uint8_t* workspace, int sm_count, size_t l2_budget,
                            int* launches, cudaStream_t stream);
 
+// CTA-pair tensor-core matcher (hamming_tc2.cu): tcgen05.mma.cta_group::2, train rows expanded inside the kernel (no workspace)
+int knn2_tc2_splits(int batch, int q_rows, int n_max, int sm_count);
+cudaError_t launch_knn2_tc2(const KnnParams& p, int batch, int q_rows, int sm_count, int* launches, cudaStream_t stream);
+
 // ---------------------------------------------------------------- ratio compaction (compact.cu)
 struct CompactParams {
     const uint8_t* keep;       // [batch][n_max]

@@ -35,7 +35,7 @@ def _fro_diff(A, B):
 # ------------------------------------------------------------------------------ matcher
 @pytest.mark.parametrize("nq,nt", [(1, 2), (5, 1), (7, 3), (33, 129), (500, 700), (2048, 2048), (1000, 4099),
                                    (4100, 257)])
-@pytest.mark.parametrize("variant", [-1, 11, 16])
+@pytest.mark.parametrize("variant", [-1, 11, 16, 17])
 def test_knn2_bit_exact(ops, nq, nt, variant):
     ops.context(0).set_matcher_config(4, variant, 6)
     rng = np.random.default_rng(nq * 10007 + nt)
@@ -55,7 +55,7 @@ def test_knn2_bit_exact(ops, nq, nt, variant):
     assert np.array_equal(idx.cpu().numpy(), ni) and np.array_equal(dist.cpu().numpy(), nd)
 
 
-@pytest.mark.parametrize("variant", [11, 16])
+@pytest.mark.parametrize("variant", [11, 16, 17])
 def test_knn2_all_equal_descriptors(ops, variant):
     q = np.full((300, 32), 0xA5, dtype=np.uint8)
     t = np.full((513, 32), 0xA5, dtype=np.uint8)
@@ -68,7 +68,7 @@ def test_knn2_all_equal_descriptors(ops, variant):
     assert not keep.any()           # 0 < 0.75*0 is False
 
 
-@pytest.mark.parametrize("variant", [11, 16])
+@pytest.mark.parametrize("variant", [11, 16, 17])
 def test_knn2_extreme_distances(ops, variant):
     """Distances 0, 1, 255 and 256 (complemented descriptors) and 300 identical train rows: key packing limits."""
     rng = np.random.default_rng(256)
@@ -86,7 +86,7 @@ def test_knn2_extreme_distances(ops, variant):
     assert np.array_equal(idx.cpu().numpy(), ri) and np.array_equal(dist.cpu().numpy(), rd)
 
 
-@pytest.mark.parametrize("variant", [11, 16])
+@pytest.mark.parametrize("variant", [11, 16, 17])
 def test_knn2_batched_with_empty_frames(ops, variant):
     """Frames with zero rows on either side of a pair (the persistent tensor-core kernel skips such items)."""
     F, N = 6, 600
@@ -125,7 +125,7 @@ def test_knn2_empty(ops):
                                             (2, 1, 16), (2, 2, 3), (8, 2, 2), (4, 3, 6), (2, 3, 2), (8, 3, 8),
                                             (4, 5, 6), (2, 5, 1), (8, 5, 8), (4, 7, 6), (2, 7, 16), (8, 7, 3),
                                             (4, 9, 6), (2, 9, 3), (8, 9, 8), (4, 11, 6), (2, 11, 16), (8, 11, 1),
-                                            (4, 16, 6)])
+                                            (4, 16, 6), (4, 17, 6)])
 def test_knn2_every_config_is_bit_identical(ops, r, variant, ctas):
     q, t = synth.correlated_descriptors(3000, 2500, seed=r * 100 + variant * 10 + ctas)
     t[100:200] = t[300:400]
@@ -190,7 +190,7 @@ def test_knn2_tensor_l2_resident_sub_batches(ops):
         assert (i2[b, nq:] == -7).all()
 
 
-@pytest.mark.parametrize("variant", [11, 16])
+@pytest.mark.parametrize("variant", [11, 16, 17])
 def test_knn2_batched_ragged(ops, variant):
     F, N = 5, 700
     rng = np.random.default_rng(5)
