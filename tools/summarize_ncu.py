@@ -16,7 +16,8 @@ METRICS = [
     "sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active",
     "sm__inst_executed_pipe_fp64.avg.pct_of_peak_sustained_active",
     "sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active",
-    "sm__pipe_tc_cycles_active.avg.pct_of_peak_sustained_active", "sm__inst_executed_pipe_tmem.avg.pct_of_peak_sustained_active",
+    "sm__pipe_tc_cycles_active.avg.pct_of_peak_sustained_active", "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active",
+    "smsp__average_warps_issue_stalled_dispatch_stall_per_issue_active.ratio", "sm__inst_executed_pipe_tmem.avg.pct_of_peak_sustained_active",
     "l1tex__data_pipe_tc_wavefronts_mem_shared.sum.pct_of_peak_sustained_elapsed", "lts__throughput.avg.pct_of_peak_sustained_elapsed",
     "smsp__issue_active.avg.pct_of_peak_sustained_active", "smsp__inst_executed.sum",
     "smsp__sass_thread_inst_executed_op_ffma_pred_on.sum", "smsp__sass_thread_inst_executed_op_fmul_pred_on.sum",
