@@ -203,6 +203,18 @@ TVG_API int tvg_bundle_adjust_pairs(tvg_ctx* ctx, const double* pix1, const doub
                             long long pose1_stride, double* pose2, long long pose2_stride, double* points4d,
                             int iters, double lambda0, double* cost, int32_t* accepted, void* stream);
 
+/* Sliding-window bundle adjustment over W <= 8 consecutive frames, batched over windows -- the multi-frame form of the
+ * same TODO (slam.py:267); no reference behaviour, specification = oracle/bundle_window.py.  Same Levenberg-Marquardt
+ * scheme as tvg_bundle_adjust_pairs over the poses of the cameras c >= n_fixed (n_fixed >= 1 leading cameras stay put:
+ * 1 leaves the scale gauge to the damping, 2 fixes it) and the points, points eliminated by the Schur complement
+ * (reduced camera system of size 6 (W - n_fixed)), one CTA per window, fp64, fixed-order sums.
+ * obs f64[batch][n_max][W][2] pixels of point j in camera c, vis u8[batch][n_max][W]; poses f64[batch][W][16]
+ * camera-to-world and points4d f64[batch][n_max][4] are refined in place; n_pts int32[batch] (NULL -> n);
+ * cost f64[batch][2] = initial / final; accepted int32[batch] (may be NULL). */
+TVG_API int tvg_bundle_adjust_window(tvg_ctx* ctx, const double* obs, const uint8_t* vis, int batch, int n_max, int n,
+                             const int32_t* n_pts, int W, int n_fixed, const double* kinv_host, double* poses,
+                             double* points4d, int iters, double lambda0, double* cost, int32_t* accepted, void* stream);
+
 /* Cheirality vote over the four (R, +-t) decompositions of E (north-star extra; the reference uses the
  * trace / t_z heuristics of slam.py:174-181 instead).  votes int32[batch][4], Rts f64[batch][4][16],
  * choice int32[batch].  mask may be NULL. */

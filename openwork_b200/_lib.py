@@ -88,6 +88,8 @@ SIGNATURES = {
                                  c_vp, c_vp]),
     "tvg_bundle_adjust_pairs": (C.c_int, [c_vp, c_vp, c_vp, C.c_int, C.c_int, C.c_int, c_vp, c_vp, c_vp, c_vp,
                                           C.c_longlong, c_vp, C.c_longlong, c_vp, C.c_int, C.c_double, c_vp, c_vp, c_vp]),
+    "tvg_bundle_adjust_window": (C.c_int, [c_vp, c_vp, c_vp, C.c_int, C.c_int, C.c_int, c_vp, C.c_int, C.c_int, c_vp, c_vp,
+                                           c_vp, C.c_int, C.c_double, c_vp, c_vp, c_vp]),
     "tvg_pairs_device": (C.c_int, [c_vp, C.POINTER(PairsIO), c_vp]),
     "tvg_set_host_chunk": (C.c_int, [c_vp, C.c_int]),
     "tvg_set_matcher_l2_budget": (C.c_int, [c_vp, C.c_longlong]),

@@ -15,7 +15,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT_DIR = os.path.join(HERE, "_lib")
 LIB = os.path.join(OUT_DIR, "libtvg_b200.so")
-SOURCES = ["hamming_knn2.cu", "hamming_tc.cu", "hamming_tc2.cu", "compact.cu", "ransac.cu", "ransac_score.cu", "pose_tri.cu", "bundle.cu",
+SOURCES = ["hamming_knn2.cu", "hamming_tc.cu", "hamming_tc2.cu", "compact.cu", "ransac.cu", "ransac_score.cu", "pose_tri.cu", "bundle.cu", "bundle_window.cu",
            "frontend.cu", "c_api.cu", "c_api_dist.cu", "microbench.cu"]
 # per-source extra flags: the scoring kernel's instruction order is chosen by hand for the register file, and
 # ptxas keeps the source order only at -O1 (see csrc/ransac_score.cu)

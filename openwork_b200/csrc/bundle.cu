@@ -6,35 +6,14 @@
 //   a fixed number of iterations, a step accepted iff the cost decreases (lambda /= 10, else *= 10).
 // One CTA per pair; a thread owns points j = tid, tid + 256, ...; all arithmetic fp64; the 6x6 reduced camera system
 // is assembled with a fixed-order block reduction (deterministic) and solved by thread 0.
-#include "tvg_common.cuh"
+#include "bundle_common.cuh"
 #include "tvg_kernels.h"
-#include "tvg_linalg.cuh"
 
 namespace tvg {
 namespace {
+using namespace ba;
 
-constexpr int BA_THREADS = 256;
 constexpr int BA_NRED = 54;   // U (21) + g_c (6) + sum W V^-1 W^T (21) + sum W V^-1 g_p (6)
-
-struct Cam {
-    double R[9], t[3];
-};
-
-__device__ __forceinline__ void cam_from_pose(const double* pose, Cam& c) {   // P = inv(pose), top 3x4
-    double inv[16];
-    inverse4(pose, inv);
-#pragma unroll
-    for (int r = 0; r < 3; ++r) {
-#pragma unroll
-        for (int k = 0; k < 3; ++k) c.R[r * 3 + k] = inv[r * 4 + k];
-        c.t[r] = inv[r * 4 + 3];
-    }
-}
-
-__device__ __forceinline__ void to_cam(const Cam& c, const double (&X)[3], double (&Xc)[3]) {
-#pragma unroll
-    for (int r = 0; r < 3; ++r) Xc[r] = fma(c.R[r * 3], X[0], fma(c.R[r * 3 + 1], X[1], fma(c.R[r * 3 + 2], X[2], c.t[r])));
-}
 
 // squared reprojection error of one point in both views
 __device__ __forceinline__ double point_cost(const Cam& c1, const Cam& c2, const double (&X)[3], double x1, double y1,
@@ -103,50 +82,6 @@ __device__ __forceinline__ void point_system(const double (&r)[4], const double 
     for (int a = 0; a < 6; ++a)
 #pragma unroll
         for (int k = 0; k < 3; ++k) W[a][k] = Jc[0][a] * Jp2[0][k] + Jc[1][a] * Jp2[1][k];
-}
-
-// exp([w]x) R, exp([w]x) t + v   (Rodrigues)
-__device__ void cam_update(const Cam& c, const double (&d)[6], Cam& o) {
-    const double th2 = d[0] * d[0] + d[1] * d[1] + d[2] * d[2], th = sqrt(th2);
-    double A, B;   // sin(th)/th, (1 - cos(th))/th^2
-    if (th < 1e-8) { A = 1.0 - th2 / 6.0; B = 0.5 - th2 / 24.0; }
-    else { A = sin(th) / th; B = (1.0 - cos(th)) / th2; }
-    const double K[9] = {0.0, -d[2], d[1], d[2], 0.0, -d[0], -d[1], d[0], 0.0};
-    double E[9];
-#pragma unroll
-    for (int i = 0; i < 3; ++i)
-#pragma unroll
-        for (int j = 0; j < 3; ++j) {
-            double k2 = 0.0;
-#pragma unroll
-            for (int k = 0; k < 3; ++k) k2 += K[i * 3 + k] * K[k * 3 + j];
-            E[i * 3 + j] = (i == j ? 1.0 : 0.0) + A * K[i * 3 + j] + B * k2;
-        }
-#pragma unroll
-    for (int i = 0; i < 3; ++i) {
-#pragma unroll
-        for (int j = 0; j < 3; ++j) o.R[i * 3 + j] = E[i * 3] * c.R[j] + E[i * 3 + 1] * c.R[3 + j] + E[i * 3 + 2] * c.R[6 + j];
-        o.t[i] = E[i * 3] * c.t[0] + E[i * 3 + 1] * c.t[1] + E[i * 3 + 2] * c.t[2] + d[3 + i];
-    }
-}
-
-// fixed-order block sum of NV values per thread -> s_out[NV] (same result for every launch)
-template <int NV>
-__device__ __forceinline__ void block_sum_vec(const double (&v)[NV], double (*s_part)[BA_THREADS / 32], double* s_out) {
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-#pragma unroll
-    for (int i = 0; i < NV; ++i) {
-        const double w = warp_sum_f64(v[i]);
-        if (lane == 0) s_part[i][warp] = w;
-    }
-    __syncthreads();
-    if (threadIdx.x < NV) {
-        double t = 0.0;
-#pragma unroll
-        for (int w = 0; w < BA_THREADS / 32; ++w) t += s_part[threadIdx.x][w];
-        s_out[threadIdx.x] = t;
-    }
-    __syncthreads();
 }
 
 __global__ void __launch_bounds__(BA_THREADS) bundle_pairs_kernel(const BundleParams p) {

@@ -453,6 +453,30 @@ int tvg_bundle_adjust_pairs(tvg_ctx* ctx, const double* pix1, const double* pix2
     return 0;
 }
 
+int tvg_bundle_adjust_window(tvg_ctx* ctx, const double* obs, const uint8_t* vis, int batch, int n_max, int n,
+                             const int32_t* n_pts, int W, int n_fixed, const double* kinv_host, double* poses,
+                             double* points4d, int iters, double lambda0, double* cost, int32_t* accepted, void* stream) {
+    if (!ctx) return fail(-1, "ctx is NULL");
+    if (batch < 0 || n_max < 0 || n < 0 || n > n_max || iters < 0 || !(lambda0 > 0.0))
+        return fail(-2, "tvg_bundle_adjust_window: bad sizes / iters / lambda0");
+    if (W < 2 || W > tvg::bundle_window_max_cameras() || n_fixed < 1 || n_fixed >= W)
+        return fail(-2, "tvg_bundle_adjust_window: 2 <= W <= 8 cameras, 1 <= n_fixed < W");
+    if (batch == 0) return 0;
+    if (!obs || !vis || !kinv_host || !poses || !points4d || !cost) return fail(-3, "tvg_bundle_adjust_window: NULL array");
+    if (!aligned16(obs)) return fail(-4, "tvg_bundle_adjust_window: obs must be 16-byte aligned");
+    DeviceGuard g(ctx->device);
+    ctx->cur_stream = (cudaStream_t)stream;
+    tvg::BundleWindowParams p{};
+    p.obs = obs; p.vis = vis; p.n_pts = n_pts; p.n_max = n_max; p.n = n; p.W = W; p.n_fixed = n_fixed; p.iters = iters;
+    p.lambda0 = lambda0;
+    memcpy(p.kinv, kinv_host, sizeof(p.kinv));
+    p.poses = poses; p.points4d = points4d; p.cost = cost; p.accepted = accepted;
+    TVG_GET(ctx, S_BA_TRIAL, tvg::bundle_window_scratch_doubles(batch, n_max) * sizeof(double), p.scratch, double*);
+    TVG_CUDA(tvg::launch_bundle_window(p, batch, (cudaStream_t)stream));
+    ctx->launches += 1;
+    return 0;
+}
+
 int tvg_map_accumulate(tvg_ctx* ctx, const double* points4d, const uint8_t* good, const int32_t* n_pts,
                        const int32_t* seq_off, int nseq, int n_max, long long cap, int include_origin,
                        double* map_points, int32_t* map_count, int32_t* pair_off, void* stream) {

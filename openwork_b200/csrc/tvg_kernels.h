@@ -199,6 +199,24 @@ struct BundleParams {
 };
 cudaError_t launch_bundle_pairs(const BundleParams& p, int batch, cudaStream_t stream);
 
+// ---------------------------------------------------------------- sliding-window bundle adjustment (bundle_window.cu)
+struct BundleWindowParams {
+    const double* obs;         // [batch][n_max][W][2] pixel observations of point j in camera c
+    const uint8_t* vis;        // [batch][n_max][W] visibility mask
+    const int32_t* n_pts;      // [batch] (NULL -> n)
+    int n_max, n, W, n_fixed, iters;
+    double lambda0;
+    double kinv[9];
+    double* poses;             // [batch][W][16] camera-to-world, cameras >= n_fixed refined in place
+    double* points4d;          // [batch][n_max][4], refined in place (w stays 1)
+    double* scratch;           // bundle_window_scratch_doubles(batch, n_max)
+    double* cost;              // [batch][2] initial / final cost (normalised coordinates)
+    int32_t* accepted;         // [batch] accepted steps (may be NULL)
+};
+size_t bundle_window_scratch_doubles(int batch, int n_max);
+int bundle_window_max_cameras();
+cudaError_t launch_bundle_window(const BundleWindowParams& p, int batch, cudaStream_t stream);
+
 struct MapParams {
     const double* points4d;    // [batch][n_max][4]
     const uint8_t* good;       // [batch][n_max]

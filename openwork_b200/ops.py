@@ -476,6 +476,74 @@ def bundle_adjust_pairs(pix1, pix2, pose1, pose2, points4d, K, n_pts=None, use=N
     return pose2.view(B, 4, 4), pts, cost, acc
 
 
+def bundle_adjust_window(obs, vis, poses, points4d, K, n_pts=None, n_fixed=1, iters=10, lambda0=1e-3, ctx=None):
+    """Sliding-window bundle adjustment over W <= 8 consecutive frames (the multi-frame form of the `g2o bundle
+    adjustment` TODO at slam.py:267; spec: oracle/bundle_window.py), batched over windows.
+
+    obs f64[B,N,W,2] pixels of point j in camera c, vis bool/u8[B,N,W], poses f64[B,W,4,4] camera-to-world (the
+    reference's `pose`), points4d f64[B,N,4]; the first ``n_fixed`` cameras stay put.  Returns (poses_refined,
+    points4d_refined, cost f64[B,2] = initial / final, accepted int32[B]); inputs are not modified."""
+    dev = _device_of(obs, poses, points4d)
+    obs = _dev(obs, torch.float64, dev).contiguous()
+    B, N, W = obs.shape[0], obs.shape[1], obs.shape[2]
+    v8 = _dev(vis, None, dev).to(torch.uint8).contiguous()
+    P = _dev(poses, torch.float64, dev).reshape(B, W, 16).clone()
+    pts = _dev(points4d, torch.float64, dev).reshape(B, N, 4).clone()
+    cnt = None if n_pts is None else _dev(n_pts, torch.int32, dev).contiguous()
+    kinv = np.ascontiguousarray(np.linalg.inv(np.asarray(K, dtype=np.float64)))
+    ctx = ctx or context(dev.index)
+    cost = torch.zeros((B, 2), dtype=torch.float64, device=dev)
+    acc = torch.zeros(B, dtype=torch.int32, device=dev)
+    check(ctx.lib.tvg_bundle_adjust_window(ctx.handle, _p(obs), _p(v8), B, N, N, _p(cnt), int(W), int(n_fixed),
+                                           kinv.ctypes.data_as(C.c_void_p), _p(P), _p(pts), int(iters), float(lambda0),
+                                           _p(cost), _p(acc), _stream()), "tvg_bundle_adjust_window")
+    return P.view(B, W, 4, 4), pts, cost, acc
+
+
+def window_tracks(out, kps, b0, W):
+    """Feature tracks over the W consecutive frames b0 .. b0+W-1 of ONE sequence, chained from the pair pipeline's
+    inlier matches (outputs ``qidx, tidx, inl_idx, n_inl, points4d`` of :func:`process_pairs_device` with the default
+    consecutive pairing): the inlier (t, q) of pair b links keypoint t of frame b to keypoint q of frame b+1; a track
+    is extended while its keypoint keeps being matched (when several queries claim one train keypoint the lowest
+    query wins).  Returns (obs f64[n,W,2] pixels, vis u8[n,W], points4d f64[n,4] = the triangulation of the pair that
+    started the track) as CUDA tensors -- the inputs of :func:`bundle_adjust_window`.  Host-side bookkeeping helper
+    (one small synchronisation per pair), not part of the hot path."""
+    dev = kps.device
+    N = kps.shape[1]
+    cur = torch.full((N,), -1, dtype=torch.long, device=dev)      # track id of every keypoint of the current frame
+    obs, vis, pts = [], [], []
+    n_tracks = 0
+    for c in range(W - 1):
+        b = b0 + c
+        n = int(out["n_inl"][b].item())
+        inl = out["inl_idx"][b, :n].long()
+        q, t = out["qidx"][b][inl].long(), out["tidx"][b][inl].long()
+        ts, perm = torch.sort(t, stable=True)                     # one query per train keypoint: the lowest
+        first = torch.ones_like(ts, dtype=torch.bool)
+        first[1:] = ts[1:] != ts[:-1]
+        keep = perm[first]
+        q, t, row = q[keep], t[keep], keep
+        ids = cur[t]
+        new = ids < 0
+        n_new = int(new.sum().item())
+        ids = torch.where(new, n_tracks + torch.cumsum(new.long(), 0) - 1, ids)
+        if n_new:
+            obs.append(torch.zeros((n_new, W, 2), dtype=torch.float64, device=dev))
+            vis.append(torch.zeros((n_new, W), dtype=torch.uint8, device=dev))
+            pts.append(out["points4d"][b][row[new]])
+        O, V = torch.cat(obs) if len(obs) > 1 else obs[0], torch.cat(vis) if len(vis) > 1 else vis[0]
+        obs, vis = [O], [V]
+        O[ids[new], c] = kps[b][t[new]]
+        V[ids[new], c] = 1
+        O[ids, c + 1] = kps[b + 1][q]
+        V[ids, c + 1] = 1
+        n_tracks += n_new
+        nxt = torch.full((N,), -1, dtype=torch.long, device=dev)
+        nxt[q] = ids
+        cur = nxt
+    return obs[0], vis[0], torch.cat(pts)
+
+
 def _np(x):
     return x.detach().cpu().numpy() if isinstance(x, torch.Tensor) else np.asarray(x)
 
