@@ -97,6 +97,40 @@ def test_window_oracle_reaches_a_minimum_scipy_cannot_improve():
     assert 2.0 * sp2.cost >= c1 * (1 - 1e-6)
 
 
+def test_window_tracks_chains_inlier_matches_across_frames():
+    """ops.window_tracks on hand-written matches (CPU tensors): a track is extended while its keypoint is matched
+    again, a train keypoint claimed by two queries goes to the lowest query, new tracks start where none ends."""
+    import torch
+    from openwork_b200 import ops
+    N, W = 6, 3
+    kps = torch.arange(3 * N * 2, dtype=torch.float64).reshape(3, N, 2)
+    # pair 0 (frame 0 -> 1): rows (q,t) = (0,3) (1,4) (2,4) (5,0); row 2 is an outlier; rows 1 and 3.. : inliers 0,1,3
+    # pair 1 (frame 1 -> 2): rows (q,t) = (2,0) (3,1) (4,5); all inliers.  q of pair 0 = t of pair 1 continues a track.
+    qidx = torch.tensor([[0, 1, 2, 5, 0, 0], [2, 3, 4, 0, 0, 0]], dtype=torch.int32)
+    tidx = torch.tensor([[3, 4, 4, 0, 0, 0], [0, 1, 5, 0, 0, 0]], dtype=torch.int32)
+    inl_idx = torch.tensor([[0, 1, 3, 0, 0, 0], [0, 1, 2, 0, 0, 0]], dtype=torch.int32)
+    n_inl = torch.tensor([3, 3], dtype=torch.int32)
+    pts = torch.arange(2 * N * 4, dtype=torch.float64).reshape(2, N, 4)
+    out = dict(qidx=qidx, tidx=tidx, inl_idx=inl_idx, n_inl=n_inl, points4d=pts)
+    obs, vis, p4 = ops.window_tracks(out, kps, 0, W)
+    # pair 0 sorted by train keypoint: t=0 (row 3, q=5), t=3 (row 0, q=0), t=4 (row 1, q=1) -> tracks 0, 1, 2
+    # pair 1: t=0 -> q=2 continues track 1 (frame-1 keypoint 0); t=1 -> q=3 continues track 2; t=5 -> q=4 continues 0
+    assert obs.shape == (3, W, 2) and vis.shape == (3, W)
+    assert vis.numpy().tolist() == [[1, 1, 1]] * 3
+    k = kps.numpy()
+    np.testing.assert_array_equal(obs[0].numpy(), [k[0, 0], k[1, 5], k[2, 4]])
+    np.testing.assert_array_equal(obs[1].numpy(), [k[0, 3], k[1, 0], k[2, 2]])
+    np.testing.assert_array_equal(obs[2].numpy(), [k[0, 4], k[1, 1], k[2, 3]])
+    # the 3-D start of a track is the triangulation of the pair (compacted inlier order) that started it
+    np.testing.assert_array_equal(p4.numpy(), pts[0, [2, 0, 1]].numpy())
+    # a track that is not matched again stops, and a fresh one starts on an unclaimed keypoint
+    tidx2 = tidx.clone(); tidx2[1, 2] = 2                         # frame-1 keypoint 2 carries no track
+    obs, vis, p4 = ops.window_tracks(dict(out, tidx=tidx2), kps, 0, W)
+    assert vis.numpy().tolist() == [[1, 1, 0], [1, 1, 1], [1, 1, 1], [0, 1, 1]]
+    np.testing.assert_array_equal(obs[3, 1:].numpy(), [k[1, 2], k[2, 4]])
+    np.testing.assert_array_equal(p4[3].numpy(), pts[1, 2].numpy())
+
+
 @pytest.mark.gpu
 @pytest.mark.parametrize("W,n_fixed,n", [(2, 1, 300), (5, 1, 700), (8, 2, 1500), (3, 1, 40)])
 def test_gpu_window_matches_oracle(W, n_fixed, n):
