@@ -9,8 +9,8 @@
 //   pass 0   thread = point: V = sum_c Jp^T Jp (damped), its inverse, g_p              -> per-point scratch
 //   pass a   (one per free camera) thread = point: W_a = Jc^T Jp, Y_a = W_a V^-1        -> per-point scratch;
 //            U_a = sum Jc^T Jc, g_a = sum Jc^T r, sum Y_a g_p by a fixed-order block reduction
-//   Schur    thread = entry (a, i, b, j) of the reduced camera system: S -= sum_j Y_a[i,:] . W_b[j,:] over the points
-//            in index order
+//   Schur    thread = (camera pair a <= b, point slice): the 6x6 block sum_j Y_a W_b^T over the slice's points in
+//            registers, slices folded into S in slice order
 //   solve    Gaussian elimination with partial pivoting of the 6 (W - n_fixed) system in shared memory
 //   update   thread = point: X - V^-1 (g_p + sum_a W_a^T d_a), trial cost, accept / reject
 #include "bundle_common.cuh"
@@ -187,22 +187,54 @@ __global__ void __launch_bounds__(BA_THREADS) bundle_window_kernel(const BundleW
             }
             __syncthreads();
         }
-        // ---- Schur complement: S[(a,i)][(b,j)] -= sum over the points of Y_a[i,:] . W_b[j,:]   (points in index order)
-        for (int e = tid; e < ns * ns; e += BA_THREADS) {
-            const int row = e / ns, col = e % ns;
-            if (col < row) continue;                                  // symmetric: upper triangle, mirrored below
-            const int a = row / 6, i = row % 6, bb = col / 6, jj = col % 6;
-            const double* ya = scam + (size_t)a * BW_CAM + 18 + i * 3;
-            const double* wb = scam + (size_t)bb * BW_CAM + jj * 3;
-            double sum = 0.0;
-            for (int j = 0; j < n; ++j) {
-                const size_t oj = (size_t)j * nv * BW_CAM;
-                sum = fma(ya[oj], wb[oj], fma(ya[oj + 1], wb[oj + 1], fma(ya[oj + 2], wb[oj + 2], sum)));
+        // ---- Schur complement: S[(a,.)][(b,.)] -= sum over the points of Y_a W_b^T.  Thread = (camera pair a <= b,
+        // point slice): a 6x6 block in registers, 18 + 18 contiguous doubles per point for 108 multiply-adds, only the
+        // points both cameras see; the slices are then folded into S one after the other (fixed order)
+        {
+            const int npair = nv * (nv + 1) / 2;
+            const int nslice = max(BA_THREADS / npair, 1);
+            const int pr = tid / nslice, sl = tid % nslice;
+            int a = 0, bb = 0;
+            if (pr < npair) {
+                int rest = pr;
+                while (rest >= nv - a) { rest -= nv - a; ++a; }
+                bb = a + rest;
             }
-            s_S[row][col] -= sum;
-            if (col != row) s_S[col][row] -= sum;
+            double blk[6][6];
+#pragma unroll
+            for (int i = 0; i < 6; ++i)
+#pragma unroll
+                for (int c = 0; c < 6; ++c) blk[i][c] = 0.0;
+            if (pr < npair) {
+                for (int j = sl; j < n; j += nslice) {
+                    if (!vis[(size_t)j * W + nf + a] || !vis[(size_t)j * W + nf + bb]) continue;
+                    const double* ya = scam + ((size_t)j * nv + a) * BW_CAM + 18;
+                    const double* wb = scam + ((size_t)j * nv + bb) * BW_CAM;
+                    double y[18], w[18];
+#pragma unroll
+                    for (int k = 0; k < 18; ++k) { y[k] = ya[k]; w[k] = wb[k]; }
+#pragma unroll
+                    for (int i = 0; i < 6; ++i)
+#pragma unroll
+                        for (int c = 0; c < 6; ++c)
+                            blk[i][c] = fma(y[i * 3], w[c * 3],
+                                            fma(y[i * 3 + 1], w[c * 3 + 1], fma(y[i * 3 + 2], w[c * 3 + 2], blk[i][c])));
+                }
+            }
+            for (int s = 0; s < nslice; ++s) {
+                if (pr < npair && sl == s) {
+#pragma unroll
+                    for (int i = 0; i < 6; ++i)
+#pragma unroll
+                        for (int c = 0; c < 6; ++c) {
+                            if (a == bb && c < i) continue;              // diagonal block: upper triangle, mirrored
+                            s_S[6 * a + i][6 * bb + c] -= blk[i][c];
+                            if (!(a == bb && c == i)) s_S[6 * bb + c][6 * a + i] -= blk[i][c];
+                        }
+                }
+                __syncthreads();
+            }
         }
-        __syncthreads();
         // ---- solve: Gaussian elimination with partial pivoting, all threads
         if (tid == 0) s_ok = 1;
         __syncthreads();

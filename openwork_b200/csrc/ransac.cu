@@ -971,7 +971,7 @@ __global__ void __launch_bounds__(SOLVE_WARPS * 32) ransac_solve_kernel(const Ra
         if (!conv) jacobi_eig9_warp(s_G[warp], s_V[warp], s_cs[warp], n);   // near-degenerate inlier sets
         if (lane == 0) {
             double En[9];
-            essential_project(n, En);
+            if (!essential_project_fast(n, En)) essential_project(n, En);
             essential_denormalise(En, ws[45], ws[46], ws[47], ws[48], ws[49], ws[50], E);
             bool fin = true;
 #pragma unroll

@@ -286,10 +286,91 @@ __device__ __forceinline__ double sampson_residual(const double (&E)[9], double 
     return fabs(num) / sqrt(f0 * f0 + f1 * f1 + g0 * g0 + g1 * g1);
 }
 
+// U and V of a numerically rank-two 3x3 matrix (an essential matrix: what extract_Rt is given) without iterating:
+// v2 = the largest cross product of two rows (the null vector), {p, q} an orthonormal basis of its complement, then ONE
+// exact Jacobi rotation diagonalises the 2x2 Gram matrix of M [p q]; u_i = M v_i / s_i.  Same conventions as svd3
+// (s0 >= s1, u2 = u0 x u1, v2 = v0 x v1).  ~120 fp64 operations against ~1000.  Returns false -- caller falls back to
+// svd3 -- unless |M v2| <= 1e-10 |M|_F and s1 / s0 > ~1e-4.
+__device__ __forceinline__ bool svd3_rank2(const double (&M)[9], double (&u)[3][3], double (&v)[3][3]) {
+    const double r0[3] = {M[0], M[1], M[2]}, r1[3] = {M[3], M[4], M[5]}, r2[3] = {M[6], M[7], M[8]};
+    double w[3], c1[3], c2[3];
+    cross3(r0, r1, w);
+    cross3(r0, r2, c1);
+    cross3(r1, r2, c2);
+    double nw = w[0] * w[0] + w[1] * w[1] + w[2] * w[2];
+    const double n1 = c1[0] * c1[0] + c1[1] * c1[1] + c1[2] * c1[2];
+    const double n2 = c2[0] * c2[0] + c2[1] * c2[1] + c2[2] * c2[2];
+    if (n1 > nw) { nw = n1; w[0] = c1[0]; w[1] = c1[1]; w[2] = c1[2]; }
+    if (n2 > nw) { nw = n2; w[0] = c2[0]; w[1] = c2[1]; w[2] = c2[2]; }
+    double fro2 = 0.0;
+#pragma unroll
+    for (int i = 0; i < 9; ++i) fro2 = fma(M[i], M[i], fro2);
+    if (!(nw > 1e-8 * fro2 * fro2) || !isfinite(fro2)) return false;
+    const double iw = rsqrt(nw);
+    const double z[3] = {w[0] * iw, w[1] * iw, w[2] * iw};
+    double res = 0.0;
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+        const double e = M[r * 3] * z[0] + M[r * 3 + 1] * z[1] + M[r * 3 + 2] * z[2];
+        res = fma(e, e, res);
+    }
+    if (res > 1e-20 * fro2) return false;
+    // p = e_k x z for the axis k where |z_k| is smallest (never parallel to z), q = z x p
+    const double a0 = fabs(z[0]), a1 = fabs(z[1]), a2 = fabs(z[2]);
+    double ax[3] = {0.0, 0.0, 0.0};
+    if (a0 <= a1 && a0 <= a2) ax[0] = 1.0;
+    else if (a1 <= a2) ax[1] = 1.0;
+    else ax[2] = 1.0;
+    double pv[3], qv[3];
+    cross3(ax, z, pv);
+    const double ip = rsqrt(pv[0] * pv[0] + pv[1] * pv[1] + pv[2] * pv[2]);
+    pv[0] *= ip; pv[1] *= ip; pv[2] *= ip;
+    cross3(z, pv, qv);
+    double cp[3], cq[3];
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+        cp[r] = M[r * 3] * pv[0] + M[r * 3 + 1] * pv[1] + M[r * 3 + 2] * pv[2];
+        cq[r] = M[r * 3] * qv[0] + M[r * 3 + 1] * qv[1] + M[r * 3 + 2] * qv[2];
+    }
+    const double alpha = cp[0] * cp[0] + cp[1] * cp[1] + cp[2] * cp[2];
+    const double beta = cq[0] * cq[0] + cq[1] * cq[1] + cq[2] * cq[2];
+    const double gamma = cp[0] * cq[0] + cp[1] * cq[1] + cp[2] * cq[2];
+    double c = 1.0, sn = 0.0;
+    if (gamma * gamma > 1e-32 * alpha * beta && gamma != 0.0) {
+        const double zeta = (beta - alpha) / (2.0 * gamma);
+        const double t = copysign(1.0 / (fabs(zeta) + sqrt(fma(zeta, zeta, 1.0))), zeta);
+        c = 1.0 / sqrt(fma(t, t, 1.0));
+        sn = c * t;
+    }
+    double g0[3], g1[3], v0[3], v1[3];
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+        g0[r] = c * cp[r] - sn * cq[r];
+        g1[r] = sn * cp[r] + c * cq[r];
+        v0[r] = c * pv[r] - sn * qv[r];
+        v1[r] = sn * pv[r] + c * qv[r];
+    }
+    const double m0 = g0[0] * g0[0] + g0[1] * g0[1] + g0[2] * g0[2];
+    const double m1 = g1[0] * g1[0] + g1[1] * g1[1] + g1[2] * g1[2];
+    const bool sw = m0 < m1;
+    const double i0 = 1.0 / sqrt(sw ? m1 : m0), i1 = 1.0 / sqrt(sw ? m0 : m1);
+    if (!isfinite(i0) || !isfinite(i1)) return false;
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+        u[0][r] = (sw ? g1[r] : g0[r]) * i0;
+        u[1][r] = (sw ? g0[r] : g1[r]) * i1;
+        v[0][r] = sw ? v1[r] : v0[r];
+        v[1][r] = sw ? v0[r] : v1[r];
+    }
+    cross3(u[0], u[1], u[2]);
+    cross3(v[0], v[1], v[2]);
+    return true;
+}
+
 // extract_Rt (slam.py:167-186): R = U W V^T, or U W^T V^T when trace(R) < 0; t = U[:,2] with t_z >= 0.
 __device__ __forceinline__ void extract_rt(const double (&E)[9], double (&Rt)[16]) {
     double u[3][3], s[3], v[3][3];
-    svd3(E, u, s, v);
+    if (!svd3_rank2(E, u, v)) svd3(E, u, s, v);
     // U W = [u1, -u0, u2] ; U W^T = [-u1, u0, u2]   (columns)
     double Ra[9], Rb[9];
 #pragma unroll
