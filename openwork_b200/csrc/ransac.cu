@@ -457,46 +457,65 @@ __device__ void jacobi_eig9_warp(double (*G)[9], double (*V)[9], double* cs /*[8
 
 // The same eigenvector by inverse iteration on the Cholesky factor of G + delta I (delta = 1e-13 tr G keeps the factor
 // positive when the smallest eigenvalue is numerically zero, i.e. on noise-free data; the shift does not move the
-// eigenvectors).  One thread; L lives in shared memory.  The well-separated case -- an inlier set explained by one
-// essential matrix -- converges in 3-5 solves of 90 multiply-adds; returns false (caller falls back to the Jacobi
-// sweep) when the two smallest eigenvalues are too close to separate in 40 solves or the factorisation breaks down.
-__device__ bool eig9_smallest_inverse_iteration(const double (*G)[9], double (*L)[9], double (&x)[9]) {
+// eigenvectors).  One thread, everything in registers: g = the upper triangle of G in row order (45 values, the layout
+// of refit_ws), L packed the same way by rows of the lower triangle, every index static.  The well-separated case --
+// an inlier set explained by one essential matrix -- converges in 3-10 solves of 72 multiply-adds; returns false (the
+// caller falls back to the Jacobi sweep) when the two smallest eigenvalues are too close to separate in 40 solves or
+// the factorisation breaks down.
+__device__ __forceinline__ constexpr int tri_lo(int i, int j) { return i * (i + 1) / 2 + j; }          // j <= i
+__device__ __forceinline__ constexpr int tri_up(int i, int j) { return i * 9 - i * (i - 1) / 2 + (j - i); }  // j >= i
+
+__device__ __forceinline__ bool eig9_smallest_inverse_iteration(const double (&g)[45], double (&x)[9]) {
     double tr = 0.0;
-    for (int i = 0; i < 9; ++i) tr += G[i][i];
+#pragma unroll
+    for (int i = 0; i < 9; ++i) tr += g[tri_up(i, i)];
     if (!(tr > 0.0) || !isfinite(tr)) return false;
     const double delta = 1e-13 * tr;
-    double idiag[9];
+    double L[45], idiag[9];
+    bool ok = true;
+#pragma unroll
     for (int j = 0; j < 9; ++j) {
-        double d = G[j][j] + delta;
-        for (int k = 0; k < j; ++k) d = fma(-L[j][k], L[j][k], d);
-        if (!(d > 0.0)) return false;
+        double d = g[tri_up(j, j)] + delta;
+#pragma unroll
+        for (int k = 0; k < j; ++k) d = fma(-L[tri_lo(j, k)], L[tri_lo(j, k)], d);
+        ok = ok && (d > 0.0);
         const double inv = rsqrt(d);
         idiag[j] = inv;
-        L[j][j] = d * inv;
+        L[tri_lo(j, j)] = d * inv;
+#pragma unroll
         for (int i = j + 1; i < 9; ++i) {
-            double v = G[i][j];
-            for (int k = 0; k < j; ++k) v = fma(-L[i][k], L[j][k], v);
-            L[i][j] = v * inv;
+            double v = g[tri_up(j, i)];
+#pragma unroll
+            for (int k = 0; k < j; ++k) v = fma(-L[tri_lo(i, k)], L[tri_lo(j, k)], v);
+            L[tri_lo(i, j)] = v * inv;
         }
     }
+    if (!ok) return false;
+#pragma unroll
     for (int i = 0; i < 9; ++i) x[i] = 1.0 / 3.0;
     for (int it = 0; it < 40; ++it) {
         double y[9];
+#pragma unroll
         for (int i = 0; i < 9; ++i) {            // L y = x
             double v = x[i];
-            for (int k = 0; k < i; ++k) v = fma(-L[i][k], y[k], v);
+#pragma unroll
+            for (int k = 0; k < i; ++k) v = fma(-L[tri_lo(i, k)], y[k], v);
             y[i] = v * idiag[i];
         }
+#pragma unroll
         for (int i = 8; i >= 0; --i) {           // L^T z = y   (z overwrites y)
             double v = y[i];
-            for (int k = i + 1; k < 9; ++k) v = fma(-L[k][i], y[k], v);
+#pragma unroll
+            for (int k = i + 1; k < 9; ++k) v = fma(-L[tri_lo(k, i)], y[k], v);
             y[i] = v * idiag[i];
         }
         double nn = 0.0, dot = 0.0;
+#pragma unroll
         for (int i = 0; i < 9; ++i) { nn = fma(y[i], y[i], nn); dot = fma(y[i], x[i], dot); }
         if (!(nn > 0.0) || !isfinite(nn)) return false;
         const double sc = (dot < 0.0 ? -1.0 : 1.0) * rsqrt(nn);
         double diff = 0.0;
+#pragma unroll
         for (int i = 0; i < 9; ++i) {
             const double z = y[i] * sc;
             diff = fmax(diff, fabs(z - x[i]));
@@ -554,13 +573,27 @@ __global__ void __launch_bounds__(REFIT_THREADS, 2) ransac_refit_kernel(const Ra
     const double2* dst = reinterpret_cast<const double2*>(p.dst) + ob;
     const int per = (M + REFIT_THREADS - 1) / REFIT_THREADS;
     const int lo = min(M, tid * per), hi = min(M, lo + per);
+    // (a thread owns at most REFIT_BIG_N / REFIT_THREADS = 16 consecutive rows: its inlier flags live in one word;
+    // rows are loaded four at a time so that the loads of a group are in flight together)
     int cnt = 0;
+    unsigned bits = 0u;
     double sum[4] = {0.0, 0.0, 0.0, 0.0};
-    for (int m = lo; m < hi; ++m) {
-        const double2 s = src[m], d = dst[m];
-        const bool in = sampson_residual(Eb, s.x, s.y, d.x, d.y) < p.thr;
-        p.mask[ob + m] = in ? 1 : 0;
-        if (in) { ++cnt; sum[0] += s.x; sum[1] += s.y; sum[2] += d.x; sum[3] += d.y; }
+    for (int m0 = lo; m0 < hi; m0 += 4) {
+        double2 s4[4], d4[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+            if (m0 + k < hi) { s4[k] = __ldg(src + m0 + k); d4[k] = __ldg(dst + m0 + k); }
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            if (m0 + k >= hi) break;
+            const double2 s = s4[k], d = d4[k];
+            const bool in = sampson_residual(Eb, s.x, s.y, d.x, d.y) < p.thr;
+            p.mask[ob + m0 + k] = in ? 1 : 0;
+            if (in) {
+                bits |= 1u << (m0 + k - lo);
+                ++cnt; sum[0] += s.x; sum[1] += s.y; sum[2] += d.x; sum[3] += d.y;
+            }
+        }
     }
     int incl = cnt;
 #pragma unroll
@@ -582,14 +615,32 @@ __global__ void __launch_bounds__(REFIT_THREADS, 2) ransac_refit_kernel(const Ra
         const int ft = p.pair_t ? p.pair_t[b] : b;
         const double2* kq = p.kps_q ? reinterpret_cast<const double2*>(p.kps_q) + (size_t)fq * p.n_max : nullptr;
         const double2* kt = p.kps_t ? reinterpret_cast<const double2*>(p.kps_t) + (size_t)ft * p.n_max : nullptr;
-        for (int m = lo; m < hi; ++m) {
-            if (!p.mask[ob + m]) continue;
-            p.inl_idx[ob + pos] = m;
-            if (kq) {
-                reinterpret_cast<double2*>(p.pix_curr)[ob + pos] = kq[p.qidx[ob + m]];
-                reinterpret_cast<double2*>(p.pix_last)[ob + pos] = kt[p.tidx[ob + m]];
+        for (unsigned rem = bits; rem;) {       // four inliers at a time: index loads, then gathers, then stores
+            int mm[4], qi[4], ti[4];
+            double2 a4[4], b4[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                mm[k] = rem ? lo + __ffs(rem) - 1 : -1;
+                rem &= rem - 1u;
             }
-            ++pos;
+            if (kq) {
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+                    if (mm[k] >= 0) { qi[k] = __ldg(p.qidx + ob + mm[k]); ti[k] = __ldg(p.tidx + ob + mm[k]); }
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+                    if (mm[k] >= 0) { a4[k] = __ldg(kq + qi[k]); b4[k] = __ldg(kt + ti[k]); }
+            }
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                if (mm[k] < 0) break;
+                p.inl_idx[ob + pos] = mm[k];
+                if (kq) {
+                    reinterpret_cast<double2*>(p.pix_curr)[ob + pos] = a4[k];
+                    reinterpret_cast<double2*>(p.pix_last)[ob + pos] = b4[k];
+                }
+                ++pos;
+            }
         }
     }
     if (tid == 0) {
@@ -612,11 +663,22 @@ __global__ void __launch_bounds__(REFIT_THREADS, 2) ransac_refit_kernel(const Ra
 #pragma unroll
     for (int k = 0; k < 4; ++k) c[k] = block_sum_f64<REFIT_THREADS>(sum[k], s_buf) / (double)total;
     double qs = 0.0, qd = 0.0;
-    for (int m = lo; m < hi; ++m) {
-        if (!p.mask[ob + m]) continue;
-        const double2 s = src[m], d = dst[m];
-        qs = fma(s.x - c[0], s.x - c[0], qs); qs = fma(s.y - c[1], s.y - c[1], qs);
-        qd = fma(d.x - c[2], d.x - c[2], qd); qd = fma(d.y - c[3], d.y - c[3], qd);
+    for (unsigned rem = bits; rem;) {
+        int mm[4];
+        double2 s4[4], d4[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            mm[k] = rem ? lo + __ffs(rem) - 1 : -1;
+            rem &= rem - 1u;
+            if (mm[k] >= 0) { s4[k] = __ldg(src + mm[k]); d4[k] = __ldg(dst + mm[k]); }
+        }
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            if (mm[k] < 0) break;
+            const double2 s = s4[k], d = d4[k];
+            qs = fma(s.x - c[0], s.x - c[0], qs); qs = fma(s.y - c[1], s.y - c[1], qs);
+            qd = fma(d.x - c[2], d.x - c[2], qd); qd = fma(d.y - c[3], d.y - c[3], qd);
+        }
     }
     qs = block_sum_f64<REFIT_THREADS>(qs, s_buf);
     qd = block_sum_f64<REFIT_THREADS>(qd, s_buf);
@@ -626,9 +688,13 @@ __global__ void __launch_bounds__(REFIT_THREADS, 2) ransac_refit_kernel(const Ra
     double acc[45];
 #pragma unroll
     for (int i = 0; i < 45; ++i) acc[i] = 0.0;
-    for (int m = lo; m < hi; ++m) {
-        if (!p.mask[ob + m]) continue;
-        const double2 s = src[m], d = dst[m];
+    double2 s_nx = make_double2(0.0, 0.0), d_nx = s_nx;
+    unsigned rem = bits;
+    if (rem) { const int m = lo + __ffs(rem) - 1; s_nx = __ldg(src + m); d_nx = __ldg(dst + m); }
+    while (rem) {
+        const double2 s = s_nx, d = d_nx;
+        rem &= rem - 1u;
+        if (rem) { const int m = lo + __ffs(rem) - 1; s_nx = __ldg(src + m); d_nx = __ldg(dst + m); }   // next row in flight
         const double xs = ss * s.x - ss * c[0], ys = ss * s.y - ss * c[1];
         const double xd = sd * d.x - sd * c[2], yd = sd * d.y - sd * c[3];
         const double a[9] = {xd * xs, xd * ys, xd, yd * xs, yd * ys, yd, xs, ys, 1.0};
@@ -671,6 +737,7 @@ constexpr int REFIT_BIG_N = 4096;
 constexpr int REFIT_BIG_ROWS = 2048;
 constexpr int REFIT_BIG_STRIDE = 64;    // doubles per (pair, block): [0] count, [1..4] sums, [5..6] q sums, [8..52] A^T A
 static int refit_nblk(int n_max) { return n_max > REFIT_BIG_ROWS ? (n_max + REFIT_BIG_ROWS - 1) / REFIT_BIG_ROWS : 1; }
+static_assert(REFIT_BIG_N <= 32 * REFIT_THREADS, "ransac_refit_kernel keeps a thread's inlier flags in one 32-bit word");
 int ransac_refit_big_blocks(int n_max, bool force) { return (n_max > REFIT_BIG_N || force) ? refit_nblk(n_max) : 0; }
 int ransac_refit_big_stride() { return REFIT_BIG_STRIDE; }
 
@@ -955,20 +1022,27 @@ __global__ void __launch_bounds__(SOLVE_WARPS * 32) ransac_solve_kernel(const Ra
     if (flag == 0) return;   // no model: NaNs already written
     double E[9];
     if (flag == 2) {
-        for (int t = lane; t < 45; t += 32) {
-            int i = 0, rem = t;
-            while (rem >= 9 - i) { rem -= 9 - i; ++i; }
-            const int j = i + rem;
-            const double v = ws[t];
-            s_G[warp][i][j] = v;
-            s_G[warp][j][i] = v;
-        }
-        __syncwarp();
         double n[9];
         int conv = 0;
-        if (lane == 0) conv = eig9_smallest_inverse_iteration(s_G[warp], s_V[warp], n) ? 1 : 0;
+        if (lane == 0) {
+            double g[45];
+#pragma unroll
+            for (int t = 0; t < 45; ++t) g[t] = ws[t];
+            conv = eig9_smallest_inverse_iteration(g, n) ? 1 : 0;
+        }
         conv = __shfl_sync(0xffffffffu, conv, 0);
-        if (!conv) jacobi_eig9_warp(s_G[warp], s_V[warp], s_cs[warp], n);   // near-degenerate inlier sets
+        if (!conv) {   // near-degenerate inlier sets: the warp-wide Jacobi sweep
+            for (int t = lane; t < 45; t += 32) {
+                int i = 0, rem = t;
+                while (rem >= 9 - i) { rem -= 9 - i; ++i; }
+                const int j = i + rem;
+                const double v = ws[t];
+                s_G[warp][i][j] = v;
+                s_G[warp][j][i] = v;
+            }
+            __syncwarp();
+            jacobi_eig9_warp(s_G[warp], s_V[warp], s_cs[warp], n);
+        }
         if (lane == 0) {
             double En[9];
             if (!essential_project_fast(n, En)) essential_project(n, En);
