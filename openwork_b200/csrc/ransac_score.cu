@@ -3,6 +3,7 @@
 //
 // This file is compiled with `-Xptxas -O1` (openwork_b200/build.py): at that level ptxas keeps the instruction order of
 // the source, and the order below is chosen for the register file (see score_row).
+#include <cstdlib>
 #include "tvg_common.cuh"
 #include "tvg_kernels.h"
 
@@ -21,7 +22,7 @@ constexpr int SCORE_MAX_ROWS = 32768;     // rows per work item: the packed 16-b
 //     acc - 0xFFFF0000  ==  acc + 0x10000       -> high lane += 1
 // so after <= 32768 rows  low = count, high = (band - count) mod 2^16.
 // (Measured alternatives: SHF + IADD per counter = 4 integer instructions per evaluation, round 1; packed
-// fma.rn.f32x2 over two hypotheses: FFMA2 issues at half the FFMA rate on B200, tools/microbench/fp32_pipes.cu.)
+// fma.rn.f32x2 over two hypotheses: score_row_pairs below -- same time, half the issue slots.)
 // Register-file bandwidth shapes the instruction order (measured: tools/microbench/ffma_operands.cu -- 0.46 of the
 // FFMA peak with three fresh register operands per instruction, 0.93 with two): a B200 sub-partition reads its
 // registers through two banks (even / odd index), one distinct register per bank per clock, so an FFMA whose three
@@ -107,12 +108,87 @@ __device__ __forceinline__ void score_row(const float (&e)[HPT][9], const float4
     }
 }
 
+// ---- the same evaluation on PAIRS of hypotheses: fma.rn.f32x2 (FFMA2, new with sm_100) performs the two FMAs of a
+// pair (hypothesis 2j in the low half, 2j+1 in the high half of a 64-bit register pair) in ONE instruction.  The FP32
+// pipe does not get faster -- FFMA2 occupies it for two clocks (tools/microbench/ffma2_operands.cu: 0.91-0.98 of 128
+// FMA/clk/SM with up to two fresh pair operands, 0.66 with three) -- but an evaluation needs half the issue slots, and
+// the coordinate is a SCALAR operand broadcast to both halves (`R.F32` in SASS, what ptxas makes of mov.b64 {x, x}).
+// Every FMA is the same IEEE fp32 operation as in score_row, so counts and bands are bit-identical.
+// Measured (profiles/r2_kernels.md): 1.10 ms per C2 batch, the SAME as the scalar form, with the issue slots down from
+// 88 % to 52 % and the instruction count from 1.09 G to 0.64 G -- so the scoring stage is bound by operand delivery
+// to the FP32 pipe (pipe 76 % active, warps waiting on math-pipe throttle), not by instruction issue.  Opt-in
+// (TVG_SCORE_PACKED=1); the scalar form stays the default.
+typedef unsigned long long f32x2;
+__device__ __forceinline__ f32x2 pair_of(float lo, float hi) { f32x2 r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi)); return r; }
+__device__ __forceinline__ f32x2 both(float v) { f32x2 r; asm("mov.b64 %0, {%1, %1};" : "=l"(r) : "f"(v)); return r; }
+__device__ __forceinline__ void halves(f32x2 v, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+#define TVG_FMA2(d, a, b, c) asm volatile("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c))
+
+template <int NP>
+__device__ __forceinline__ void score_row_pairs(const f32x2 (&e)[NP][9], const float4 c, float nthr2, float nband, float c1,
+                                                float k1, unsigned (&acc)[2 * NP]) {
+    const f32x2 cx = both(c.x), cy = both(c.y), cu = both(c.z), cv = both(c.w);
+    const f32x2 pc1 = both(c1), pk1 = both(k1), pnthr2 = both(nthr2);
+    f32x2 t0[NP], t1[NP], t2[NP], f0[NP], f1[NP], f2[NP], s0[NP], s1[NP], nn[NP], g0[NP], g1[NP], num[NP];
+    f32x2 den[NP], n2[NP], t[NP];
+#pragma unroll
+    for (int k = 0; k < NP; ++k) {
+        TVG_FMA2(t0[k], e[k][1], cy, e[k][2]);
+        TVG_FMA2(t1[k], e[k][4], cy, e[k][5]);
+        TVG_FMA2(t2[k], e[k][7], cy, e[k][8]);
+    }
+#pragma unroll
+    for (int k = 0; k < NP; ++k) {
+        TVG_FMA2(f0[k], e[k][0], cx, t0[k]);
+        TVG_FMA2(f1[k], e[k][3], cx, t1[k]);
+        TVG_FMA2(f2[k], e[k][6], cx, t2[k]);
+    }
+#pragma unroll
+    for (int k = 0; k < NP; ++k) {
+        TVG_FMA2(s0[k], e[k][3], cv, e[k][6]);
+        TVG_FMA2(s1[k], e[k][4], cv, e[k][7]);
+        TVG_FMA2(nn[k], f1[k], cv, f2[k]);
+    }
+#pragma unroll
+    for (int k = 0; k < NP; ++k) {
+        TVG_FMA2(g0[k], e[k][0], cu, s0[k]);
+        TVG_FMA2(g1[k], e[k][1], cu, s1[k]);
+        TVG_FMA2(num[k], f0[k], cu, nn[k]);
+    }
+#pragma unroll
+    for (int k = 0; k < NP; ++k) TVG_FMA2(den[k], g1[k], g1[k], pc1);
+#pragma unroll
+    for (int k = 0; k < NP; ++k) TVG_FMA2(n2[k], num[k], num[k], pk1);
+#pragma unroll
+    for (int k = 0; k < NP; ++k) TVG_FMA2(den[k], g0[k], g0[k], den[k]);
+#pragma unroll
+    for (int k = 0; k < NP; ++k) TVG_FMA2(den[k], f1[k], f1[k], den[k]);
+#pragma unroll
+    for (int k = 0; k < NP; ++k) TVG_FMA2(den[k], f0[k], f0[k], den[k]);
+#pragma unroll
+    for (int k = 0; k < NP; ++k) TVG_FMA2(t[k], den[k], pnthr2, n2[k]);
+#pragma unroll
+    for (int k = 0; k < NP; ++k) {
+        float ta, tb, da, db;
+        halves(t[k], ta, tb);
+        halves(den[k], da, db);
+        // |t| - band den: scalar FFMAs (the |.| is an operand modifier there; FFMA2 has none)
+        const float bta = fmaf(nband, da, fabsf(ta)), btb = fmaf(nband, db, fabsf(tb));
+        unsigned wa, wb;
+        asm("prmt.b32 %0, %1, %2, 0xFFBB;" : "=r"(wa) : "r"(__float_as_uint(ta)), "r"(__float_as_uint(bta)));
+        asm("prmt.b32 %0, %1, %2, 0xFFBB;" : "=r"(wb) : "r"(__float_as_uint(tb)), "r"(__float_as_uint(btb)));
+        acc[2 * k] -= wa;
+        acc[2 * k + 1] -= wb;
+    }
+}
+
 // Persistent CTAs pull work items from a device-side queue (atomic counter): item = (pair, row slot, block of
 // HPT * 128 hypotheses).  A thread owns HPT hypotheses (E in registers); the item's correspondences stream through a
 // two-stage shared-memory ring filled by TMA bulk copies; one broadcast LDS.128 feeds HPT evaluations.  Items whose
 // row slot lies beyond the pair's match count (known only on the device) cost one queue pop.
-template <int HPT, bool SSE>
+template <int HPT, bool SSE, bool PK>
 __global__ void __launch_bounds__(SCORE_THREADS) ransac_score_kernel(const RansacParams p, int items, int hblocks) {
+    static_assert(!(PK && SSE) && (!PK || HPT % 2 == 0), "the packed form scores pairs of hypotheses, counts only");
     extern __shared__ __align__(128) unsigned char score_smem[];
     // a stage holds SCORE_CHUNK rows + one spare row, so the row prefetch of the inner loop needs no bounds check
     float4(*corr)[SCORE_CHUNK + 1] = reinterpret_cast<float4(*)[SCORE_CHUNK + 1]>(score_smem);
@@ -152,6 +228,7 @@ __global__ void __launch_bounds__(SCORE_THREADS) ransac_score_kernel(const Ransa
             if (n > 1) issue(1);
         }
         float e[HPT][9];
+        f32x2 e2[PK ? HPT / 2 : 1][9];
         int h[HPT];
         unsigned acc[HPT];
         float sse[HPT];
@@ -162,6 +239,12 @@ __global__ void __launch_bounds__(SCORE_THREADS) ransac_score_kernel(const Ransa
             for (int i = 0; i < 9; ++i) e[k][i] = (h[k] < p.H) ? p.E32[((size_t)b * 9 + i) * p.H + h[k]] : 0.0f;
             acc[k] = 0u; sse[k] = 0.0f;
         }
+        if (PK) {
+#pragma unroll
+            for (int k = 0; k < HPT / 2; ++k)
+#pragma unroll
+                for (int i = 0; i < 9; ++i) e2[k][i] = pair_of(e[2 * k][i], e[2 * k + 1][i]);
+        }
         for (int i = 0; i < n; ++i) {
             const uint32_t gi = g + (uint32_t)i;
             mbar_wait(&bar[gi & 1u], (gi >> 1) & 1u);
@@ -171,7 +254,8 @@ __global__ void __launch_bounds__(SCORE_THREADS) ransac_score_kernel(const Ransa
 #pragma unroll(8 / HPT)
             for (int j = 0; j < rows; ++j) {
                 const float4 cn = cp[j + 1];   // next row in flight while this one is evaluated (spare row at the end)
-                score_row<HPT, SSE>(e, c, nthr2, nband, c1, k1, acc, sse);
+                if (PK) score_row_pairs<PK ? HPT / 2 : 1>(e2, c, nthr2, nband, c1, k1, reinterpret_cast<unsigned (&)[PK ? HPT : 2]>(acc));
+                else score_row<HPT, SSE>(e, c, nthr2, nband, c1, k1, acc, sse);
                 c = cn;
             }
             __syncthreads();   // everyone is done with this stage before TMA refills it
@@ -201,26 +285,42 @@ void ransac_score_constants(RansacParams* p) {
 // Work decomposition of the scoring launch.  hpt hypotheses per thread; `slots` row ranges of `rows_per_slot`
 // correspondences each (partial sums merged by the reduce kernel); persistent grid of `ctas_per_sm` CTAs per SM
 // (dynamic shared memory is padded so that no more fit), chosen so that the item count fills whole rounds.
-static int score_max_ctas(int hpt) {
-    static int cached[5] = {0, 0, 0, 0, 0};
-    if (!cached[hpt]) {
-        int n = 0;
-        cudaError_t e = (hpt == 4)
-            ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, ransac_score_kernel<4, false>, SCORE_THREADS, 2 * (SCORE_CHUNK + 1) * 16)
-            : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, ransac_score_kernel<2, false>, SCORE_THREADS, 2 * (SCORE_CHUNK + 1) * 16);
-        if (e != cudaSuccess || n < 1) { cudaGetLastError(); n = hpt == 4 ? 5 : 8; }
-        cached[hpt] = n;
+static bool score_packed_default() {
+    static int v = -1;
+    if (v < 0) {
+        const char* s = getenv("TVG_SCORE_PACKED");   // 1 selects the FFMA2 form (A/B timing, tools/score_sweep.py)
+        v = (s && s[0] == '1') ? 1 : 0;
     }
-    return cached[hpt];
+    return v != 0;
+}
+
+static int score_max_ctas(int hpt, bool packed) {
+    static int cached[2][5] = {{0, 0, 0, 0, 0}, {0, 0, 0, 0, 0}};
+    int& c = cached[packed ? 1 : 0][hpt];
+    if (!c) {
+        int n = 0;
+        const int smem = 2 * (SCORE_CHUNK + 1) * 16;
+        cudaError_t e;
+        if (packed)
+            e = (hpt == 4) ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, ransac_score_kernel<4, false, true>, SCORE_THREADS, smem)
+                           : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, ransac_score_kernel<2, false, true>, SCORE_THREADS, smem);
+        else
+            e = (hpt == 4) ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, ransac_score_kernel<4, false, false>, SCORE_THREADS, smem)
+                           : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, ransac_score_kernel<2, false, false>, SCORE_THREADS, smem);
+        if (e != cudaSuccess || n < 1) { cudaGetLastError(); n = hpt == 4 ? 5 : 8; }
+        c = n;
+    }
+    return c;
 }
 
 void ransac_score_plan(int batch, int n_max, int H, int sm_count, int cfg_hpt, int cfg_ctas, ScorePlan* out) {
     ScorePlan pl{};
     pl.hpt = (cfg_hpt == 4) ? 4 : 2;
+    pl.packed = score_packed_default() ? 1 : 0;
     const int per_block = pl.hpt * SCORE_THREADS;
     pl.hblocks = (H + per_block - 1) / per_block;
     const int chunks = (n_max + SCORE_CHUNK - 1) / SCORE_CHUNK > 0 ? (n_max + SCORE_CHUNK - 1) / SCORE_CHUNK : 1;
-    int max_c = score_max_ctas(pl.hpt);
+    int max_c = score_max_ctas(pl.hpt, pl.packed != 0);
     if (cfg_ctas > 0 && cfg_ctas < max_c) max_c = cfg_ctas;
     // row slots: one when (pair, hypothesis block) items alone give >= 4 rounds of the persistent grid, else split
     // the rows (a single huge pair); never more than SCORE_MAX_ROWS rows per slot
@@ -239,7 +339,7 @@ void ransac_score_plan(int batch, int n_max, int H, int sm_count, int cfg_hpt, i
     // dynamic queue evens out the last round, so filling whole rounds matters less than the issue mix.
     int best_c = pl.hpt == 4 ? 4 : 6;
     if (best_c > max_c) best_c = max_c;
-    if (cfg_ctas > 0) best_c = cfg_ctas < score_max_ctas(pl.hpt) ? cfg_ctas : score_max_ctas(pl.hpt);
+    if (cfg_ctas > 0) best_c = cfg_ctas < score_max_ctas(pl.hpt, pl.packed != 0) ? cfg_ctas : score_max_ctas(pl.hpt, pl.packed != 0);
     pl.ctas_per_sm = best_c;
     const long long g = (long long)sm_count * best_c;
     pl.grid = (int)(pl.items < g ? pl.items : g);
@@ -257,16 +357,17 @@ cudaError_t launch_ransac_score(const RansacParams& p, int batch, const ScorePla
     // the fp32 sum of squared residuals is diagnostic (selection uses the exact fp64 re-score): computed
     // only when the caller asked for it
     (void)batch;
-#define TVG_SCORE_LAUNCH(HPT, SSE)                                                                                    \
+#define TVG_SCORE_LAUNCH(HPT, SSE, PK)                                                                                \
     do {                                                                                                              \
-        cudaError_t e__ = cudaFuncSetAttribute(ransac_score_kernel<HPT, SSE>, cudaFuncAttributeMaxDynamicSharedMemorySize, pl.smem); \
+        cudaError_t e__ = cudaFuncSetAttribute(ransac_score_kernel<HPT, SSE, PK>, cudaFuncAttributeMaxDynamicSharedMemorySize, pl.smem); \
         if (e__ != cudaSuccess) return e__;                                                                           \
-        ransac_score_kernel<HPT, SSE><<<pl.grid, SCORE_THREADS, pl.smem, stream>>>(p, pl.items, pl.hblocks);         \
+        ransac_score_kernel<HPT, SSE, PK><<<pl.grid, SCORE_THREADS, pl.smem, stream>>>(p, pl.items, pl.hblocks);     \
     } while (0)
+    const bool pk = pl.packed != 0 && !p.want_sse;
     if (pl.hpt == 4) {
-        if (p.want_sse) TVG_SCORE_LAUNCH(4, true); else TVG_SCORE_LAUNCH(4, false);
+        if (p.want_sse) TVG_SCORE_LAUNCH(4, true, false); else if (pk) TVG_SCORE_LAUNCH(4, false, true); else TVG_SCORE_LAUNCH(4, false, false);
     } else {
-        if (p.want_sse) TVG_SCORE_LAUNCH(2, true); else TVG_SCORE_LAUNCH(2, false);
+        if (p.want_sse) TVG_SCORE_LAUNCH(2, true, false); else if (pk) TVG_SCORE_LAUNCH(2, false, true); else TVG_SCORE_LAUNCH(2, false, false);
     }
 #undef TVG_SCORE_LAUNCH
     return cudaGetLastError();

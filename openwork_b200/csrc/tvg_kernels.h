@@ -132,6 +132,7 @@ cudaError_t launch_ransac_fit(const RansacParams& p, int batch, cudaStream_t str
 // scoring launch plan: hypotheses per thread, row slots (p.chunks) x rows per slot (p.chunk), persistent grid
 struct ScorePlan {
     int hpt, hblocks, slots, rows_per_slot, items, ctas_per_sm, grid, smem;
+    int packed;   // 1: pairs of hypotheses in 64-bit registers, fma.rn.f32x2 (FFMA2); 0: scalar FFMA form
 };
 // cfg_hpt in {0 (default 2), 2, 4}; cfg_ctas > 0 forces the resident CTAs per SM
 void ransac_score_plan(int batch, int n_max, int H, int sm_count, int cfg_hpt, int cfg_ctas, ScorePlan* out);

@@ -270,6 +270,34 @@ def test_ransac_counts_best_mask_E(ops, n, H, seed, use_words):
     np.testing.assert_allclose(g["Rt"].cpu().numpy(), tv.extract_Rt(ref["E"]), atol=1e-6)
 
 
+def test_ransac_packed_scoring_form_counts_identical(ops, tmp_path):
+    """The opt-in FFMA2 form of the scoring kernel (pairs of hypotheses in 64-bit registers, TVG_SCORE_PACKED=1: read
+    once per process, hence the child process) performs the same fp32 operations: every count, the winner and the mask
+    are bit-identical to the default scalar form."""
+    import os
+    import subprocess
+    import sys
+    src, dst, _ = _pair_correspondences(2048, 21)
+    words = synth.sample_words(1024, 21)
+    g = ops.ransac_essential(src, dst, words=words, residual_threshold=THR, return_models=True)
+    np.savez(tmp_path / "in.npz", src=src, dst=dst, words=words)
+    code = (
+        "import sys, numpy as np\n"
+        "sys.path.insert(0, %r)\n"
+        "from openwork_b200 import ops\n"
+        "d = np.load(%r)\n"
+        "g = ops.ransac_essential(d['src'], d['dst'], words=d['words'], residual_threshold=%r, return_models=True)\n"
+        "np.savez(%r, counts=g['counts'].cpu().numpy(), mask=g['mask'].cpu().numpy(), best=g['best'], E=g['E'].cpu().numpy())\n"
+    ) % (os.path.dirname(os.path.dirname(os.path.abspath(__file__))), str(tmp_path / "in.npz"), THR, str(tmp_path / "out.npz"))
+    env = dict(os.environ, TVG_SCORE_PACKED="1")
+    subprocess.run([sys.executable, "-c", code], check=True, env=env, timeout=600)
+    o = np.load(tmp_path / "out.npz")
+    assert np.array_equal(o["counts"], g["counts"].cpu().numpy())
+    assert int(o["best"]) == g["best"]
+    assert np.array_equal(o["mask"], g["mask"].cpu().numpy())
+    assert np.array_equal(o["E"], g["E"].cpu().numpy())
+
+
 def test_ransac_noise_free_scene_all_inliers(ops):
     """Closed form: noise-free correspondences of E = [t]x R -> every hypothesis explains every point."""
     rng = np.random.default_rng(0)
