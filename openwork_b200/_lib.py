@@ -132,7 +132,8 @@ def load():
             raise ImportError(
                 "openwork_b200: %s is missing and could not be built (%s) -- run `python -m openwork_b200.build`. "
                 "There is no CPU fallback." % (LIB_PATH, e))
-    lib = C.CDLL(LIB_PATH)
+    # TVG_B200_LIB: a differently-configured build of the SAME library (kernel-knob sweeps, tools/sweep_tc2_knobs.sh)
+    lib = C.CDLL(os.environ.get("TVG_B200_LIB") or LIB_PATH)
     for name, (res, args) in SIGNATURES.items():
         fn = getattr(lib, name)
         fn.restype = res

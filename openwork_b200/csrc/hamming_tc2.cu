@@ -37,8 +37,14 @@ constexpr int T2_TH = T2_TN / 2;                // train rows expanded by one CT
 constexpr int T2_KB = 256;                      // bytes per e4m3 row
 constexpr int T2_A_BLK = T2_QB * T2_KB;         // 32 KB
 constexpr int T2_B_HALF = T2_TH * T2_KB;        // 32 KB
-constexpr int T2_NST = 4;
-constexpr int T2_EXP_WARPS = 3;
+#ifndef T2_NST_N
+#define T2_NST_N 4
+#endif
+#ifndef T2_EXP_WARPS_N
+#define T2_EXP_WARPS_N 3
+#endif
+constexpr int T2_NST = T2_NST_N;                // train-tile ring stages (tools/sweep_tc2_knobs.sh times the alternatives)
+constexpr int T2_EXP_WARPS = T2_EXP_WARPS_N;    // expander warps per CTA
 #ifndef T2_CSPLIT_N
 #define T2_CSPLIT_N 1
 #endif
