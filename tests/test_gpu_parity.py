@@ -346,6 +346,47 @@ def test_extract_rt_matches_reference_conventions(ops):
     np.testing.assert_allclose(got, np.stack(refs), atol=1e-9)
 
 
+def test_extract_rt_fast_and_fallback_paths(ops):
+    """extract_Rt takes U, V from a non-iterative rank-two SVD when E is an essential matrix to 1e-10 and from the
+    Jacobi SVD otherwise: 2000 exact essential matrices (fast path), the same matrices pushed off rank two by 1e-13
+    (still the fast path), by 1e-7 (fallback) and with well-separated, unequal singular values (fast path, the 2x2
+    rotation is not trivial) -- all against numpy's SVD through the oracle."""
+    rng = np.random.default_rng(40)
+    Es = []
+    for i in range(2000):
+        R = synth._small_rotation(rng, 0.5)
+        t = rng.normal(size=3)
+        tx = np.array([[0, -t[2], t[1]], [t[2], 0, -t[0]], [-t[1], t[0], 0]])
+        E = (tx @ R) * 10.0 ** rng.uniform(-3, 3) * rng.choice([-1, 1])
+        kind = i % 4
+        if kind == 1:
+            E = E + 1e-13 * np.linalg.norm(E) * rng.normal(size=(3, 3))
+        elif kind == 2:
+            E = E + 1e-7 * np.linalg.norm(E) * rng.normal(size=(3, 3))
+        elif kind == 3:      # T_d^T E T_s as after the refit's de-normalisation: rank two, s0 != s1
+            Ts = np.array([[rng.uniform(0.5, 3), 0, rng.normal()], [0, rng.uniform(0.5, 3), rng.normal()], [0, 0, 1]])
+            E = Ts.T @ E @ np.array([[rng.uniform(0.5, 3), 0, rng.normal()], [0, rng.uniform(0.5, 3), rng.normal()], [0, 0, 1]])
+        Es.append(E)
+    Es = np.stack(Es)
+    refs = np.stack([tv.extract_Rt(E) for E in Es])
+    got = ops.extract_rt(Es).cpu().numpy()
+    # the trace rule is discontinuous: leave out the (rare) matrices whose two candidate rotations both have a trace
+    # within 1e-6 of zero
+    U, _, Vt = np.linalg.svd(Es)
+    W = np.array([[0, -1, 0], [1, 0, 0], [0, 0, 1]], dtype=float)
+    du = np.sign(np.linalg.det(U))[:, None, None]
+    dv = np.sign(np.linalg.det(Vt))[:, None, None]
+    tra = np.trace((U * du) @ W @ (Vt * dv), axis1=1, axis2=2)
+    trb = np.trace((U * du) @ W.T @ (Vt * dv), axis1=1, axis2=2)
+    # ... and those where BOTH candidates have a positive trace: there the reference's answer is whichever sign
+    # LAPACK happened to give the singular vectors (no camera motion between consecutive frames looks like that)
+    ok = (np.abs(tra) > 1e-6) & (np.minimum(tra, trb) < 0)
+    assert ok.mean() > 0.9
+    err = np.abs(got - refs).reshape(len(Es), -1).max(axis=1)
+    tol = np.where(np.arange(len(Es)) % 4 == 2, 1e-7, 1e-9)
+    assert (err[ok] < tol[ok]).all(), (int(np.argmax(err * ok)), float((err * ok).max()))
+
+
 def test_triangulate_matches_reference(ops):
     src, dst, (lk, ck, i1, i2) = _pair_correspondences(2048, 21)
     samples = synth.sample_table(len(src), 256, 3)
