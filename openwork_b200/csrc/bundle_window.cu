@@ -6,13 +6,14 @@
 //   Levenberg-Marquardt with Marquardt diagonal scaling, points eliminated by the Schur complement (3x3 blocks),
 //   a fixed number of iterations, a step accepted iff the cost decreases (lambda /= 10, else *= 10).
 // One CTA per window, W <= 8 cameras.  All arithmetic fp64, every cross-thread sum in a fixed order (deterministic):
-//   pass 0   thread = point: V = sum_c Jp^T Jp (damped), its inverse, g_p              -> per-point scratch
-//   pass a   (one per free camera) thread = point: W_a = Jc^T Jp, Y_a = W_a V^-1        -> per-point scratch;
-//            U_a = sum Jc^T Jc, g_a = sum Jc^T r, sum Y_a g_p by a fixed-order block reduction
-//   Schur    thread = (camera pair a <= b, point slice): the 6x6 block sum_j Y_a W_b^T over the slice's points in
-//            registers, slices folded into S in slice order
+//   pass 0   thread = point: V = sum_c Jp^T Jp (damped), its inverse, g_p              -> per-point scratch (12 doubles)
+//   chunks   of 256 / (free cameras) points, two phases per chunk, nothing but the per-point scratch touches HBM:
+//            (i)  thread = (point, free camera a): W_a = Jc^T Jp and Y_a = W_a V^-1 into shared memory (72 KB);
+//                 U_a = sum Jc^T Jc, g_a = sum Jc^T r, sum Y_a g_p in registers
+//            (ii) thread = (camera pair a <= b, point slice): the 6x6 block sum_j Y_a W_b^T in registers
+//            then fixed-order folds: per-camera sums over the point slots, Schur blocks slice after slice
 //   solve    Gaussian elimination with partial pivoting of the 6 (W - n_fixed) system in shared memory
-//   update   thread = point: X - V^-1 (g_p + sum_a W_a^T d_a), trial cost, accept / reject
+//   update   thread = point: X - V^-1 (g_p + sum_a Jp^T (Jc d_a)) with the Jacobians recomputed, trial cost, accept / reject
 #include "bundle_common.cuh"
 #include "tvg_kernels.h"
 
@@ -24,7 +25,8 @@ constexpr int BW_MAXW = 8;
 constexpr int BW_MAXV = BW_MAXW - 1;          // free cameras
 constexpr int BW_MAXS = 6 * BW_MAXV;          // reduced system size (42)
 constexpr int BW_PT = 12;                     // per-point scratch doubles: V^-1 (6), g_p (3), trial X (3)
-constexpr int BW_CAM = 36;                    // per (point, free camera): W (18), Y = W V^-1 (18)
+constexpr int BW_CAM = 36;                    // per (point, free camera), shared memory only: W (18), Y = W V^-1 (18)
+constexpr int BW_SMEM = BA_THREADS * BW_CAM * 8;   // dynamic shared memory: one (point, camera) block per thread
 
 // residual and Jacobian blocks of one observation: Jp (2x3, w.r.t. the point), Jc (2x6, w.r.t. the camera's twist)
 __device__ __forceinline__ void obs_blocks(const Cam& c, const double (&X)[3], double x, double y, double (&r)[2],
@@ -58,8 +60,10 @@ __device__ __forceinline__ double obs_cost(const Cam& c, const double (&X)[3], d
 }
 
 __global__ void __launch_bounds__(BA_THREADS) bundle_window_kernel(const BundleWindowParams p) {
+    extern __shared__ __align__(16) double s_blk[];   // [points per chunk][free cameras][36]; later [33][BA_THREADS]
     __shared__ double s_part[33][BA_THREADS / 32];
     __shared__ double s_red[33];
+    __shared__ double s_sum[BW_MAXV][33];
     __shared__ double s_S[BW_MAXS][BW_MAXS + 1];     // reduced camera system, last column = right-hand side
     __shared__ double s_d[BW_MAXS];
     __shared__ Cam s_cam[BW_MAXW], s_trial[BW_MAXW];
@@ -72,8 +76,7 @@ __global__ void __launch_bounds__(BA_THREADS) bundle_window_kernel(const BundleW
     const double2* obs = reinterpret_cast<const double2*>(p.obs) + ob * W;
     const uint8_t* vis = p.vis + ob * W;
     double* X4 = p.points4d + ob * 4;
-    double* spt = p.scratch + ob * (BW_PT + (size_t)BW_CAM * BW_MAXV);
-    double* scam = spt + (size_t)p.n_max * BW_PT;                 // [n_max][nv][36]
+    double* spt = p.scratch + ob * BW_PT;
     if (tid < W) cam_from_pose(p.poses + ((size_t)b * W + tid) * 16, s_cam[tid]);
     if (tid == 0) { s_lambda = p.lambda0; s_accepted = 0; }
     __syncthreads();
@@ -139,90 +142,108 @@ __global__ void __launch_bounds__(BA_THREADS) bundle_window_kernel(const BundleW
         }
         for (int e = tid; e < ns * (ns + 1); e += BA_THREADS) s_S[e / (ns + 1)][e % (ns + 1)] = 0.0;
         __syncthreads();
-        // ---- pass a: one free camera at a time
-        for (int a = 0; a < nv; ++a) {
-            const Cam cam = s_cam[nf + a];
-            double acc[33];   // U_a (21), g_a (6), sum Y_a g_p (6)
-#pragma unroll
-            for (int i = 0; i < 33; ++i) acc[i] = 0.0;
-            for (int j = tid; j < n; j += BA_THREADS) {
-                double* oc = scam + ((size_t)j * nv + a) * BW_CAM;
-                if (!vis[(size_t)j * W + nf + a]) {
-#pragma unroll
-                    for (int i = 0; i < BW_CAM; ++i) oc[i] = 0.0;
-                    continue;
-                }
-                const double X[3] = {X4[(size_t)j * 4], X4[(size_t)j * 4 + 1], X4[(size_t)j * 4 + 2]};
-                const double* o = spt + (size_t)j * BW_PT;
-                const double Vi[3][3] = {{o[0], o[1], o[2]}, {o[1], o[3], o[4]}, {o[2], o[4], o[5]}};
-                double x, y, r[2], Jp[2][3], Jc[2][6];
-                norm(obs[(size_t)j * W + nf + a], x, y);
-                obs_blocks(cam, X, x, y, r, Jp, Jc);
-                int t = 0;
-#pragma unroll
-                for (int i = 0; i < 6; ++i) {
-                    double Wr[3], Yr[3];
-#pragma unroll
-                    for (int k = 0; k < 3; ++k) Wr[k] = Jc[0][i] * Jp[0][k] + Jc[1][i] * Jp[1][k];
-#pragma unroll
-                    for (int k = 0; k < 3; ++k) Yr[k] = Wr[0] * Vi[0][k] + Wr[1] * Vi[1][k] + Wr[2] * Vi[2][k];
-#pragma unroll
-                    for (int k = 0; k < 3; ++k) { oc[i * 3 + k] = Wr[k]; oc[18 + i * 3 + k] = Yr[k]; }
-#pragma unroll
-                    for (int c = i; c < 6; ++c) acc[t++] += Jc[0][i] * Jc[0][c] + Jc[1][i] * Jc[1][c];
-                    acc[21 + i] += Jc[0][i] * r[0] + Jc[1][i] * r[1];
-                    acc[27 + i] += Yr[0] * o[6] + Yr[1] * o[7] + Yr[2] * o[8];
-                }
-            }
-            block_sum_vec<33>(acc, s_part, s_red);
-            if (tid == 0) {
-                int t = 0;
-                for (int i = 0; i < 6; ++i)
-                    for (int c = i; c < 6; ++c) {
-                        const double u = s_red[t++] * (i == c ? 1.0 + lambda : 1.0);
-                        s_S[6 * a + i][6 * a + c] = u;
-                        s_S[6 * a + c][6 * a + i] = u;
-                    }
-                for (int i = 0; i < 6; ++i) s_S[6 * a + i][ns] = -(s_red[21 + i] - s_red[27 + i]);
-            }
-            __syncthreads();
-        }
-        // ---- Schur complement: S[(a,.)][(b,.)] -= sum over the points of Y_a W_b^T.  Thread = (camera pair a <= b,
-        // point slice): a 6x6 block in registers, 18 + 18 contiguous doubles per point for 108 multiply-adds, only the
-        // points both cameras see; the slices are then folded into S one after the other (fixed order)
+        // ---- chunks of PCH points: (i) W / Y blocks of every (point, free camera) into shared memory + per-camera
+        // sums, (ii) the Schur blocks of every camera pair from shared memory
         {
+            const int PCH = BA_THREADS / nv;                 // points per chunk
+            const int cp = tid / nv, ca = tid % nv;          // phase (i): this thread's point slot and free camera
+            const bool worker = tid < PCH * nv;
             const int npair = nv * (nv + 1) / 2;
             const int nslice = max(BA_THREADS / npair, 1);
-            const int pr = tid / nslice, sl = tid % nslice;
+            const int pr = tid / nslice, sl = tid % nslice;  // phase (ii): camera pair and point slice
             int a = 0, bb = 0;
             if (pr < npair) {
                 int rest = pr;
                 while (rest >= nv - a) { rest -= nv - a; ++a; }
                 bb = a + rest;
             }
+            const Cam cam = s_cam[nf + ca];
+            double acc[33];   // U_a (21), g_a (6), sum Y_a g_p (6) of camera ca over this thread's points
+#pragma unroll
+            for (int i = 0; i < 33; ++i) acc[i] = 0.0;
             double blk[6][6];
 #pragma unroll
             for (int i = 0; i < 6; ++i)
 #pragma unroll
                 for (int c = 0; c < 6; ++c) blk[i][c] = 0.0;
-            if (pr < npair) {
-                for (int j = sl; j < n; j += nslice) {
-                    if (!vis[(size_t)j * W + nf + a] || !vis[(size_t)j * W + nf + bb]) continue;
-                    const double* ya = scam + ((size_t)j * nv + a) * BW_CAM + 18;
-                    const double* wb = scam + ((size_t)j * nv + bb) * BW_CAM;
-                    double y[18], w[18];
+            for (int j0 = 0; j0 < n; j0 += PCH) {
+                if (worker) {
+                    const int j = j0 + cp;
+                    double* oc = s_blk + (size_t)(cp * nv + ca) * BW_CAM;
+                    if (j < n && vis[(size_t)j * W + nf + ca]) {
+                        const double X[3] = {X4[(size_t)j * 4], X4[(size_t)j * 4 + 1], X4[(size_t)j * 4 + 2]};
+                        const double* o = spt + (size_t)j * BW_PT;
+                        const double Vi[3][3] = {{o[0], o[1], o[2]}, {o[1], o[3], o[4]}, {o[2], o[4], o[5]}};
+                        const double gp[3] = {o[6], o[7], o[8]};
+                        double x, y, r[2], Jp[2][3], Jc[2][6];
+                        norm(obs[(size_t)j * W + nf + ca], x, y);
+                        obs_blocks(cam, X, x, y, r, Jp, Jc);
+                        int t = 0;
 #pragma unroll
-                    for (int k = 0; k < 18; ++k) { y[k] = ya[k]; w[k] = wb[k]; }
+                        for (int i = 0; i < 6; ++i) {
+                            double Wr[3], Yr[3];
 #pragma unroll
-                    for (int i = 0; i < 6; ++i)
+                            for (int k = 0; k < 3; ++k) Wr[k] = Jc[0][i] * Jp[0][k] + Jc[1][i] * Jp[1][k];
 #pragma unroll
-                        for (int c = 0; c < 6; ++c)
-                            blk[i][c] = fma(y[i * 3], w[c * 3],
-                                            fma(y[i * 3 + 1], w[c * 3 + 1], fma(y[i * 3 + 2], w[c * 3 + 2], blk[i][c])));
+                            for (int k = 0; k < 3; ++k) Yr[k] = Wr[0] * Vi[0][k] + Wr[1] * Vi[1][k] + Wr[2] * Vi[2][k];
+#pragma unroll
+                            for (int k = 0; k < 3; ++k) { oc[i * 3 + k] = Wr[k]; oc[18 + i * 3 + k] = Yr[k]; }
+#pragma unroll
+                            for (int c = i; c < 6; ++c) acc[t++] += Jc[0][i] * Jc[0][c] + Jc[1][i] * Jc[1][c];
+                            acc[21 + i] += Jc[0][i] * r[0] + Jc[1][i] * r[1];
+                            acc[27 + i] += Yr[0] * gp[0] + Yr[1] * gp[1] + Yr[2] * gp[2];
+                        }
+                    } else {
+#pragma unroll
+                        for (int i = 0; i < BW_CAM; ++i) oc[i] = 0.0;   // unseen (or past the end): contributes exact zeros
+                    }
                 }
+                __syncthreads();
+                if (pr < npair) {
+                    const int lim = min(PCH, n - j0);
+                    for (int jl = sl; jl < lim; jl += nslice) {
+                        const double* ya = s_blk + (size_t)(jl * nv + a) * BW_CAM + 18;
+                        const double* wb = s_blk + (size_t)(jl * nv + bb) * BW_CAM;
+                        double y[18], w[18];
+#pragma unroll
+                        for (int k = 0; k < 18; ++k) { y[k] = ya[k]; w[k] = wb[k]; }
+#pragma unroll
+                        for (int i = 0; i < 6; ++i)
+#pragma unroll
+                            for (int c = 0; c < 6; ++c)
+                                blk[i][c] = fma(y[i * 3], w[c * 3],
+                                                fma(y[i * 3 + 1], w[c * 3 + 1], fma(y[i * 3 + 2], w[c * 3 + 2], blk[i][c])));
+                    }
+                }
+                __syncthreads();
             }
-            for (int s = 0; s < nslice; ++s) {
-                if (pr < npair && sl == s) {
+            // per-camera sums: every thread's 33 partials through shared memory, summed over the point slots in order
+            if (worker) {
+#pragma unroll
+                for (int e = 0; e < 33; ++e) s_blk[(size_t)e * BA_THREADS + tid] = acc[e];
+            }
+            __syncthreads();
+            for (int q = tid; q < nv * 33; q += BA_THREADS) {
+                const int qa = q / 33, e = q % 33;
+                double t = 0.0;
+                for (int c2 = 0; c2 < PCH; ++c2) t += s_blk[(size_t)e * BA_THREADS + c2 * nv + qa];
+                s_sum[qa][e] = t;
+            }
+            __syncthreads();
+            if (tid < nv) {
+                int t = 0;
+                for (int i = 0; i < 6; ++i)
+                    for (int c = i; c < 6; ++c) {
+                        const double u = s_sum[tid][t++] * (i == c ? 1.0 + lambda : 1.0);
+                        s_S[6 * tid + i][6 * tid + c] = u;
+                        s_S[6 * tid + c][6 * tid + i] = u;
+                    }
+                for (int i = 0; i < 6; ++i) s_S[6 * tid + i][ns] = -(s_sum[tid][21 + i] - s_sum[tid][27 + i]);
+            }
+            __syncthreads();
+            // Schur complement: S[(a,.)][(b,.)] -= the blocks, slice after slice (fixed order)
+            for (int sfold = 0; sfold < nslice; ++sfold) {
+                if (pr < npair && sl == sfold) {
 #pragma unroll
                     for (int i = 0; i < 6; ++i)
 #pragma unroll
@@ -295,17 +316,21 @@ __global__ void __launch_bounds__(BA_THREADS) bundle_window_kernel(const BundleW
                 double e3[3] = {o[6], o[7], o[8]};
                 bool seen = false;
                 for (int c = 0; c < W; ++c) seen = seen || vis[(size_t)j * W + c];
-                for (int a = 0; a < nv; ++a) {
-                    const double* wa = scam + ((size_t)j * nv + a) * BW_CAM;
-#pragma unroll
-                    for (int k = 0; k < 3; ++k) {
-                        double wd = 0.0;
-#pragma unroll
-                        for (int i = 0; i < 6; ++i) wd += wa[i * 3 + k] * s_d[6 * a + i];
-                        e3[k] += wd;
-                    }
-                }
                 const double X[3] = {X4[(size_t)j * 4], X4[(size_t)j * 4 + 1], X4[(size_t)j * 4 + 2]};
+                for (int a = 0; a < nv; ++a) {            // e3 += W_a^T d_a = Jp^T (Jc d_a), Jacobians recomputed
+                    if (!vis[(size_t)j * W + nf + a]) continue;
+                    double x, y, r[2], Jp[2][3], Jc[2][6];
+                    norm(obs[(size_t)j * W + nf + a], x, y);
+                    obs_blocks(s_cam[nf + a], X, x, y, r, Jp, Jc);
+                    double s2[2] = {0.0, 0.0};
+#pragma unroll
+                    for (int i = 0; i < 6; ++i) {
+                        s2[0] += Jc[0][i] * s_d[6 * a + i];
+                        s2[1] += Jc[1][i] * s_d[6 * a + i];
+                    }
+#pragma unroll
+                    for (int k = 0; k < 3; ++k) e3[k] += Jp[0][k] * s2[0] + Jp[1][k] * s2[1];
+                }
                 if (seen) {
                     o[9] = X[0] - (o[0] * e3[0] + o[1] * e3[1] + o[2] * e3[2]);
                     o[10] = X[1] - (o[1] * e3[0] + o[3] * e3[1] + o[4] * e3[2]);
@@ -356,12 +381,14 @@ __global__ void __launch_bounds__(BA_THREADS) bundle_window_kernel(const BundleW
 }  // namespace
 
 size_t bundle_window_scratch_doubles(int batch, int n_max) {
-    return (size_t)batch * (n_max > 0 ? n_max : 1) * (BW_PT + (size_t)BW_CAM * BW_MAXV);
+    return (size_t)batch * (n_max > 0 ? n_max : 1) * BW_PT;
 }
 int bundle_window_max_cameras() { return BW_MAXW; }
 
 cudaError_t launch_bundle_window(const BundleWindowParams& p, int batch, cudaStream_t stream) {
-    bundle_window_kernel<<<batch, ba::BA_THREADS, 0, stream>>>(p);
+    cudaError_t e = cudaFuncSetAttribute(bundle_window_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, BW_SMEM);
+    if (e != cudaSuccess) return e;
+    bundle_window_kernel<<<batch, ba::BA_THREADS, BW_SMEM, stream>>>(p);
     return cudaGetLastError();
 }
 
