@@ -53,6 +53,21 @@ constexpr int T2_EPI_WARPS = 4 * T2_NQB * T2_CSPLIT;   // (measured: 16 warps wi
                                                 // 0.93 vs 0.88 ms -- the epilogue is bound by the integer pipe, not by latency)
 constexpr int T2_THREADS = 32 * (1 + T2_EXP_WARPS + T2_EPI_WARPS);
 constexpr int T2_CW = T2_TN / T2_CSPLIT;        // columns per epilogue warp and tile (128)
+// Column halves: the accumulator of a query block is filled and drained as two independent 128-column halves (MMA
+// N = 128, four full / empty barrier pairs instead of two), so that the tensor-memory load of one half is in flight
+// while the epilogue's arithmetic runs on the other and the MMAs of a half start as soon as that half has been read.
+#ifndef T2_HALVES_N
+#define T2_HALVES_N 0
+#endif
+#ifndef T2_SPLIT_LD_N
+#define T2_SPLIT_LD_N 1                         // 64-column loads of a tile whose arithmetic precedes the accumulator's release
+#endif
+#ifndef T2_FIRST_LD_N
+#define T2_FIRST_LD_N 1                         // 64-column loads waited for before that arithmetic starts (>= T2_SPLIT_LD_N)
+#endif
+constexpr int T2_NC = T2_HALVES_N ? 2 : 1;      // column halves per accumulator
+constexpr int T2_CN = T2_TN / T2_NC;            // MMA N
+static_assert(T2_NC == 1 || T2_CSPLIT == 1, "column halves replace the column split of the epilogue warps");
 constexpr int T2_XCH = T2_NQB * T2_QB * 8;      // top-2 hand-off between the column halves of a row (uint2 per row)
 constexpr int T2_CONST = 2 * 4096;              // the two constant operand blocks of the offset MMA (see below)
 constexpr int T2_SMEM = T2_NQB * T2_A_BLK + T2_NST * T2_B_HALF + T2_XCH + T2_CONST + 256;
@@ -63,7 +78,8 @@ constexpr int T2_UPT = (T2_UNITS + 32 * T2_EXP_WARPS - 1) / (32 * T2_EXP_WARPS);
 #define T2_LISTS 4
 #endif
 // instruction descriptor: D = f16, A = B = e4m3, both K-major, N >> 3 at bit 17, M >> 4 at bit 24 (M = 256 over the pair)
-constexpr uint32_t T2_IDESC = ((uint32_t)(T2_TN >> 3) << 17) | ((uint32_t)((2 * T2_QB) >> 4) << 24);
+constexpr uint32_t T2_IDESC = ((uint32_t)(T2_CN >> 3) << 17) | ((uint32_t)((2 * T2_QB) >> 4) << 24);
+constexpr uint64_t T2_B_HALF_STEP = (uint64_t)(((T2_TH / T2_NC) / 8) * 2048) >> 4;   // B rows of the next column half, in descriptor units
 
 __device__ __forceinline__ uint32_t t2_cta_rank() {
     uint32_t r;
@@ -192,9 +208,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(T2_THREADS, 1) knn2_
     uint64_t* full = bars;                       // [NST]  operand halves of both CTAs written      (waited on in the leader)
     uint64_t* empty = full + T2_NST;             // [NST]  MMAs that read the stage are complete    (commit, both CTAs)
     uint64_t* a_full = empty + T2_NST;           // [NQB]  query blocks of both CTAs written        (leader)
-    uint64_t* acc_full = a_full + T2_NQB;        // [NQB]  accumulator complete                     (commit, both CTAs)
-    uint64_t* acc_empty = acc_full + T2_NQB;     // [NQB]  accumulator read back by both CTAs       (leader)
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + T2_NQB);
+    uint64_t* acc_full = a_full + T2_NQB;        // [NQB][NC]  accumulator (half) complete          (commit, both CTAs)
+    uint64_t* acc_empty = acc_full + T2_NQB * T2_NC;   // [NQB][NC]  read back by both CTAs             (leader)
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + T2_NQB * T2_NC);
 
     const KnnParams& p = a.k;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -203,7 +219,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(T2_THREADS, 1) knn2_
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < T2_NST; ++s) { mbar_init(full + s, 2 * T2_EXP_WARPS); mbar_init(empty + s, 1); }
-        for (int h = 0; h < T2_NQB; ++h) { mbar_init(a_full + h, 8); mbar_init(acc_full + h, 1); mbar_init(acc_empty + h, 8 * T2_CSPLIT); }
+        for (int h = 0; h < T2_NQB; ++h) mbar_init(a_full + h, 8);
+        for (int h = 0; h < T2_NQB * T2_NC; ++h) { mbar_init(acc_full + h, 1); mbar_init(acc_empty + h, 8 * T2_CSPLIT); }
         fence_mbar_init();
     }
     for (int i = threadIdx.x; i < T2_CONST / 4; i += T2_THREADS)   // A: 1.0 (0x38), B: 36.0 (0x61)
@@ -249,18 +266,23 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(T2_THREADS, 1) knn2_
 #pragma unroll
                     for (int h = 0; h < T2_NQB; ++h) {
                         if (j == j0) t2_wait(a_full + h, it & 1);
-                        t2_wait(acc_empty + h, (step & 1) ^ 1);
-                        t2_fence_after();
                         const uint64_t a_desc = t2_smem_desc(smem_u32(a_smem + h * T2_A_BLK));
-                        if (t2_elect_one()) {
 #pragma unroll
-                            for (int k = 0; k < T2_KB / 32; ++k)   // 32 K-bytes = two core matrices = 256 B = 16 address units
-                                t2_mma(tmem_base + h * T2_TN, a_desc + (uint64_t)(k * 16), b_desc + (uint64_t)(k * 16), T2_IDESC, k > 0);
-                            t2_mma(tmem_base + h * T2_TN, c_a_desc, c_b_desc, T2_IDESC, 1);   // + 1152, last
-                            t2_commit(acc_full + h);
-                            if (h == T2_NQB - 1) t2_commit(empty + s);
+                        for (int c = 0; c < T2_NC; ++c) {
+                            t2_wait(acc_empty + h * T2_NC + c, (step & 1) ^ 1);
+                            t2_fence_after();
+                            if (t2_elect_one()) {
+                                const uint32_t d = tmem_base + h * T2_TN + c * T2_CN;
+                                const uint64_t bd = b_desc + (uint64_t)c * T2_B_HALF_STEP;
+#pragma unroll
+                                for (int k = 0; k < T2_KB / 32; ++k)   // 32 K-bytes = two core matrices = 256 B = 16 address units
+                                    t2_mma(d, a_desc + (uint64_t)(k * 16), bd + (uint64_t)(k * 16), T2_IDESC, k > 0);
+                                t2_mma(d, c_a_desc, c_b_desc, T2_IDESC, 1);   // + 1152, last
+                                t2_commit(acc_full + h * T2_NC + c);
+                                if (h == T2_NQB - 1 && c == T2_NC - 1) t2_commit(empty + s);
+                            }
+                            __syncwarp();
                         }
-                        __syncwarp();
                     }
                 }
                 ++it;
@@ -361,6 +383,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(T2_THREADS, 1) knn2_
             return false;
         };
         uint32_t use = 0;
+        uint32_t va[2][32], vb[2][32];   // column-half form: the two register halves of the accumulator read-back
+        bool early0 = false;             // half 0 of the tile about to be processed is already on its way into va
+        (void)va; (void)vb; (void)early0;
         {
             int fq, nq, qi;
             if (sub == 0 && next_live(cluster - n_clusters, fq, nq, qi)) write_a(fq, nq, qi);
@@ -370,64 +395,181 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(T2_THREADS, 1) knn2_
             const bool live = item_info(item, b, qi, fq, ft, nq, nt, j0, j1);
             uint32_t g1 = TVG_SENTINEL_KEY, g2 = TVG_SENTINEL_KEY;       // dist << 23 | train idx
             if (!live) j1 = j0;
-            for (int j = j0; j < j1; ++j, ++use) {
-                t2_wait(acc_full + h, use & 1);
-                t2_fence_after();
-                uint32_t v[T2_CW / 64][32];
-#pragma unroll
-                for (int c = 0; c < T2_CW / 64; ++c) t2_ld64_pack16(taddr + c * 64, v[c]);
-                t2_ld_wait();
-                // the accumulator is in registers now: hand it back to the MMA warp before the arithmetic
-                t2_fence_before();
-                __syncwarp();
-                if (lane == 0) t2_arrive_remote(acc_empty + h, 0);
-                // last tile of the item: every MMA that read this A block is complete -> stage the next item's rows
-                if (sub == 0 && j == j1 - 1) {
-                    int fq2, nq2, qi2;
-                    if (next_live(item, fq2, nq2, qi2)) write_a(fq2, nq2, qi2);
-                }
-                uint32_t m1[T2_LISTS], m2[T2_LISTS];
-#pragma unroll
-                for (int l = 0; l < T2_LISTS; ++l) m1[l] = m2[l] = 0xFFFFFFFFu;
-                const int cols = min(T2_TN, nt - j * T2_TN);
-                if (a.ablate & 1) { g1 = min(g1, v[0][0] ^ v[1][1]); continue; }
-                auto chunk = [&](auto masked) {
-#pragma unroll
-                    for (int c = 0; c < T2_CW / 64; ++c)
-#pragma unroll
-                        for (int i = 0; i < 32; i += 2) {
-                            uint32_t key[2];
-#pragma unroll
-                            for (int u = 0; u < 2; ++u) {
-                                const uint32_t pl = (uint32_t)(sub * (T2_CW / 2) + c * 32 + i + u);
-                                // accumulator = 1024 + d in f16 = bit pattern 0x6400 | d per 16-bit lane; * 128 + C_p ->
-                                // (d << 7) | p per lane (the 0x6400 terms overflow into constants that C_p cancels)
-                                key[u] = v[c][i + u] * p.w128 + (pl | (((pl - 0x32u) & 0xFFFFu) << 16));
-                                if (decltype(masked)::value) {
-                                    if (2 * (int)pl >= cols) key[u] |= 0x0000FFFFu;
-                                    if (2 * (int)pl + 1 >= cols) key[u] |= 0xFFFF0000u;
-                                }
-                            }
-                            // two keys per update: 5 min/max (one 3-input) instead of 6
-                            const int l = (i >> 1) & (T2_LISTS - 1);
-                            const uint32_t lo = __vminu2(key[0], key[1]), hi = __vmaxu2(key[0], key[1]);
-                            m2[l] = __vimin3_u16x2(m2[l], hi, __vmaxu2(m1[l], lo));
-                            m1[l] = __vminu2(m1[l], lo);
-                        }
+            if constexpr (T2_NC == 2) {
+                // ---- column halves: while the arithmetic runs on one half (64 registers), the tensor-memory load of the
+                // next half is in flight into the other 64; a half goes back to the MMA warp as soon as it has been read
+                auto ld_half = [&](int c, uint32_t (&v)[2][32]) {
+                    t2_ld64_pack16(taddr + c * T2_CN, v[0]);
+                    t2_ld64_pack16(taddr + c * T2_CN + 64, v[1]);
                 };
-                if (cols >= T2_TN) chunk(std::false_type{}); else chunk(std::true_type{});
+                for (int j = j0; j < j1; ++j, ++use) {
+                    const int cols = min(T2_TN, nt - j * T2_TN);
+                    uint32_t m1[T2_LISTS], m2[T2_LISTS];
 #pragma unroll
-                for (int l = 1; l < T2_LISTS; ++l) {
-                    const uint32_t hi = __vmaxu2(m1[0], m1[l]);
-                    m1[0] = __vminu2(m1[0], m1[l]);
-                    m2[0] = __vminu2(hi, __vminu2(m2[0], m2[l]));
+                    for (int l = 0; l < T2_LISTS; ++l) m1[l] = m2[l] = 0xFFFFFFFFu;
+                    // columns [0, 64) of a half come from the leader CTA's train rows, [64, 128) from the peer's: register
+                    // i of load g of half c holds tile rows 2 * pl and 2 * pl + 1 with pl = 64 g + 32 c + i
+                    auto arith = [&](const uint32_t (&v)[2][32], auto cc, auto masked) {
+                        constexpr int c = decltype(cc)::value;
+#pragma unroll
+                        for (int g = 0; g < 2; ++g)
+#pragma unroll
+                            for (int i = 0; i < 32; i += 2) {
+                                uint32_t key[2];
+#pragma unroll
+                                for (int u = 0; u < 2; ++u) {
+                                    const uint32_t pl = (uint32_t)(64 * g + 32 * c + i + u);
+                                    key[u] = v[g][i + u] * p.w128 + (pl | (((pl - 0x32u) & 0xFFFFu) << 16));
+                                    if (decltype(masked)::value) {
+                                        if (2 * (int)pl >= cols) key[u] |= 0x0000FFFFu;
+                                        if (2 * (int)pl + 1 >= cols) key[u] |= 0xFFFF0000u;
+                                    }
+                                }
+                                const int l = (i >> 1) & (T2_LISTS - 1);
+                                const uint32_t lo = __vminu2(key[0], key[1]), hi = __vmaxu2(key[0], key[1]);
+                                m2[l] = __vimin3_u16x2(m2[l], hi, __vmaxu2(m1[l], lo));
+                                m1[l] = __vminu2(m1[l], lo);
+                            }
+                    };
+                    // ---- half 0
+                    if (!early0) {
+                        t2_wait(acc_full + h * 2, use & 1);
+                        t2_fence_after();
+                        ld_half(0, va);
+                    }
+                    t2_ld_wait();
+                    t2_fence_before();
+                    __syncwarp();
+                    if (lane == 0) t2_arrive_remote(acc_empty + h * 2, 0);
+                    // half 1 of the same tile is usually complete by now (its MMAs follow half 0's)
+                    const bool early1 = __all_sync(0xffffffffu, t2_try(acc_full + h * 2 + 1, use & 1));
+                    if (early1) {
+                        t2_fence_after();
+                        ld_half(1, vb);
+                    }
+                    if (!(a.ablate & 1)) {
+                        if (cols >= T2_TN) arith(va, std::integral_constant<int, 0>{}, std::false_type{});
+                        else arith(va, std::integral_constant<int, 0>{}, std::true_type{});
+                    }
+                    // ---- half 1
+                    if (!early1) {
+                        t2_wait(acc_full + h * 2 + 1, use & 1);
+                        t2_fence_after();
+                        ld_half(1, vb);
+                    }
+                    t2_ld_wait();
+                    t2_fence_before();
+                    __syncwarp();
+                    if (lane == 0) t2_arrive_remote(acc_empty + h * 2 + 1, 0);
+                    // last tile of the item: every MMA that read this A block is complete -> stage the next item's rows
+                    if (j == j1 - 1) {
+                        int fq2, nq2, qi2;
+                        if (next_live(item, fq2, nq2, qi2)) write_a(fq2, nq2, qi2);
+                    }
+                    // half 0 of the item's next tile, if it is complete already
+                    early0 = false;
+                    if (j + 1 < j1) {
+                        early0 = __all_sync(0xffffffffu, t2_try(acc_full + h * 2, (use + 1) & 1));
+                        if (early0) {
+                            t2_fence_after();
+                            ld_half(0, va);
+                        }
+                    }
+                    if (a.ablate & 1) { g1 = min(g1, va[0][0] ^ vb[1][1]); continue; }
+                    if (cols >= T2_TN) arith(vb, std::integral_constant<int, 1>{}, std::false_type{});
+                    else arith(vb, std::integral_constant<int, 1>{}, std::true_type{});
+#pragma unroll
+                    for (int l = 1; l < T2_LISTS; ++l) {
+                        const uint32_t hi = __vmaxu2(m1[0], m1[l]);
+                        m1[0] = __vminu2(m1[0], m1[l]);
+                        m2[0] = __vminu2(hi, __vminu2(m2[0], m2[l]));
+                    }
+#pragma unroll
+                    for (int w = 0; w < 4; ++w) {
+                        const uint32_t k16 = (((w & 2) ? m2[0] : m1[0]) >> ((w & 1) * 16)) & 0xFFFFu;
+                        if (k16 != 0xFFFFu) {
+                            const uint32_t key = ((k16 >> 7) << TVG_KEY_SHIFT) | (uint32_t)(j * T2_TN + 2 * (k16 & 127u) + (w & 1));
+                            top2_insert(g1, g2, key);
+                        }
+                    }
                 }
+            } else {
+                for (int j = j0; j < j1; ++j, ++use) {
+                    t2_wait(acc_full + h, use & 1);
+                    t2_fence_after();
+                    uint32_t v[T2_CW / 64][32];
+                    uint32_t m1[T2_LISTS], m2[T2_LISTS];
 #pragma unroll
-                for (int w = 0; w < 4; ++w) {
-                    const uint32_t k16 = (((w & 2) ? m2[0] : m1[0]) >> ((w & 1) * 16)) & 0xFFFFu;
-                    if (k16 != 0xFFFFu) {
-                        const uint32_t key = ((k16 >> 7) << TVG_KEY_SHIFT) | (uint32_t)(j * T2_TN + 2 * (k16 & 127u) + (w & 1));
-                        top2_insert(g1, g2, key);
+                    for (int l = 0; l < T2_LISTS; ++l) m1[l] = m2[l] = 0xFFFFFFFFu;
+                    const int cols = min(T2_TN, nt - j * T2_TN);
+                    auto chunk = [&](auto masked, auto c_lo, auto c_hi) {
+#pragma unroll
+                        for (int c = decltype(c_lo)::value; c < decltype(c_hi)::value; ++c)
+#pragma unroll
+                            for (int i = 0; i < 32; i += 2) {
+                                uint32_t key[2];
+#pragma unroll
+                                for (int u = 0; u < 2; ++u) {
+                                    const uint32_t pl = (uint32_t)(sub * (T2_CW / 2) + c * 32 + i + u);
+                                    // accumulator = 1024 + d in f16 = bit pattern 0x6400 | d per 16-bit lane; * 128 + C_p ->
+                                    // (d << 7) | p per lane (the 0x6400 terms overflow into constants that C_p cancels)
+                                    key[u] = v[c][i + u] * p.w128 + (pl | (((pl - 0x32u) & 0xFFFFu) << 16));
+                                    if (decltype(masked)::value) {
+                                        if (2 * (int)pl >= cols) key[u] |= 0x0000FFFFu;
+                                        if (2 * (int)pl + 1 >= cols) key[u] |= 0xFFFF0000u;
+                                    }
+                                }
+                                // two keys per update: 5 min/max (one 3-input) instead of 6
+                                const int l = (i >> 1) & (T2_LISTS - 1);
+                                const uint32_t lo = __vminu2(key[0], key[1]), hi = __vmaxu2(key[0], key[1]);
+                                m2[l] = __vimin3_u16x2(m2[l], hi, __vmaxu2(m1[l], lo));
+                                m1[l] = __vminu2(m1[l], lo);
+                            }
+                    };
+                    constexpr int NLD = T2_CW / 64;              // tensor-memory loads per tile and warp (4)
+                    constexpr int SPL = (T2_SPLIT_LD_N && NLD >= 2) ? T2_SPLIT_LD_N : 0;   // loads whose arithmetic runs before the release
+                    using C0 = std::integral_constant<int, 0>;
+                    using CS = std::integral_constant<int, SPL>;
+                    using CN = std::integral_constant<int, NLD>;
+                    if (SPL > 0) {
+                        // first half of the columns, then the second half's load runs behind the first arithmetic
+#pragma unroll
+                        for (int c = 0; c < T2_FIRST_LD_N; ++c) t2_ld64_pack16(taddr + c * 64, v[c]);
+                        t2_ld_wait();
+#pragma unroll
+                        for (int c = T2_FIRST_LD_N; c < NLD; ++c) t2_ld64_pack16(taddr + c * 64, v[c]);
+                        if (!(a.ablate & 1)) {
+                            if (cols >= T2_TN) chunk(std::false_type{}, C0{}, CS{}); else chunk(std::true_type{}, C0{}, CS{});
+                        }
+                    } else {
+#pragma unroll
+                        for (int c = 0; c < NLD; ++c) t2_ld64_pack16(taddr + c * 64, v[c]);
+                    }
+                    t2_ld_wait();
+                    // the accumulator is in registers now: hand it back to the MMA warp before the (rest of the) arithmetic
+                    t2_fence_before();
+                    __syncwarp();
+                    if (lane == 0) t2_arrive_remote(acc_empty + h, 0);
+                    // last tile of the item: every MMA that read this A block is complete -> stage the next item's rows
+                    if (sub == 0 && j == j1 - 1) {
+                        int fq2, nq2, qi2;
+                        if (next_live(item, fq2, nq2, qi2)) write_a(fq2, nq2, qi2);
+                    }
+                    if (a.ablate & 1) { g1 = min(g1, v[0][0] ^ v[1][1]); continue; }
+                    if (cols >= T2_TN) chunk(std::false_type{}, CS{}, CN{}); else chunk(std::true_type{}, CS{}, CN{});
+    #pragma unroll
+                    for (int l = 1; l < T2_LISTS; ++l) {
+                        const uint32_t hi = __vmaxu2(m1[0], m1[l]);
+                        m1[0] = __vminu2(m1[0], m1[l]);
+                        m2[0] = __vminu2(hi, __vminu2(m2[0], m2[l]));
+                    }
+    #pragma unroll
+                    for (int w = 0; w < 4; ++w) {
+                        const uint32_t k16 = (((w & 2) ? m2[0] : m1[0]) >> ((w & 1) * 16)) & 0xFFFFu;
+                        if (k16 != 0xFFFFu) {
+                            const uint32_t key = ((k16 >> 7) << TVG_KEY_SHIFT) | (uint32_t)(j * T2_TN + 2 * (k16 & 127u) + (w & 1));
+                            top2_insert(g1, g2, key);
+                        }
                     }
                 }
             }

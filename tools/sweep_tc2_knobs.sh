@@ -13,10 +13,18 @@ build() {  # name, -D flags
   nvcc -shared -gencode arch=compute_100a,code=sm_100a -o $OUT/libtvg_$1.so $objs $OUT/$1.o -ldl
   rm $OUT/$1.o
 }
-build base ""
-build lists2 "-DT2_LISTS=2"
-build lists8 "-DT2_LISTS=8"
-build exp2 "-DT2_EXP_WARPS_N=2"
-build exp4 "-DT2_EXP_WARPS_N=4"
-build nst3 "-DT2_NST_N=3"
+if [ "$1" = "epilogue" ]; then   # how the epilogue overlaps its tensor-memory loads with the arithmetic
+  build spl0 "-DT2_SPLIT_LD_N=0"
+  build spl1 "-DT2_SPLIT_LD_N=1"
+  build spl2 "-DT2_SPLIT_LD_N=2"
+  build halves "-DT2_HALVES_N=1"
+  build first1 "-DT2_SPLIT_LD_N=1 -DT2_FIRST_LD_N=1"
+else
+  build base ""
+  build lists2 "-DT2_LISTS=2"
+  build lists8 "-DT2_LISTS=8"
+  build exp2 "-DT2_EXP_WARPS_N=2"
+  build exp4 "-DT2_EXP_WARPS_N=4"
+  build nst3 "-DT2_NST_N=3"
+fi
 ls -la $OUT
