@@ -65,6 +65,9 @@ constexpr int T2_CW = T2_TN / T2_CSPLIT;        // columns per epilogue warp and
 #ifndef T2_FIRST_LD_N
 #define T2_FIRST_LD_N 1                         // 64-column loads waited for before that arithmetic starts (>= T2_SPLIT_LD_N)
 #endif
+#ifndef T2_EARLY_LD_N
+#define T2_EARLY_LD_N 0                         // next tile's first load behind the last quarter of the arithmetic (measured: 0.83 ms against 0.72 -- slower)
+#endif
 constexpr int T2_NC = T2_HALVES_N ? 2 : 1;      // column halves per accumulator
 constexpr int T2_CN = T2_TN / T2_NC;            // MMA N
 static_assert(T2_NC == 1 || T2_CSPLIT == 1, "column halves replace the column split of the epilogue warps");
@@ -494,10 +497,13 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(T2_THREADS, 1) knn2_
                     }
                 }
             } else {
+                uint32_t v[T2_CW / 64][32];
+                bool early = false;      // the first 64 columns of the tile about to be processed are already on their way into v[0]
                 for (int j = j0; j < j1; ++j, ++use) {
-                    t2_wait(acc_full + h, use & 1);
-                    t2_fence_after();
-                    uint32_t v[T2_CW / 64][32];
+                    if (!early) {
+                        t2_wait(acc_full + h, use & 1);
+                        t2_fence_after();
+                    }
                     uint32_t m1[T2_LISTS], m2[T2_LISTS];
 #pragma unroll
                     for (int l = 0; l < T2_LISTS; ++l) m1[l] = m2[l] = 0xFFFFFFFFu;
@@ -533,8 +539,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(T2_THREADS, 1) knn2_
                     using CN = std::integral_constant<int, NLD>;
                     if (SPL > 0) {
                         // first half of the columns, then the second half's load runs behind the first arithmetic
+                        if (!early) {
 #pragma unroll
-                        for (int c = 0; c < T2_FIRST_LD_N; ++c) t2_ld64_pack16(taddr + c * 64, v[c]);
+                            for (int c = 0; c < T2_FIRST_LD_N; ++c) t2_ld64_pack16(taddr + c * 64, v[c]);
+                        }
                         t2_ld_wait();
 #pragma unroll
                         for (int c = T2_FIRST_LD_N; c < NLD; ++c) t2_ld64_pack16(taddr + c * 64, v[c]);
@@ -556,7 +564,22 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(T2_THREADS, 1) knn2_
                         if (next_live(item, fq2, nq2, qi2)) write_a(fq2, nq2, qi2);
                     }
                     if (a.ablate & 1) { g1 = min(g1, v[0][0] ^ v[1][1]); continue; }
-                    if (cols >= T2_TN) chunk(std::false_type{}, CS{}, CN{}); else chunk(std::true_type{}, CS{}, CN{});
+                    constexpr bool EARLY = T2_EARLY_LD_N && SPL == 1 && T2_FIRST_LD_N == 1 && NLD >= 3;
+                    using CL = std::integral_constant<int, EARLY ? NLD - 1 : NLD>;
+                    if (cols >= T2_TN) chunk(std::false_type{}, CS{}, CL{}); else chunk(std::true_type{}, CS{}, CL{});
+                    early = false;
+                    if (EARLY) {
+                        // the item's next tile: if its MMAs are complete already, its first 64 columns load (into v[0],
+                        // consumed above) behind the last quarter of this tile's arithmetic
+                        if (j + 1 < j1) {
+                            early = __all_sync(0xffffffffu, t2_try(acc_full + h, (use + 1) & 1));
+                            if (early) {
+                                t2_fence_after();
+                                t2_ld64_pack16(taddr, v[0]);
+                            }
+                        }
+                        if (cols >= T2_TN) chunk(std::false_type{}, CL{}, CN{}); else chunk(std::true_type{}, CL{}, CN{});
+                    }
     #pragma unroll
                     for (int l = 1; l < T2_LISTS; ++l) {
                         const uint32_t hi = __vmaxu2(m1[0], m1[l]);

@@ -18,7 +18,9 @@ if [ "$1" = "epilogue" ]; then   # how the epilogue overlaps its tensor-memory l
   build spl1 "-DT2_SPLIT_LD_N=1"
   build spl2 "-DT2_SPLIT_LD_N=2"
   build halves "-DT2_HALVES_N=1"
-  build first1 "-DT2_SPLIT_LD_N=1 -DT2_FIRST_LD_N=1"
+  build first2 "-DT2_SPLIT_LD_N=1 -DT2_FIRST_LD_N=2"
+  build early0 "-DT2_EARLY_LD_N=0"
+  build early1 "-DT2_EARLY_LD_N=1"
 else
   build base ""
   build lists2 "-DT2_LISTS=2"
