@@ -25,6 +25,12 @@ namespace tvg {
 
 // ------------------------------------------------------------------------------------ fit
 constexpr int FIT_THREADS = 64;
+#ifndef FIT_MIN_CTAS_N
+#define FIT_MIN_CTAS_N 1
+#endif
+// resident CTAs per SM the register allocation aims at: 1 = no cap (154 registers, 12 warps per SM: 0.133 ms per 1 Mi
+// hypotheses); 8 (128 registers, 16 warps, 46 doubles spilled) measured 0.152 ms
+constexpr int FIT_MIN_CTAS = FIT_MIN_CTAS_N;
 
 __device__ __forceinline__ bool hartley8(const double (&x)[8], const double (&y)[8], double& s, double& cx,
                                          double& cy) {
@@ -46,7 +52,7 @@ __device__ __forceinline__ bool hartley8(const double (&x)[8], const double (&y)
     return isfinite(s);
 }
 
-__global__ void __launch_bounds__(FIT_THREADS) ransac_fit_kernel(const RansacParams p) {
+__global__ void __launch_bounds__(FIT_THREADS, FIT_MIN_CTAS) ransac_fit_kernel(const RansacParams p) {
     const int b = blockIdx.y;
     const int h = blockIdx.x * FIT_THREADS + threadIdx.x;
     if (h >= p.H) return;
