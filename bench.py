@@ -358,6 +358,7 @@ def c5_huge_pair(ops, K, dev, rank, world, local, barrier, reps=5):
     equals_single_rank, info): equals_single_rank compares, on every rank, the G-rank outputs bit for bit with the
     same call on a context without a communicator."""
     import torch
+    import torch.distributed as dist
     from openwork_b200 import _lib, dist as tdist, synth
     lk, ld, ck, cd = synth.make_pair_large(C5_N, 5005)
     words = torch.from_numpy(synth.sample_words(C5_H, 5005).view(np.int32)).to(dev)
@@ -385,12 +386,25 @@ def c5_huge_pair(ops, K, dev, rank, world, local, barrier, reps=5):
     launches = (ctx.launches - l0) // reps
     ctx.set_profile(True)
     acc = None
+    xacc = [0.0, 0.0]
     for _ in range(3):
+        barrier()                                        # ranks enter together: what is left in the exchanges is theirs
         out = run(ctx, out)
         sm = ctx.stage_ms()
         acc = sm if acc is None else {k: acc[k] + v for k, v in sm.items()}
+        x1, x2 = ctx.exchange_ms()
+        xacc = [xacc[0] + x1, xacc[1] + x2]
     ctx.set_profile(False)
     stage = {k: v / 3 for k, v in acc.items()}
+    # the two exchange steps on this rank (each includes waiting for the slowest rank): min / max over the ranks
+    xt = torch.tensor([xacc[0] / 3, xacc[1] / 3, -xacc[0] / 3, -xacc[1] / 3], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(xt, op=dist.ReduceOp.MAX)
+    xt = [float(v) for v in xt.cpu()]
+    exchange_ms = {"matcher_outputs_allgather": {"max_over_ranks": xt[0], "min_over_ranks": -xt[2]},
+                   "best_records_allgather": {"max_over_ranks": xt[1], "min_over_ranks": -xt[3]},
+                   "note": "CUDA events around the NCCL calls on every rank, ranks released by a barrier; a rank's time "
+                           "includes waiting for the slowest rank, so the minimum is the transfer itself"}
     M, n_in = int(out["m_count"].item()), int(out["n_inl"].item())
     same = None
     if world > 1:
@@ -406,7 +420,7 @@ def c5_huge_pair(ops, K, dev, rank, world, local, barrier, reps=5):
         solo.close()
     info = {"kpts": C5_N, "hypotheses": C5_H, "matches": M, "inliers": n_in, "best": int(out["best"].item()),
             "status": int(out["status"].item()), "launches_per_pair": int(launches),
-            "collectives_per_pair": 2 if world > 1 else 0,
+            "collectives_per_pair": 2 if world > 1 else 0, "exchange_ms": exchange_ms,
             "exchange": "all-gather of idx/dist/keep blocks (17 B per query row) + all-gather of one 96-byte record per rank"}
     return ms, stage, same, info
 

@@ -361,6 +361,10 @@ typedef struct tvg_huge_pair_io {
     int32_t* status;     /* [1] */
 } tvg_huge_pair_io;
 TVG_API int tvg_huge_pair(tvg_ctx* ctx, const tvg_huge_pair_io* io, void* stream);
+/* With profiling on (tvg_set_profile): durations in ms of the two exchange steps of the last tvg_huge_pair call on THIS
+ * rank -- ms[0] = the all-gather of the matcher outputs, ms[1] = the all-gather of the best records.  Each includes the
+ * wait for the slowest rank to arrive; the minimum over the ranks is the transfer itself. */
+TVG_API int tvg_get_exchange_ms(tvg_ctx* ctx, float* ms);
 
 #ifdef __cplusplus
 }

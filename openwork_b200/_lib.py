@@ -96,6 +96,7 @@ SIGNATURES = {
     "tvg_set_score_config": (C.c_int, [c_vp, C.c_int, C.c_int]),
     "tvg_set_profile": (C.c_int, [c_vp, C.c_int]),
     "tvg_get_stage_ms": (C.c_int, [c_vp, c_f32p, C.c_int]),
+    "tvg_get_exchange_ms": (C.c_int, [c_vp, c_f32p]),
     "tvg_pairs_host": (C.c_int, [c_vp, C.POINTER(PairsIO), C.c_int, C.POINTER(C.c_longlong),
                                  C.POINTER(C.c_longlong), c_vp]),
     "tvg_pairs_host_submit": (C.c_int, [c_vp, C.POINTER(PairsIO), C.c_int, C.POINTER(C.c_longlong),
@@ -190,6 +191,13 @@ class Context:
         buf = (C.c_float * 9)()
         check(self.lib.tvg_get_stage_ms(self.handle, buf, 9), "tvg_get_stage_ms")
         return dict(zip(self.STAGES, [float(v) for v in buf]))
+
+    def exchange_ms(self):
+        """(exchange 1, exchange 2) durations in ms of the last profiled tvg_huge_pair call on this rank; each includes
+        the wait for the slowest rank."""
+        buf = (C.c_float * 2)()
+        check(self.lib.tvg_get_exchange_ms(self.handle, buf), "tvg_get_exchange_ms")
+        return float(buf[0]), float(buf[1])
 
     def set_matcher_l2_budget(self, nbytes=0):
         check(self.lib.tvg_set_matcher_l2_budget(self.handle, int(nbytes)), "tvg_set_matcher_l2_budget")

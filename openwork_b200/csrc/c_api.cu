@@ -73,6 +73,8 @@ void tvg_ctx_destroy(tvg_ctx* ctx) {
     if (ctx->done_event) cudaEventDestroy(ctx->done_event);
     for (int i = 0; i < TVG_PROF_MARKS; ++i)
         if (ctx->prof[i]) cudaEventDestroy(ctx->prof[i]);
+    for (int i = 0; i < 4; ++i)
+        if (ctx->xprof[i]) cudaEventDestroy(ctx->xprof[i]);
     delete ctx;
 }
 

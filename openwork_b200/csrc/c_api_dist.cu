@@ -186,6 +186,7 @@ int tvg_huge_pair(tvg_ctx* ctx, const tvg_huge_pair_io* io, void* stream) {
     }
     // 2. exchange step 1: fixed-size all-gather of the matcher outputs (rank order == ascending query order); no
     //    size exchange, no host synchronisation.  One NCCL group = one launch.
+    if ((rc = ctx->xmark(0, st))) return rc;
     if (world > 1) {
         TVG_NCCL(a->GroupStart());
         TVG_NCCL(a->AllGather(idx + (size_t)rank * per * 2, idx, (size_t)per * 2, ncclInt32, ctx->comm->comm, st));
@@ -195,6 +196,7 @@ int tvg_huge_pair(tvg_ctx* ctx, const tvg_huge_pair_io* io, void* stream) {
         ctx->launches += 1;
     }
     // 3. ratio compaction + gathers + K-normalisation over ALL query rows, on every rank (identical results)
+    if ((rc = ctx->xmark(1, st))) return rc;
     if ((rc = ctx->mark(1, st))) return rc;
     rc = tvg_ratio_compact(ctx, keep, idx, 1, n_max, io->nq, nullptr, nullptr, nullptr, io->curr_kps, io->last_kps, io->kinv,
                            qidx, tidx, m_count, src, dst, corr32, stream);
@@ -221,10 +223,12 @@ int tvg_huge_pair(tvg_ctx* ctx, const tvg_huge_pair_io* io, void* stream) {
     // 5. exchange step 2: ONE all-gather of the ranks' 96-byte records {count, hypothesis, exact sum r^2, E}; every
     //    rank then applies the reference's selection rule (most inliers, smallest sum r^2, earliest trial) to the
     //    same list -- exact fp64 keys, so G ranks pick what one rank picks.
+    if ((rc = ctx->xmark(2, st))) return rc;
     if (world > 1) {
         TVG_NCCL(a->AllGather(recs + rank, recs, sizeof(tvg::BestRec), ncclUint8, ctx->comm->comm, st));
         ctx->launches += 1;
     }
+    if ((rc = ctx->xmark(3, st))) return rc;
     TVG_CUDA(tvg::launch_ransac_merge_records(run.p, recs, world, st));
     ctx->launches += 1;
     // 6. mask, refit, extract_Rt on every rank (identical), then pose and triangulation of the inliers
@@ -245,6 +249,17 @@ int tvg_huge_pair(tvg_ctx* ctx, const tvg_huge_pair_io* io, void* stream) {
                          stream);
     if (rc) return rc;
     return ctx->mark(9, st);
+}
+
+int tvg_get_exchange_ms(tvg_ctx* ctx, float* ms) {
+    if (!ctx || !ms) return fail(-1, "ctx / ms is NULL");
+    for (int i = 0; i < 4; ++i)
+        if (!ctx->xprof[i]) return fail(-5, "tvg_get_exchange_ms: no profiled tvg_huge_pair call yet");
+    DeviceGuard g(ctx->device);
+    TVG_CUDA(cudaEventSynchronize(ctx->xprof[3]));
+    TVG_CUDA(cudaEventElapsedTime(&ms[0], ctx->xprof[0], ctx->xprof[1]));
+    TVG_CUDA(cudaEventElapsedTime(&ms[1], ctx->xprof[2], ctx->xprof[3]));
+    return 0;
 }
 
 }  // extern "C"

@@ -60,6 +60,16 @@ struct tvg_ctx {
     // optional stage timing of tvg_pairs_device (tvg_set_profile): events at the stage boundaries
     bool profile = false;
     cudaEvent_t prof[TVG_PROF_MARKS] = {};
+    cudaEvent_t xprof[4] = {};   // tvg_huge_pair: start / end of exchange 1 and of exchange 2 (same profiling switch)
+    int xmark(int i, cudaStream_t st) {
+        if (!profile) return 0;
+        if (!xprof[i]) {
+            cudaError_t e = cudaEventCreate(&xprof[i]);
+            if (e != cudaSuccess) return cuda_fail(e, "cudaEventCreate");
+        }
+        cudaError_t e = cudaEventRecord(xprof[i], st);
+        return e == cudaSuccess ? 0 : cuda_fail(e, "cudaEventRecord");
+    }
     int mark(int i, cudaStream_t st) {
         if (!profile) return 0;
         if (!prof[i]) {
