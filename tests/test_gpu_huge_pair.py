@@ -90,6 +90,28 @@ def test_too_few_matches_reports_status_1(ops):
     assert np.isnan(o["E"]).all()
 
 
+def test_stage_and_exchange_timers_of_a_profiled_call(ops):
+    """tvg_set_profile + tvg_get_stage_ms / tvg_get_exchange_ms after tvg_huge_pair: nine stage times and the two
+    exchange times (near zero on one rank: nothing is exchanged), an error before any profiled call."""
+    from openwork_b200 import _lib
+    lk, ld, ck, cd = synth.make_pair(1500, 9)
+    ctx = _lib.Context(0)
+    try:
+        with pytest.raises(_lib.TvgError):
+            ctx.exchange_ms()
+        ctx.set_profile(True)
+        o = ops.huge_pair(ck, cd, lk, ld, K, words=synth.sample_words(256, 9), ctx=ctx)
+        st = ctx.stage_ms()
+        x1, x2 = ctx.exchange_ms()
+        ctx.set_profile(False)
+        assert int(o["status"][0]) == 0
+        assert set(st) == set(_lib.Context.STAGES) and all(np.isfinite(v) and v >= 0 for v in st.values())
+        assert st["score"] > 0 and st["knn2"] > 0
+        assert 0 <= x1 < 1.0 and 0 <= x2 < 1.0
+    finally:
+        ctx.close()
+
+
 def _check_c5_against_oracle(o, lk, ld, ck, cd, words, n_sub=48, seed=0):
     """Oracle checks that stay cheap at C5 size (used by the one-rank test and the multi-rank worker)."""
     n, H = len(cd), len(words)
